@@ -1,0 +1,308 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU restatement of geograypher's multiview-projection hot path.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
+import this module; ``geograypher_b200`` never does.
+
+Two halves:
+
+* visibility (``pix2face``): C restatement in ``oracle_raster.c`` (see its header for the contract and for
+  why sub-pixel parity with VTK / PyTorch3D is UNPINNED), called through ctypes here;
+* everything after visibility -- ``project_images``, ``aggregate_projected_images``, the one-hot-vote
+  variant, ``render_flat``'s gather, ``save_renders``' uint8 cast, ``inds_to_one_hot`` and
+  ``find_argmax_nonzero_value`` -- is in-repo NumPy in the reference and is restated literally below.  These
+  restatements are PINNED: ``tests/golden/make_golden.py`` runs the reference's own code (imported from
+  /root/reference with its missing third-party imports stubbed) on the same inputs and
+  ``tests/test_oracle_golden.py`` checks equality.
+
+All ``file:line`` citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+SUBPIX = 256
+DEFAULT_ZNEAR = 1e-3
+
+
+class OraCamera(ctypes.Structure):
+    _fields_ = [
+        ("m", ctypes.c_float * 12),
+        ("f", ctypes.c_float),
+        ("px", ctypes.c_float),
+        ("py", ctypes.c_float),
+        ("W", ctypes.c_int32),
+        ("H", ctypes.c_int32),
+        ("znear", ctypes.c_float),
+    ]
+
+
+def build(force: bool = False) -> Path:
+    """Compile oracle_raster.c with the committed Makefile (gcc, -ffp-contract=off, OpenMP)."""
+    so = _HERE / "liboracle_raster.so"
+    src = _HERE / "oracle_raster.c"
+    if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "-B"], check=True, capture_output=True)
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        so = build()
+        lib = ctypes.CDLL(str(so))
+        lib.ora_project.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(OraCamera)] + [
+            ctypes.c_void_p
+        ] * 4
+        lib.ora_project.restype = None
+        lib.ora_rasterize.argtypes = [
+            ctypes.c_void_p,
+            ctypes.c_int64,
+            ctypes.c_void_p,
+            ctypes.c_int64,
+            ctypes.POINTER(OraCamera),
+            ctypes.c_void_p,
+            ctypes.c_void_p,
+            ctypes.c_void_p,
+            ctypes.c_int,
+        ]
+        lib.ora_rasterize.restype = None
+        lib.ora_num_threads.restype = ctypes.c_int
+        _LIB = lib
+    return _LIB
+
+
+def num_threads() -> int:
+    return int(_lib().ora_num_threads())
+
+
+# --------------------------------------------------------------------------------------------------
+# Camera model (cameras/cameras.py:56-102, 136-152, 179-200; derived_meshes.py:739-794)
+# --------------------------------------------------------------------------------------------------
+def scaled_image_size(image_height: int, image_width: int, image_scale: float = 1.0):
+    """(h, w) = (int(H*s), int(W*s)) -- cameras/cameras.py:197-200."""
+    return int(image_height * image_scale), int(image_width * image_scale)
+
+
+def make_camera(
+    cam_to_world,
+    f,
+    cx,
+    cy,
+    image_width,
+    image_height,
+    render_img_scale=1.0,
+    origin=None,
+    znear=DEFAULT_ZNEAR,
+):
+    """Float32 camera record of the rasterization contract from geograypher camera parameters.
+
+    world_to_cam = inv(cam_to_world) (cameras.py:84); pinhole with the principal point measured from the
+    image centre (cameras.py:75-76, derived_meshes.py:772-780).  ``render_img_scale`` keeps the vertical
+    field of view like the pyvista path does (cameras.py:472, meshes.py:1801, 1820-1822):
+    f' = f*h'/H, principal point (w'/2 + cx*h'/H, h'/2 + cy*h'/H).  ``origin`` is the float64 point that was
+    subtracted from the mesh vertices before they were rounded to float32; it is folded into the
+    translation in float64.
+    """
+    c2w = np.asarray(cam_to_world, dtype=np.float64)
+    w2c = np.linalg.inv(c2w)
+    m = w2c[:3, :4].copy()
+    if origin is not None:
+        m[:, 3] = m[:, 3] + m[:, :3] @ np.asarray(origin, dtype=np.float64)
+    h, w = scaled_image_size(image_height, image_width, render_img_scale)
+    s = h / float(image_height)
+    cam = OraCamera()
+    m32 = m.astype(np.float32).reshape(-1)
+    for k in range(12):
+        cam.m[k] = float(m32[k])
+    cam.f = np.float32(f * s)
+    cam.px = np.float32(w / 2.0 + cx * s)
+    cam.py = np.float32(h / 2.0 + cy * s)
+    cam.W = w
+    cam.H = h
+    cam.znear = np.float32(znear)
+    return cam
+
+
+def camera_to_array(cam: OraCamera) -> np.ndarray:
+    """(18,) float32 view [m0..m11, f, px, py, W, H, znear] -- handy for tests that feed the same camera
+    to the CUDA library."""
+    return np.array(
+        list(cam.m) + [cam.f, cam.px, cam.py, float(cam.W), float(cam.H), cam.znear],
+        dtype=np.float32,
+    )
+
+
+# --------------------------------------------------------------------------------------------------
+# Visibility
+# --------------------------------------------------------------------------------------------------
+def project(verts32: np.ndarray, cam: OraCamera):
+    """Stage 1 of the contract: returns (X, Y) int32 fixed point (1/256 px), invz float32, valid bool."""
+    verts32 = np.ascontiguousarray(verts32, dtype=np.float32)
+    V = verts32.shape[0]
+    X = np.empty(V, np.int32)
+    Y = np.empty(V, np.int32)
+    invz = np.empty(V, np.float32)
+    valid = np.empty(V, np.uint8)
+    _lib().ora_project(
+        verts32.ctypes.data, V, ctypes.byref(cam), X.ctypes.data, Y.ctypes.data, invz.ctypes.data,
+        valid.ctypes.data,
+    )
+    return X, Y, invz, valid.astype(bool)
+
+
+def rasterize(verts32, faces, cam: OraCamera, want_depth=False, want_margin=False, nthreads=0):
+    """pix2face for one view: (H, W) int64 face IDs, -1 where no face (meshes.py:1712-1718).
+
+    Returns ``pix2face`` or ``(pix2face, depth_w, margin)`` (None for the parts not requested).
+    """
+    verts32 = np.ascontiguousarray(verts32, dtype=np.float32)
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    H, W = int(cam.H), int(cam.W)
+    out = np.empty((H, W), np.int32)
+    depth = np.empty((H, W), np.float64) if want_depth else None
+    margin = np.empty((H, W), np.float64) if want_margin else None
+    _lib().ora_rasterize(
+        verts32.ctypes.data,
+        verts32.shape[0],
+        faces.ctypes.data,
+        faces.shape[0],
+        ctypes.byref(cam),
+        out.ctypes.data,
+        depth.ctypes.data if depth is not None else None,
+        margin.ctypes.data if margin is not None else None,
+        int(nthreads),
+    )
+    p2f = out.astype(np.int64)
+    if want_depth or want_margin:
+        return p2f, depth, margin
+    return p2f
+
+
+# --------------------------------------------------------------------------------------------------
+# After visibility: literal NumPy of the reference
+# --------------------------------------------------------------------------------------------------
+def inds_to_one_hot(inds_image, num_classes, ignore_ind=255):
+    """predictors/segmentor.py:37-69 -- (h, w) indices -> (h, w, C) bool; ignore / out-of-range -> all False."""
+    del ignore_ind  # the reference computes but never uses it once num_classes is given (:53-57)
+    one_hot = np.zeros(inds_image.shape[:2] + (num_classes,), dtype=bool)
+    for i in range(num_classes):
+        one_hot[..., i] = inds_image == i
+    return one_hot
+
+
+def project_image(pix2face, img, n_faces, compat_negative_index=True):
+    """One iteration of project_images, meshes.py:1988-2002.
+
+    NumPy fancy assignment: for a face hit by several pixels the LAST pixel in row-major order wins.
+    With ``compat_negative_index`` (the reference's behaviour, TODO at meshes.py:2000) background pixels
+    (-1) index face n_faces-1; without it they are skipped.
+    """
+    n_channels = 1 if img.ndim == 2 else img.shape[-1]
+    textured_faces = np.full((n_faces, n_channels), fill_value=np.nan)
+    flat_img = np.reshape(img, (img.shape[0] * img.shape[1], -1))
+    flat_p2f = pix2face.flatten()
+    if compat_negative_index:
+        textured_faces[flat_p2f] = flat_img
+    else:
+        keep = flat_p2f >= 0
+        textured_faces[flat_p2f[keep]] = flat_img[keep]
+    return textured_faces
+
+
+def aggregate(pix2faces, images, n_faces, compat_negative_index=True, check_null_image=False):
+    """aggregate_projected_images, meshes.py:2046-2084 (sum over views with NaN -> 0, count of views that
+    saw a face, mean).  Returns (average, projection_counts, summed_projection)."""
+    counts = np.zeros(n_faces)
+    summed = None
+    for p2f, img in zip(pix2faces, images):
+        if check_null_image and not np.any(np.isfinite(img)):
+            n_channels = 1 if img.ndim == 2 else img.shape[-1]
+            proj = np.full((n_faces, n_channels), np.nan)
+        else:
+            proj = project_image(p2f, img, n_faces, compat_negative_index)
+        if summed is None:
+            summed = proj.astype(float)
+        else:
+            summed = np.nansum([summed, proj], axis=0)
+        counts += np.any(np.isfinite(proj), axis=1).astype(int)
+    summed[counts == 0] = np.nan
+    with np.errstate(invalid="ignore", divide="ignore"):
+        average = np.divide(summed, np.expand_dims(counts, 1))
+    return average, counts, summed
+
+
+def aggregate_votes(pix2faces, index_images, n_faces, n_classes, compat_negative_index=True):
+    """TexturedPhotogrammetryMeshIndexPredictions.aggregate_projected_images, derived_meshes.py:415-550,
+    with dense int arrays instead of scipy CSR: every face whose winning pixel holds a finite class index
+    votes once for that class.  Returns (average, counts (F,), summed (F, n_classes))."""
+    counts = np.zeros(n_faces, dtype=np.int64)
+    summed = np.zeros((n_faces, n_classes), dtype=np.int64)
+    for p2f, img in zip(pix2faces, index_images):
+        if not np.any(np.isfinite(img)):  # check_null_image=True, meshes.py:1995
+            continue
+        proj = project_image(p2f, img, n_faces, compat_negative_index)
+        idx = np.nonzero(np.isfinite(np.squeeze(proj, axis=1)))[0]
+        if len(idx) == 0:
+            continue
+        counts[idx] += 1
+        cls = proj[idx, 0].astype(int)
+        summed[idx, cls] += 1
+    average = np.zeros((n_faces, n_classes))
+    seen = counts > 0
+    average[seen] = summed[seen] * np.reciprocal(counts[seen].astype(float))[:, None]
+    return average, counts, summed
+
+
+def render_flat_gather(pix2face, face_texture):
+    """Per-view body of render_flat, meshes.py:1921-1937: NaN where pix2face == -1."""
+    face_texture = np.asarray(face_texture, dtype=float)
+    if face_texture.ndim == 1:
+        face_texture = face_texture[:, None]
+    img_shape = pix2face.shape[:2]
+    flat = pix2face.flatten()
+    inds = np.where(flat != -1)[0]
+    out = np.full((flat.shape[0], face_texture.shape[1]), fill_value=np.nan)
+    out[inds] = face_texture[flat[inds]]
+    return out.reshape(img_shape + (face_texture.shape[1],))
+
+
+def cast_render_to_uint8(rendered, null_value=0):
+    """save_renders' cast rule, meshes.py:2323-2334 (NULL_TEXTURE_INT_VALUE = 0, constants.py:27)."""
+    rendered = np.array(rendered, dtype=float, copy=True)
+    with np.errstate(invalid="ignore"):
+        mask = np.logical_or.reduce(
+            [rendered < 0, rendered > 255, np.logical_not(np.isfinite(rendered))]
+        )
+    rendered[mask] = null_value
+    return np.squeeze(rendered.astype(np.uint8))
+
+
+def vert_to_face_texture_mean(vertex_texture, faces):
+    """Non-discrete branch of vert_to_face_texture, meshes.py:985-987: mean of the 3 vertex rows."""
+    return np.mean(np.asarray(vertex_texture, dtype=float)[faces], axis=1)
+
+
+def find_argmax_nonzero_value(array, keepdims=False, axis=1):
+    """utils/indexing.py:9-32."""
+    argmax = np.argmax(array, axis=axis, keepdims=keepdims).astype(float)
+    zero_sum_mask = np.sum(array, axis=axis) == 0
+    infinite_mask = np.any(~np.isfinite(array), axis=axis)
+    argmax[np.logical_or(zero_sum_mask, infinite_mask)] = np.nan
+    return argmax
+
+
+# --------------------------------------------------------------------------------------------------
+# Whole path, for bench.py's CPU baseline and for tests
+# --------------------------------------------------------------------------------------------------
+def pix2face_set(verts32, faces, cams, nthreads=0):
+    """(n, H, W) int64 -- meshes.py:1735-1749 (per-camera recursion + np.stack)."""
+    return np.stack([rasterize(verts32, faces, c, nthreads=nthreads) for c in cams], axis=0)

@@ -1,0 +1,245 @@
+/*
+ * oracle/oracle_raster.c  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement of the visibility ("pix2face") step of geograypher's multiview
+ * projection path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the product path never does.
+ *
+ * What it restates (file:line under /root/reference):
+ *   - TexturedPhotogrammetryMesh.pix2face            geograypher/meshes/meshes.py:1678-1856
+ *     "for each pixel, the ID of the nearest mesh face along the ray, -1 if none".
+ *   - the pinhole model of the PyTorch3D back-end    geograypher/meshes/derived_meshes.py:739-794
+ *     x = f*Xc/Zc + W/2 + cx ,  y = f*Yc/Zc + H/2 + cy   (camera frame +X right, +Y down, +Z fwd;
+ *     geograypher/cameras/cameras.py:446-477 uses the same frame: up = -Y, look = +Z).
+ *   - float32 vertex / camera data inside the rasterizer (derived_meshes.py:631, 761-764).
+ *
+ * The arithmetic of the rasterization itself lives in un-vendored third-party code
+ * (VTK 9.2.6 OpenGL through pyvista 0.42.2, poetry.lock; or PyTorch3D MeshRasterizer), which is
+ * absent from /root/reference and cannot be run in the build container.  PARITY UNPINNED at the
+ * sub-pixel level: this file restates the published algorithm both share (sample at pixel
+ * centres, nearest positive depth wins) and fixes the unspecified parts in an explicit
+ * contract (DESIGN.md "Rasterization contract"):
+ *   C1  projection in IEEE float32, round-to-nearest, fixed operation order, no FMA contraction
+ *   C2  screen coordinates snapped to 1/256 px fixed point (GPU-style 8 sub-pixel bits)
+ *   C3  coverage = exact integer edge functions, pixel centre (j+0.5, i+0.5), top-left fill rule
+ *   C4  depth = 1/z_cam interpolated linearly in screen space (perspective-correct), nearest wins,
+ *       exact ties -> lowest face ID
+ *   C5  a face with any vertex at z_cam < znear (or non-finite) is dropped
+ * It is pinned against the reference's own known-answer tests for this path
+ * (tests/test_derived_meshes.py:23-76, tests/test_derived_cameras.py:339-415) in
+ * tests/test_oracle_reference_pins.py.
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC).
+ * -ffp-contract=off is REQUIRED: contract C1 forbids fused multiply-add in the projection.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORA_SUBPIX 256
+#define ORA_HALF 128
+#define ORA_CLAMP 536870912.0f /* 2^29 sub-pixel units */
+
+typedef struct {
+    float m[12];  /* world_to_cam rows 0..2, row-major 3x4 */
+    float f;      /* focal length, pixels (already scaled for render_img_scale) */
+    float px, py; /* principal point in pixels: W/2 + cx, H/2 + cy */
+    int32_t W, H; /* raster size */
+    float znear;  /* contract C5 */
+} ora_camera;
+
+/* Contract C1+C2 for one vertex.  volatile-free: relies on -ffp-contract=off and SSE float math. */
+static inline int project_vertex(const float *v, const ora_camera *c, int32_t *X, int32_t *Y,
+                                 float *invz) {
+    const float x = v[0], y = v[1], z = v[2];
+    const float *m = c->m;
+    float t;
+    t = m[0] * x;
+    t = t + m[1] * y;
+    t = t + m[2] * z;
+    const float xc = t + m[3];
+    t = m[4] * x;
+    t = t + m[5] * y;
+    t = t + m[6] * z;
+    const float yc = t + m[7];
+    t = m[8] * x;
+    t = t + m[9] * y;
+    t = t + m[10] * z;
+    const float zc = t + m[11];
+    if (!(zc >= c->znear) || !isfinite(xc) || !isfinite(yc) || !isfinite(zc)) {
+        *X = 0;
+        *Y = 0;
+        *invz = 0.0f;
+        return 0;
+    }
+    float sx = (c->f * xc) / zc + c->px;
+    float sy = (c->f * yc) / zc + c->py;
+    float fx = nearbyintf(sx * (float)ORA_SUBPIX); /* round-half-even */
+    float fy = nearbyintf(sy * (float)ORA_SUBPIX);
+    if (!isfinite(fx) || !isfinite(fy)) {
+        *X = 0;
+        *Y = 0;
+        *invz = 0.0f;
+        return 0;
+    }
+    if (fx > ORA_CLAMP) fx = ORA_CLAMP;
+    if (fx < -ORA_CLAMP) fx = -ORA_CLAMP;
+    if (fy > ORA_CLAMP) fy = ORA_CLAMP;
+    if (fy < -ORA_CLAMP) fy = -ORA_CLAMP;
+    *X = (int32_t)fx;
+    *Y = (int32_t)fy;
+    *invz = 1.0f / zc;
+    return 1;
+}
+
+/* Stage 1 on its own: project every vertex (used to check the CUDA projection bit for bit). */
+void ora_project(const float *verts, int64_t V, const ora_camera *cam, int32_t *X, int32_t *Y,
+                 float *invz, uint8_t *valid) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < V; ++i) {
+        valid[i] = (uint8_t)project_vertex(verts + 3 * i, cam, X + i, Y + i, invz + i);
+    }
+}
+
+static inline int64_t floordiv(int64_t a, int64_t b) {
+    int64_t q = a / b, r = a % b;
+    return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+
+/* Contract C3 tie rule: a sample exactly on an edge (E == 0) belongs to the triangle iff the edge is a
+ * "left" edge (A > 0: interior lies towards +x) or a "top" edge (A == 0 and B > 0: horizontal edge with
+ * the interior towards +y, i.e. below it on a y-down screen).  (A,B) = gradient of E. */
+static inline int edge_inclusive(int64_t A, int64_t B) { return (A > 0) || (A == 0 && B > 0); }
+
+/*
+ * Rasterize one view.
+ *   pix2face : H*W int32, -1 = no face                                  (required)
+ *   depth_w  : H*W double, best 1/z_cam (0 where no face)               (optional)
+ *   margin   : H*W double, (w_best - w_second)/w_best, 1 if no runner-up (optional; contract: a pixel is
+ *              "depth-safe" iff margin > eps_depth)
+ * Faces are visited in increasing ID inside every row band, so "strictly nearer replaces" realises the
+ * lowest-ID tie-break of C4.
+ */
+void ora_rasterize(const float *verts, int64_t V, const int32_t *faces, int64_t F, const ora_camera *cam,
+                   int32_t *pix2face, double *depth_w, double *margin, int nthreads) {
+    const int W = cam->W, H = cam->H;
+    int32_t *X = (int32_t *)malloc(sizeof(int32_t) * (size_t)V);
+    int32_t *Y = (int32_t *)malloc(sizeof(int32_t) * (size_t)V);
+    float *IZ = (float *)malloc(sizeof(float) * (size_t)V);
+    uint8_t *OK = (uint8_t *)malloc((size_t)V);
+    ora_project(verts, V, cam, X, Y, IZ, OK);
+
+    const size_t P = (size_t)W * (size_t)H;
+    double *wbest = (double *)malloc(sizeof(double) * P);
+    double *wsecond = margin ? (double *)malloc(sizeof(double) * P) : NULL;
+    for (size_t p = 0; p < P; ++p) {
+        pix2face[p] = -1;
+        wbest[p] = 0.0;
+    }
+    if (wsecond) memset(wsecond, 0, sizeof(double) * P);
+
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    int nbands = nthreads * 4;
+    if (nbands > H) nbands = H;
+    if (nbands < 1) nbands = 1;
+
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int band = 0; band < nbands; ++band) {
+        const int r0 = (int)((int64_t)H * band / nbands);
+        const int r1 = (int)((int64_t)H * (band + 1) / nbands);
+        for (int64_t fi = 0; fi < F; ++fi) {
+            const int32_t i0 = faces[3 * fi], i1 = faces[3 * fi + 1], i2 = faces[3 * fi + 2];
+            if (i0 < 0 || i1 < 0 || i2 < 0 || i0 >= V || i1 >= V || i2 >= V) continue;
+            if (!(OK[i0] && OK[i1] && OK[i2])) continue; /* C5 */
+            int64_t x0 = X[i0], y0 = Y[i0], x1 = X[i1], y1 = Y[i1], x2 = X[i2], y2 = Y[i2];
+            double w0 = IZ[i0], w1 = IZ[i1], w2 = IZ[i2];
+            /* bounding box in fixed point -> pixel-centre index range */
+            int64_t xmin = x0 < x1 ? x0 : x1;
+            if (x2 < xmin) xmin = x2;
+            int64_t xmax = x0 > x1 ? x0 : x1;
+            if (x2 > xmax) xmax = x2;
+            int64_t ymin = y0 < y1 ? y0 : y1;
+            if (y2 < ymin) ymin = y2;
+            int64_t ymax = y0 > y1 ? y0 : y1;
+            if (y2 > ymax) ymax = y2;
+            /* centres c = 256*j + 128 with xmin <= c <= xmax */
+            int64_t jmin = floordiv(xmin - ORA_HALF + ORA_SUBPIX - 1, ORA_SUBPIX); /* ceil */
+            int64_t jmax = floordiv(xmax - ORA_HALF, ORA_SUBPIX);
+            int64_t imin = floordiv(ymin - ORA_HALF + ORA_SUBPIX - 1, ORA_SUBPIX);
+            int64_t imax = floordiv(ymax - ORA_HALF, ORA_SUBPIX);
+            if (jmin < 0) jmin = 0;
+            if (jmax > W - 1) jmax = W - 1;
+            if (imin < r0) imin = r0;
+            if (imax > r1 - 1) imax = r1 - 1;
+            if (jmin > jmax || imin > imax) continue;
+            int64_t area2 = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+            if (area2 == 0) continue;
+            if (area2 < 0) { /* make the interior the positive side */
+                int64_t tx = x1, ty = y1;
+                double tw = w1;
+                x1 = x2;
+                y1 = y2;
+                w1 = w2;
+                x2 = tx;
+                y2 = ty;
+                w2 = tw;
+                area2 = -area2;
+            }
+            /* E_k(P) = A_k*Px + B_k*Py + C_k ; edge k runs v_k -> v_{k+1} */
+            const int64_t A0 = -(y1 - y0), B0 = (x1 - x0);
+            const int64_t A1 = -(y2 - y1), B1 = (x2 - x1);
+            const int64_t A2 = -(y0 - y2), B2 = (x0 - x2);
+            const int inc0 = edge_inclusive(A0, B0), inc1 = edge_inclusive(A1, B1),
+                      inc2 = edge_inclusive(A2, B2);
+            const double inv_area = 1.0 / (double)area2;
+            for (int64_t i = imin; i <= imax; ++i) {
+                const int64_t Py = ORA_SUBPIX * i + ORA_HALF;
+                for (int64_t j = jmin; j <= jmax; ++j) {
+                    const int64_t Px = ORA_SUBPIX * j + ORA_HALF;
+                    const int64_t E0 = B0 * (Py - y0) + A0 * (Px - x0);
+                    const int64_t E1 = B1 * (Py - y1) + A1 * (Px - x1);
+                    const int64_t E2 = B2 * (Py - y2) + A2 * (Px - x2);
+                    if (E0 < 0 || E1 < 0 || E2 < 0) continue;
+                    if ((E0 == 0 && !inc0) || (E1 == 0 && !inc1) || (E2 == 0 && !inc2)) continue;
+                    /* barycentric weights: E1 -> v0, E2 -> v1, E0 -> v2 */
+                    const double w = ((double)E1 * w0 + (double)E2 * w1 + (double)E0 * w2) * inv_area;
+                    const size_t p = (size_t)i * (size_t)W + (size_t)j;
+                    if (w > wbest[p]) {
+                        if (wsecond) wsecond[p] = wbest[p];
+                        wbest[p] = w;
+                        pix2face[p] = (int32_t)fi;
+                    } else if (wsecond && w > wsecond[p]) {
+                        wsecond[p] = w;
+                    }
+                }
+            }
+        }
+    }
+    if (depth_w) memcpy(depth_w, wbest, sizeof(double) * P);
+    if (margin) {
+        for (size_t p = 0; p < P; ++p)
+            margin[p] = (pix2face[p] >= 0) ? (wbest[p] - wsecond[p]) / wbest[p] : 1.0;
+    }
+    free(wbest);
+    if (wsecond) free(wsecond);
+    free(X);
+    free(Y);
+    free(IZ);
+    free(OK);
+}
+
+int ora_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
