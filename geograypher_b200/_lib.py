@@ -1,0 +1,273 @@
+"""ctypes binding of libgeograypher_b200.so (the C ABI declared in include/geograypher_b200.h).
+
+The library is the product's only compute path: if it is missing or no CUDA device is present every entry
+point raises -- there is no CPU fallback.  Tensors are torch CUDA tensors; only their device pointers cross
+the ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libgeograypher_b200.so"
+MAX_VIEWS_PER_CALL = 32
+
+# enums of include/geograypher_b200.h
+PRED_F32, PRED_F64, PRED_U8, PRED_INDEX_U8 = 0, 1, 2, 3
+MODE_LAST_PIXEL, MODE_PIXEL_SUM, MODE_VOTE = 0, 1, 2
+OUT_F64, OUT_F32, OUT_U8 = 0, 1, 2
+FLAG_COMPAT_NEGATIVE_INDEX, FLAG_KEEP_NAN = 1, 2
+ERR_OVERFLOW = -4
+
+EXPORTS = [
+    "gg_abi_version", "gg_last_error", "gg_create", "gg_destroy", "gg_sync", "gg_reserve",
+    "gg_last_batch_stats", "gg_set_mesh", "gg_project", "gg_rasterize", "gg_aggregate",
+    "gg_project_aggregate", "gg_finalize", "gg_render_flat",
+]
+
+
+class GGCamera(ctypes.Structure):
+    """gg_camera of the header; identical layout to the oracle's ora_camera."""
+
+    _fields_ = [
+        ("m", ctypes.c_float * 12),
+        ("f", ctypes.c_float),
+        ("px", ctypes.c_float),
+        ("py", ctypes.c_float),
+        ("W", ctypes.c_int32),
+        ("H", ctypes.c_int32),
+        ("znear", ctypes.c_float),
+    ]
+
+
+class GeograypherB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libgeograypher_b200 error {code}: {message}")
+        self.code = code
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile the CUDA sources in-tree for sm_100a (geograypher_b200/csrc/build.sh)."""
+    res = subprocess.run(["bash", str(_PKG / "csrc" / "build.sh")], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libgeograypher_b200.so failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building it if the .so is absent and nvcc is available) and set prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        build()
+    lib = ctypes.CDLL(str(LIB_PATH))
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    camp = ctypes.POINTER(GGCamera)
+    lib.gg_abi_version.restype = i32
+    lib.gg_last_error.restype = ctypes.c_char_p
+    lib.gg_create.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.gg_destroy.argtypes = [vp]
+    lib.gg_destroy.restype = None
+    lib.gg_sync.argtypes = [vp, vp]
+    lib.gg_reserve.argtypes = [vp, i64, i64]
+    lib.gg_last_batch_stats.argtypes = [vp, i32, vp]
+    lib.gg_set_mesh.argtypes = [vp, vp, i64, vp, i64, vp]
+    lib.gg_project.argtypes = [vp, camp, i32, vp, vp, vp, vp, vp]
+    lib.gg_rasterize.argtypes = [vp, camp, i32, vp, vp, vp]
+    lib.gg_aggregate.argtypes = [vp, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.gg_project_aggregate.argtypes = [vp, camp, i32, ctypes.POINTER(vp), i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.gg_finalize.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
+    lib.gg_render_flat.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp]
+    for name in EXPORTS:
+        if name not in ("gg_last_error", "gg_destroy"):
+            getattr(lib, name).restype = i32
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise GeograypherB200Error(rc, load().gg_last_error().decode("utf-8", "replace"))
+
+
+def make_camera(world_to_cam, f, cx, cy, image_width, image_height, render_img_scale=1.0, origin=None,
+                znear=1e-3) -> GGCamera:
+    """float64 camera parameters -> the float32 record of the rasterization contract.
+
+    Follows PhotogrammetryCamera (reference cameras/cameras.py:56-102): principal point offsets are measured
+    from the image centre; the scaled raster is (int(H*s), int(W*s)) (cameras.py:197-200) and keeps the
+    vertical field of view (cameras.py:472): f' = f*h'/H.  ``origin`` (float64) is the shift that was
+    subtracted from the mesh vertices before rounding them to float32.
+    """
+    m = np.asarray(world_to_cam, dtype=np.float64)[:3, :4].copy()
+    if origin is not None:
+        m[:, 3] = m[:, 3] + m[:, :3] @ np.asarray(origin, dtype=np.float64)
+    h, w = int(image_height * render_img_scale), int(image_width * render_img_scale)
+    s = h / float(image_height)
+    cam = GGCamera()
+    m32 = m.astype(np.float32).reshape(-1)
+    for k in range(12):
+        cam.m[k] = float(m32[k])
+    cam.f = np.float32(f * s)
+    cam.px = np.float32(w / 2.0 + cx * s)
+    cam.py = np.float32(h / 2.0 + cy * s)
+    cam.W = w
+    cam.H = h
+    cam.znear = np.float32(znear)
+    return cam
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(int(stream))
+
+
+class Context:
+    """One gg_context: a mesh resident on one device plus scratch.  Not thread-safe."""
+
+    def __init__(self, device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise GeograypherB200Error(-5, "no CUDA device: geograypher_b200 has no CPU fallback")
+        self.lib = load()
+        self.device = int(device)
+        self.torch = torch
+        h = ctypes.c_void_p()
+        _check(self.lib.gg_create(self.device, ctypes.byref(h)))
+        self.handle = h
+        self.n_faces = 0
+        self.n_verts = 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.gg_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------------------
+    def _dev(self):
+        return self.torch.device("cuda", self.device)
+
+    @staticmethod
+    def _cam_array(cams):
+        arr = (GGCamera * len(cams))(*cams)
+        return arr
+
+    def sync(self, stream=None):
+        _check(self.lib.gg_sync(self.handle, _stream_ptr(stream)))
+
+    def reserve(self, max_faces_per_view=0, max_bin_entries_per_view=0):
+        _check(self.lib.gg_reserve(self.handle, int(max_faces_per_view), int(max_bin_entries_per_view)))
+
+    def last_batch_stats(self, n):
+        out = np.zeros((n, 4), dtype=np.int64)
+        _check(self.lib.gg_last_batch_stats(self.handle, n, out.ctypes.data))
+        return out
+
+    # -- mesh ------------------------------------------------------------------------------------------
+    def set_mesh(self, verts32, faces32, stream=None):
+        """verts32: (V,3) float32 CUDA tensor (local frame, origin-shifted); faces32: (F,3) int32 CUDA tensor."""
+        t = self.torch
+        assert verts32.is_cuda and faces32.is_cuda
+        assert verts32.dtype == t.float32 and faces32.dtype == t.int32
+        verts32, faces32 = verts32.contiguous(), faces32.contiguous()
+        _check(self.lib.gg_set_mesh(self.handle, verts32.data_ptr(), verts32.shape[0], faces32.data_ptr(),
+                                    faces32.shape[0], _stream_ptr(stream)))
+        self.n_verts, self.n_faces = int(verts32.shape[0]), int(faces32.shape[0])
+
+    # -- stage 1 -----------------------------------------------------------------------------------------
+    def project(self, cams, stream=None):
+        t, n, V = self.torch, len(cams), self.n_verts
+        X = t.empty((n, V), dtype=t.int32, device=self._dev())
+        Y = t.empty_like(X)
+        invz = t.empty((n, V), dtype=t.float32, device=self._dev())
+        valid = t.empty((n, V), dtype=t.uint8, device=self._dev())
+        _check(self.lib.gg_project(self.handle, self._cam_array(cams), n, X.data_ptr(), Y.data_ptr(),
+                                   invz.data_ptr(), valid.data_ptr(), _stream_ptr(stream)))
+        return X, Y, invz, valid
+
+    # -- stage 1+2 -----------------------------------------------------------------------------------------
+    def rasterize(self, cams, out=None, want_depth=False, stream=None, check=True):
+        """pix2face for up to 32 same-size views: (n, H, W) int32 CUDA tensor (-1 = no face)."""
+        t, n = self.torch, len(cams)
+        H, W = cams[0].H, cams[0].W
+        if out is None:
+            out = t.empty((n, H, W), dtype=t.int32, device=self._dev())
+        depth = t.empty((n, H, W), dtype=t.float32, device=self._dev()) if want_depth else None
+        for attempt in range(4):
+            _check(self.lib.gg_rasterize(self.handle, self._cam_array(cams), n, out.data_ptr(),
+                                         depth.data_ptr() if depth is not None else None, _stream_ptr(stream)))
+            if not check:
+                break
+            try:
+                self.sync(stream)
+                break
+            except GeograypherB200Error as e:
+                if e.code != ERR_OVERFLOW or attempt == 3:
+                    raise
+                self._grow_after_overflow(n)
+        return (out, depth) if want_depth else out
+
+    def _grow_after_overflow(self, n):
+        stats = self.last_batch_stats(n)
+        self.reserve(0, int(stats[:, 2].max() * 1.25) + 1024)
+
+    # -- stage 3 -------------------------------------------------------------------------------------------
+    def aggregate(self, pix2face, pred, pred_kind, C, mode, flags, d_sum, d_count, stream=None):
+        H, W = int(pix2face.shape[-2]), int(pix2face.shape[-1])
+        _check(self.lib.gg_aggregate(self.handle, pix2face.data_ptr(), H, W, pred.data_ptr(), pred_kind, C, mode,
+                                     flags, d_sum.data_ptr(), d_count.data_ptr(), _stream_ptr(stream)))
+
+    def project_aggregate(self, cams, preds, pred_kind, C, mode, flags, d_sum, d_count, pix2face_out=None,
+                          stream=None, check=True):
+        n = len(cams)
+        ptrs = (ctypes.c_void_p * n)(*[p.data_ptr() for p in preds])
+        _check(self.lib.gg_project_aggregate(self.handle, self._cam_array(cams), n, ptrs, pred_kind, C, mode,
+                                             flags, d_sum.data_ptr(), d_count.data_ptr(),
+                                             pix2face_out.data_ptr() if pix2face_out is not None else None,
+                                             _stream_ptr(stream)))
+        if check:
+            # GG_ERR_OVERFLOW here means the accumulators hold partial sums: reserve() and restart.
+            self.sync(stream)
+
+    def finalize(self, d_sum, d_count, want_avg=True, want_argmax=True, stream=None):
+        t = self.torch
+        F, C = d_sum.shape
+        avg = t.empty_like(d_sum) if want_avg else None
+        argmax = t.empty((F,), dtype=t.float64, device=d_sum.device) if want_argmax else None
+        _check(self.lib.gg_finalize(self.handle, d_sum.data_ptr(), d_count.data_ptr(), F, C,
+                                    avg.data_ptr() if avg is not None else None,
+                                    argmax.data_ptr() if argmax is not None else None, _stream_ptr(stream)))
+        return avg, argmax
+
+    # -- stage 4 -------------------------------------------------------------------------------------------
+    def render_flat(self, pix2face, face_tex64, out_dtype=OUT_F64, out=None, stream=None):
+        """pix2face: (..., H, W) int32; face_tex64: (F, D) float64 -> (..., H, W, D)."""
+        t = self.torch
+        D = int(face_tex64.shape[1])
+        dt = {OUT_F64: t.float64, OUT_F32: t.float32, OUT_U8: t.uint8}[out_dtype]
+        if out is None:
+            out = t.empty(tuple(pix2face.shape) + (D,), dtype=dt, device=pix2face.device)
+        _check(self.lib.gg_render_flat(self.handle, pix2face.data_ptr(), pix2face.numel(), face_tex64.data_ptr(), D,
+                                       out.data_ptr(), out_dtype, _stream_ptr(stream)))
+        return out

@@ -1,0 +1,279 @@
+// Stage 3 (per-face aggregation of prediction images), its epilogue (mean + argmax) and stage 4 (render_flat
+// gather).
+//
+// Reference semantics restated (file:line under /root/reference/geograypher):
+//   meshes/meshes.py:1988-2001   textured_faces[flat_pix2face] = flat_img   -> LAST pixel (row-major) per face
+//   meshes/meshes.py:2056-2067   sum over views with NaN -> 0; a face counts once per view with a finite value
+//   meshes/meshes.py:2069-2082   rows never seen -> NaN; mean = sum / count
+//   meshes/derived_meshes.py:480-520   one-hot votes from the face's last pixel
+//   meshes/meshes.py:1921-1937   render_flat gather;  :2323-2334 uint8 cast rule
+//   utils/indexing.py:9-32       find_argmax_nonzero_value
+//   predictors/segmentor.py:59-69  inds_to_one_hot (GG_PRED_INDEX_U8 expands it on the fly)
+#include "gg_internal.cuh"
+
+namespace {
+
+#define GG_FLAG_COMPAT_NEG 1  // meshes.py:2000: background pixels (-1) index face F-1
+#define GG_FLAG_KEEP_NAN 2    // single-view corner of meshes.py:2056-2057: the first projection keeps its NaNs
+
+// ---- pass A: last pixel (row-major) of every face in this raster -------------------------------------
+// One thread handles 4 consecutive pixels; it issues an atomicMax only for the last pixel of each run of equal
+// face IDs, and skips its final run when the next lane starts with the same face (that lane, or a later one,
+// holds a larger pixel index for it).
+__global__ void __launch_bounds__(256) k_last_pixel(const int32_t *__restrict__ p2f, int64_t P, int32_t last_face,
+                                                    int compat, int aligned16, int32_t *__restrict__ winner) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p0 = t * 4;
+    int f[4];
+    if (aligned16 && p0 + 3 < P) {
+        const int4 v = *reinterpret_cast<const int4 *>(p2f + p0);
+        f[0] = v.x;
+        f[1] = v.y;
+        f[2] = v.z;
+        f[3] = v.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] = (p0 + i < P) ? p2f[p0 + i] : -2;
+    }
+    if (compat) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (f[i] == -1) f[i] = last_face;
+    }
+    const int next_first = __shfl_down_sync(0xffffffffu, f[0], 1);
+    const bool has_next = (threadIdx.x & 31) != 31;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int nxt = (i < 3) ? f[i + 1] : (has_next ? next_first : -3);
+        if (f[i] >= 0 && f[i] != nxt) atomicMax(&winner[f[i]], (int32_t)(p0 + i));
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ double load_score(const T *pred, int64_t idx) {
+    return (double)pred[idx];
+}
+
+// ---- pass B: one thread per face; consumes and resets the winner ---------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_resolve_dense(int32_t *__restrict__ winner, int64_t F,
+                                                       const T *__restrict__ pred, int C, int flags,
+                                                       double *__restrict__ sum, int32_t *__restrict__ count) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int32_t p = winner[f];
+    if (p < 0) return;
+    winner[f] = -1;
+    bool any_finite = false;
+    for (int c = 0; c < C; ++c) {
+        const double v = load_score(pred, (int64_t)p * C + c);
+        any_finite = any_finite || isfinite(v);
+        if (!isnan(v) || (flags & GG_FLAG_KEEP_NAN)) sum[f * C + c] += v;
+    }
+    if (any_finite) count[f] += 1;
+}
+
+__global__ void __launch_bounds__(256) k_resolve_index(int32_t *__restrict__ winner, int64_t F,
+                                                       const uint8_t *__restrict__ pred, int C,
+                                                       double *__restrict__ sum, int32_t *__restrict__ count) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int32_t p = winner[f];
+    if (p < 0) return;
+    winner[f] = -1;
+    const int cls = pred[p];
+    if (cls < C) sum[f * C + cls] += 1.0;
+    count[f] += 1;  // a one-hot row is always finite, even the all-zero row of an ignored pixel
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_resolve_vote(int32_t *__restrict__ winner, int64_t F,
+                                                      const T *__restrict__ pred, int C, double *__restrict__ sum,
+                                                      int32_t *__restrict__ count) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int32_t p = winner[f];
+    if (p < 0) return;
+    winner[f] = -1;
+    const double v = (double)pred[p];
+    if (!isfinite(v)) return;
+    count[f] += 1;
+    const long long cls = (long long)v;
+    if (cls >= 0 && cls < C) sum[f * C + cls] += 1.0;
+}
+
+// ---- non-reference dense mode, unfused: every pixel adds its scores -------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_pixel_sum(const int32_t *__restrict__ p2f, int64_t P,
+                                                   const T *__restrict__ pred, int C, int index_kind,
+                                                   double *__restrict__ sum, int32_t *__restrict__ count) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int f = p2f[p];
+    if (f < 0) return;
+    if (index_kind) {
+        const int cls = (int)pred[p];
+        if (cls < C) atomicAdd(&sum[(int64_t)f * C + cls], 1.0);
+    } else {
+        for (int c = 0; c < C; ++c) {
+            const double v = (double)pred[p * C + c];
+            if (!isnan(v)) atomicAdd(&sum[(int64_t)f * C + c], v);
+        }
+    }
+    atomicAdd(&count[f], 1);
+}
+
+// ---- epilogue: mean + argmax -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finalize(double *__restrict__ sum, const int32_t *__restrict__ count,
+                                                  int64_t F, int C, double *__restrict__ avg,
+                                                  double *__restrict__ argmax) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int32_t n = count[f];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (n == 0) {
+        for (int c = 0; c < C; ++c) {
+            sum[f * C + c] = nan;
+            if (avg) avg[f * C + c] = nan;
+        }
+        if (argmax) argmax[f] = nan;
+        return;
+    }
+    double best = 0.0, total = 0.0;
+    int best_c = 0;
+    bool bad = false;
+    const double dn = (double)n;
+    for (int c = 0; c < C; ++c) {
+        const double a = sum[f * C + c] / dn;
+        if (avg) avg[f * C + c] = a;
+        bad = bad || !isfinite(a);
+        total += a;
+        if (c == 0 || a > best) {
+            best = a;
+            best_c = c;
+        }
+    }
+    if (argmax) argmax[f] = (bad || total == 0.0) ? nan : (double)best_c;
+}
+
+// ---- stage 4: gather ---------------------------------------------------------------------------------------
+template <typename OUT>
+__device__ __forceinline__ OUT convert_out(double v);
+template <>
+__device__ __forceinline__ double convert_out<double>(double v) {
+    return v;
+}
+template <>
+__device__ __forceinline__ float convert_out<float>(double v) {
+    return (float)v;
+}
+template <>
+__device__ __forceinline__ uint8_t convert_out<uint8_t>(double v) {
+    // save_renders: < 0, > 255 or non-finite -> NULL_TEXTURE_INT_VALUE (0), then astype(uint8) truncates
+    if (!(v >= 0.0) || v > 255.0 || !isfinite(v)) return 0;
+    return (uint8_t)v;
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(256) k_render_flat(const int32_t *__restrict__ p2f, int64_t P,
+                                                     const double *__restrict__ tex, int D, OUT *__restrict__ out) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+        const int f = p2f[p];
+        for (int d = 0; d < D; ++d) out[p * D + d] = convert_out<OUT>(f >= 0 ? tex[(int64_t)f * D + d] : nan);
+    }
+}
+
+__global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace
+
+static int ensure_winner(gg_context *ctx, cudaStream_t st) {
+    if (ctx->winner_cap >= ctx->F && ctx->d_winner) return GG_OK;
+    if (ctx->d_winner) {
+        GG_CUDA(cudaDeviceSynchronize());
+        GG_CUDA(cudaFree(ctx->d_winner));
+        ctx->d_winner = nullptr;
+    }
+    GG_CUDA(cudaMalloc(&ctx->d_winner, (size_t)ctx->F * 4));
+    ctx->winner_cap = ctx->F;
+    k_fill_i32<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->d_winner, ctx->F, -1);
+    GG_CUDA(cudaGetLastError());
+    return GG_OK;
+}
+
+int gg_launch_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred,
+                        int pred_kind, int C, int mode, int flags, double *d_sum, int32_t *d_count,
+                        cudaStream_t st) {
+    const int64_t P = (int64_t)H * W, F = ctx->F;
+    if (P >= (1LL << 31)) {
+        gg_set_error("gg_aggregate: raster larger than 2^31 pixels");
+        return GG_ERR_INVALID;
+    }
+    if (mode == GG_MODE_PIXEL_SUM) {
+        const unsigned g = (unsigned)((P + 255) / 256);
+        switch (pred_kind) {
+            case GG_PRED_F32: k_pixel_sum<float><<<g, 256, 0, st>>>(d_pix2face, P, (const float *)d_pred, C, 0, d_sum, d_count); break;
+            case GG_PRED_F64: k_pixel_sum<double><<<g, 256, 0, st>>>(d_pix2face, P, (const double *)d_pred, C, 0, d_sum, d_count); break;
+            case GG_PRED_U8: k_pixel_sum<uint8_t><<<g, 256, 0, st>>>(d_pix2face, P, (const uint8_t *)d_pred, C, 0, d_sum, d_count); break;
+            case GG_PRED_INDEX_U8: k_pixel_sum<uint8_t><<<g, 256, 0, st>>>(d_pix2face, P, (const uint8_t *)d_pred, C, 1, d_sum, d_count); break;
+            default: gg_set_error("gg_aggregate: bad pred_kind"); return GG_ERR_INVALID;
+        }
+        GG_CUDA(cudaGetLastError());
+        return GG_OK;
+    }
+    int rc = ensure_winner(ctx, st);
+    if (rc != GG_OK) return rc;
+    const int64_t threads = (P + 3) / 4;
+    k_last_pixel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_pix2face, P, (int32_t)(F - 1),
+                                                                    flags & GG_FLAG_COMPAT_NEG,
+                                                                    (((uintptr_t)d_pix2face) & 15) == 0, ctx->d_winner);
+    GG_CUDA(cudaGetLastError());
+    const unsigned gf = (unsigned)((F + 255) / 256);
+    if (mode == GG_MODE_LAST_PIXEL) {
+        switch (pred_kind) {
+            case GG_PRED_F32: k_resolve_dense<float><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const float *)d_pred, C, flags, d_sum, d_count); break;
+            case GG_PRED_F64: k_resolve_dense<double><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const double *)d_pred, C, flags, d_sum, d_count); break;
+            case GG_PRED_U8: k_resolve_dense<uint8_t><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const uint8_t *)d_pred, C, flags, d_sum, d_count); break;
+            case GG_PRED_INDEX_U8: k_resolve_index<<<gf, 256, 0, st>>>(ctx->d_winner, F, (const uint8_t *)d_pred, C, d_sum, d_count); break;
+            default: gg_set_error("gg_aggregate: bad pred_kind"); return GG_ERR_INVALID;
+        }
+    } else if (mode == GG_MODE_VOTE) {
+        switch (pred_kind) {
+            case GG_PRED_F32: k_resolve_vote<float><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const float *)d_pred, C, d_sum, d_count); break;
+            case GG_PRED_F64: k_resolve_vote<double><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const double *)d_pred, C, d_sum, d_count); break;
+            case GG_PRED_U8:
+            case GG_PRED_INDEX_U8: k_resolve_vote<uint8_t><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const uint8_t *)d_pred, C, d_sum, d_count); break;
+            default: gg_set_error("gg_aggregate: bad pred_kind"); return GG_ERR_INVALID;
+        }
+    } else {
+        gg_set_error("gg_aggregate: bad mode");
+        return GG_ERR_INVALID;
+    }
+    GG_CUDA(cudaGetLastError());
+    return GG_OK;
+}
+
+int gg_launch_finalize(gg_context *ctx, double *d_sum, const int32_t *d_count, int64_t F, int C, double *d_avg,
+                       double *d_argmax, cudaStream_t st) {
+    (void)ctx;
+    k_finalize<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(d_sum, d_count, F, C, d_avg, d_argmax);
+    GG_CUDA(cudaGetLastError());
+    return GG_OK;
+}
+
+int gg_launch_render_flat(gg_context *ctx, const int32_t *d_pix2face, int64_t P, const double *d_tex, int D,
+                          void *d_out, int out_dtype, cudaStream_t st) {
+    const int64_t want = (P + 255) / 256;
+    const unsigned g = (unsigned)(want < (int64_t)ctx->sm_count * 32 ? (want > 0 ? want : 1) : ctx->sm_count * 32);
+    switch (out_dtype) {
+        case GG_OUT_F64: k_render_flat<double><<<g, 256, 0, st>>>(d_pix2face, P, d_tex, D, (double *)d_out); break;
+        case GG_OUT_F32: k_render_flat<float><<<g, 256, 0, st>>>(d_pix2face, P, d_tex, D, (float *)d_out); break;
+        case GG_OUT_U8: k_render_flat<uint8_t><<<g, 256, 0, st>>>(d_pix2face, P, d_tex, D, (uint8_t *)d_out); break;
+        default: gg_set_error("gg_render_flat: bad out_dtype"); return GG_ERR_INVALID;
+    }
+    GG_CUDA(cudaGetLastError());
+    return GG_OK;
+}

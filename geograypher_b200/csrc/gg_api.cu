@@ -1,0 +1,293 @@
+// extern "C" surface of libgeograypher_b200.so (declared in include/geograypher_b200.h).
+#include <cstdio>
+#include <cstring>
+
+#include "gg_internal.cuh"
+
+static thread_local std::string g_last_error;
+
+void gg_set_error(const std::string &msg) { g_last_error = msg; }
+
+int gg_cuda_fail(cudaError_t e, const char *what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return GG_ERR_CUDA;
+}
+
+namespace {
+__global__ void k_pack_mesh(const float *__restrict__ v, int64_t V, const int32_t *__restrict__ f, int64_t F,
+                            float4 *__restrict__ v4, int4 *__restrict__ f4, int *__restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V) v4[i] = make_float4(v[3 * i], v[3 * i + 1], v[3 * i + 2], 0.f);
+    if (i < F) {
+        const int a = f[3 * i], b = f[3 * i + 1], c = f[3 * i + 2];
+        if (a < 0 || b < 0 || c < 0 || a >= V || b >= V || c >= V) atomicOr(bad, 1);
+        f4[i] = make_int4(a, b, c, (int)i);
+    }
+}
+}  // namespace
+
+static int check_ctx(gg_context *ctx, bool need_mesh) {
+    if (!ctx) {
+        gg_set_error("null context");
+        return GG_ERR_INVALID;
+    }
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return gg_cuda_fail(e, "cudaSetDevice");
+    if (need_mesh && ctx->F == 0) {
+        gg_set_error("gg_set_mesh has not been called");
+        return GG_ERR_NO_MESH;
+    }
+    return GG_OK;
+}
+
+static int check_cams(const gg_camera *cams, int n) {
+    if (!cams || n < 1 || n > GG_MAX_VIEWS_PER_CALL) {
+        gg_set_error("need 1..GG_MAX_VIEWS_PER_CALL cameras");
+        return GG_ERR_INVALID;
+    }
+    for (int i = 0; i < n; ++i) {
+        if (cams[i].W != cams[0].W || cams[i].H != cams[0].H) {
+            gg_set_error("Not all cameras have the same image size");
+            return GG_ERR_INVALID;
+        }
+        if (cams[i].W < 1 || cams[i].H < 1 || cams[i].W > 32767 || cams[i].H > 32767) {
+            gg_set_error("raster size must be within 1..32767");
+            return GG_ERR_INVALID;
+        }
+    }
+    return GG_OK;
+}
+
+extern "C" {
+
+int gg_abi_version(void) { return GG_ABI_VERSION; }
+
+const char *gg_last_error(void) { return g_last_error.c_str(); }
+
+int gg_create(int device, gg_context **out) {
+    if (!out) {
+        gg_set_error("gg_create: out is null");
+        return GG_ERR_INVALID;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        gg_set_error(std::string("gg_create: no usable CUDA device (") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range") + "); there is no CPU fallback");
+        return GG_ERR_NO_DEVICE;
+    }
+    GG_CUDA(cudaSetDevice(device));
+    gg_context *ctx = new gg_context();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    GG_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    memset(&ctx->views, 0, sizeof(ctx->views));
+    *out = ctx;
+    return GG_OK;
+}
+
+void gg_destroy(gg_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_verts);
+    cudaFree(ctx->d_faces);
+    cudaFree(ctx->d_block_lo);
+    cudaFree(ctx->d_block_hi);
+    cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_winner);
+    cudaFree(ctx->d_raster);
+    delete ctx;
+}
+
+int gg_sync(gg_context *ctx, void *stream) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    GG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    GG_CUDA(cudaGetLastError());
+    for (int i = 0; i < ctx->last_batch_n; ++i) {
+        int32_t c[4];
+        GG_CUDA(cudaMemcpy(c, ctx->views.v[i].counters, sizeof(c), cudaMemcpyDeviceToHost));
+        if (c[3] != 0) {
+            char buf[256];
+            snprintf(buf, sizeof(buf),
+                     "scratch overflow in view %d of the last batch (records %d / cap %lld, bin entries %d / cap %lld): "
+                     "call gg_reserve with larger capacities and retry",
+                     i, c[1], (long long)ctx->cap_recs, c[2], (long long)ctx->cap_bins);
+            gg_set_error(buf);
+            return GG_ERR_OVERFLOW;
+        }
+    }
+    return GG_OK;
+}
+
+int gg_reserve(gg_context *ctx, int64_t max_faces_per_view, int64_t max_bin_entries_per_view) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    if (max_faces_per_view < 0 || max_bin_entries_per_view < 0) {
+        gg_set_error("gg_reserve: negative capacity");
+        return GG_ERR_INVALID;
+    }
+    ctx->req_recs = max_faces_per_view;
+    ctx->req_bins = max_bin_entries_per_view;
+    return GG_OK;
+}
+
+int gg_last_batch_stats(gg_context *ctx, int n, int64_t *h_out) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    if (n > ctx->last_batch_n) n = ctx->last_batch_n;
+    for (int i = 0; i < n; ++i) {
+        int32_t c[4];
+        GG_CUDA(cudaMemcpy(c, ctx->views.v[i].counters, sizeof(c), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 4; ++k) h_out[4 * i + k] = c[k];
+    }
+    return GG_OK;
+}
+
+int gg_set_mesh(gg_context *ctx, const float *d_verts, int64_t V, const int32_t *d_faces, int64_t F, void *stream) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    if (!d_verts || !d_faces || V < 1 || F < 1 || V >= (1LL << 31) || F >= (1LL << 31)) {
+        gg_set_error("gg_set_mesh: need 1 <= V,F < 2^31 and non-null device pointers");
+        return GG_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    GG_CUDA(cudaDeviceSynchronize());
+    cudaFree(ctx->d_verts);
+    cudaFree(ctx->d_faces);
+    cudaFree(ctx->d_block_lo);
+    cudaFree(ctx->d_block_hi);
+    cudaFree(ctx->d_winner);
+    ctx->d_verts = nullptr;
+    ctx->d_faces = nullptr;
+    ctx->d_block_lo = ctx->d_block_hi = nullptr;
+    ctx->d_winner = nullptr;
+    ctx->winner_cap = 0;
+    ctx->F = 0;
+    ctx->V = 0;
+    ctx->n_blocks = (F + GG_BLOCK_FACES - 1) / GG_BLOCK_FACES;
+    GG_CUDA(cudaMalloc(&ctx->d_verts, (size_t)V * sizeof(float4)));
+    GG_CUDA(cudaMalloc(&ctx->d_faces, (size_t)F * sizeof(int4)));
+    GG_CUDA(cudaMalloc(&ctx->d_block_lo, (size_t)ctx->n_blocks * 3 * sizeof(float)));
+    GG_CUDA(cudaMalloc(&ctx->d_block_hi, (size_t)ctx->n_blocks * 3 * sizeof(float)));
+    int *d_bad = nullptr;
+    GG_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    GG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    const int64_t n = V > F ? V : F;
+    k_pack_mesh<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_verts, V, d_faces, F, ctx->d_verts, ctx->d_faces, d_bad);
+    GG_CUDA(cudaGetLastError());
+    int bad = 0;
+    GG_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GG_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_bad);
+    if (bad) {
+        gg_set_error("gg_set_mesh: face index out of range");
+        return GG_ERR_INVALID;
+    }
+    ctx->V = V;
+    ctx->F = F;
+    rc = gg_launch_mesh_blocks(ctx, st);
+    if (rc != GG_OK) return rc;
+    GG_CUDA(cudaStreamSynchronize(st));
+    return GG_OK;
+}
+
+int gg_project(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_X, int32_t *d_Y, float *d_invz,
+               uint8_t *d_valid, void *stream) {
+    int rc = check_ctx(ctx, true);
+    if (rc != GG_OK) return rc;
+    if (!h_cams || n < 1 || n > GG_MAX_VIEWS_PER_CALL || !d_X || !d_Y || !d_invz || !d_valid) {
+        gg_set_error("gg_project: bad arguments");
+        return GG_ERR_INVALID;
+    }
+    return gg_launch_project(ctx, h_cams, n, d_X, d_Y, d_invz, d_valid, (cudaStream_t)stream);
+}
+
+int gg_rasterize(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_pix2face, float *d_depth, void *stream) {
+    int rc = check_ctx(ctx, true);
+    if (rc != GG_OK) return rc;
+    rc = check_cams(h_cams, n);
+    if (rc != GG_OK) return rc;
+    if (!d_pix2face) {
+        gg_set_error("gg_rasterize: d_pix2face is null");
+        return GG_ERR_INVALID;
+    }
+    return gg_launch_rasterize(ctx, h_cams, n, d_pix2face, d_depth, (cudaStream_t)stream);
+}
+
+int gg_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred, int pred_kind, int C,
+                 int mode, int compat_negative_index, double *d_sum, int32_t *d_count, void *stream) {
+    int rc = check_ctx(ctx, true);
+    if (rc != GG_OK) return rc;
+    if (!d_pix2face || !d_pred || !d_sum || !d_count || H < 1 || W < 1 || C < 1) {
+        gg_set_error("gg_aggregate: bad arguments");
+        return GG_ERR_INVALID;
+    }
+    return gg_launch_aggregate(ctx, d_pix2face, H, W, d_pred, pred_kind, C, mode, compat_negative_index, d_sum, d_count,
+                               (cudaStream_t)stream);
+}
+
+int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const void *const *h_pred, int pred_kind,
+                         int C, int mode, int compat_negative_index, double *d_sum, int32_t *d_count,
+                         int32_t *d_pix2face, void *stream) {
+    int rc = check_ctx(ctx, true);
+    if (rc != GG_OK) return rc;
+    rc = check_cams(h_cams, n);
+    if (rc != GG_OK) return rc;
+    if (!h_pred || !d_sum || !d_count || C < 1) {
+        gg_set_error("gg_project_aggregate: bad arguments");
+        return GG_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int W = h_cams[0].W, H = h_cams[0].H;
+    const int64_t P = (int64_t)W * H;
+    int32_t *raster = d_pix2face;
+    if (!raster) {
+        const int64_t need = P * n;
+        if (ctx->raster_cap < need) {
+            if (ctx->d_raster) {
+                GG_CUDA(cudaDeviceSynchronize());
+                GG_CUDA(cudaFree(ctx->d_raster));
+                ctx->d_raster = nullptr;
+            }
+            GG_CUDA(cudaMalloc(&ctx->d_raster, (size_t)need * 4));
+            ctx->raster_cap = need;
+        }
+        raster = ctx->d_raster;
+    }
+    rc = gg_launch_rasterize(ctx, h_cams, n, raster, nullptr, st);
+    if (rc != GG_OK) return rc;
+    for (int i = 0; i < n; ++i) {
+        rc = gg_launch_aggregate(ctx, raster + P * i, H, W, h_pred[i], pred_kind, C, mode, compat_negative_index, d_sum,
+                                 d_count, st);
+        if (rc != GG_OK) return rc;
+    }
+    return GG_OK;
+}
+
+int gg_finalize(gg_context *ctx, double *d_sum, const int32_t *d_count, int64_t F, int C, double *d_avg,
+                double *d_argmax, void *stream) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    if (!d_sum || !d_count || F < 1 || C < 1) {
+        gg_set_error("gg_finalize: bad arguments");
+        return GG_ERR_INVALID;
+    }
+    return gg_launch_finalize(ctx, d_sum, d_count, F, C, d_avg, d_argmax, (cudaStream_t)stream);
+}
+
+int gg_render_flat(gg_context *ctx, const int32_t *d_pix2face, int64_t n_pixels, const double *d_face_tex, int D,
+                   void *d_out, int out_dtype, void *stream) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    if (!d_pix2face || !d_face_tex || !d_out || n_pixels < 1 || D < 1) {
+        gg_set_error("gg_render_flat: bad arguments");
+        return GG_ERR_INVALID;
+    }
+    return gg_launch_render_flat(ctx, d_pix2face, n_pixels, d_face_tex, D, d_out, out_dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

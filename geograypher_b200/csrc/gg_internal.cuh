@@ -1,0 +1,97 @@
+// Internal declarations shared by the translation units of libgeograypher_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/geograypher_b200.h"
+
+// ---- rasterization contract constants (DESIGN.md "Rasterization contract") -------------------------
+#define GG_SUBPIX 256
+#define GG_HALF 128
+#define GG_SUBPIX_LOG2 8
+#define GG_COORD_CLAMP 536870912.0f  // 2^29 sub-pixel units
+
+// ---- tiling ------------------------------------------------------------------------------------------
+#define GG_TILE_W 64
+#define GG_TILE_H 32
+#define GG_RASTER_THREADS 256  // 8 warps; warp = 32 x 8 px region, lane = 8 consecutive px of one row
+#define GG_CHUNK 64            // faces staged in shared memory per pass
+#define GG_BLOCK_FACES 128     // faces per cull block
+
+struct GGFaceRec {             // one surviving face of one view, orientation-normalised (area2 > 0); 48 B
+    int32_t x0, y0, x1, y1, x2, y2;  // fixed-point screen coordinates (1/256 px)
+    float w0, w1, w2;                // 1/z_cam at the vertices
+    int32_t face;                    // face ID
+    uint16_t jmin, jmax, imin, imax; // pixel-centre index range, clamped to the raster
+};
+static_assert(sizeof(GGFaceRec) == 48, "GGFaceRec layout");
+
+struct GGCamBatch {  // passed by value as a __grid_constant__ kernel parameter (<= 4 KB)
+    gg_camera cam[GG_MAX_VIEWS_PER_CALL];
+};
+
+struct GGViewScratch {  // device pointers of one batch slot
+    int32_t *vis_blocks;   // [n_blocks]
+    GGFaceRec *recs;       // [cap_recs]
+    int32_t *tile_count;   // [n_tiles]   (reused as fill cursor)
+    int32_t *tile_offset;  // [n_tiles + 1]
+    int32_t *bins;         // [cap_bins]  record indices grouped by tile
+    int32_t *counters;     // [8]: 0 n_vis_blocks, 1 n_recs, 2 n_bin_entries, 3 overflow flag, 4 bg winner,
+                           //      5 rec index of face F-1 (or -1)
+};
+
+struct GGViewBatch {
+    GGViewScratch v[GG_MAX_VIEWS_PER_CALL];
+};
+
+struct gg_context {
+    int device = 0;
+    // mesh
+    int64_t V = 0, F = 0;
+    float4 *d_verts = nullptr;   // [V] xyz + pad
+    int4 *d_faces = nullptr;     // [F] i0,i1,i2,face_id
+    float *d_block_lo = nullptr; // [n_blocks*3]
+    float *d_block_hi = nullptr; // [n_blocks*3]
+    int64_t n_blocks = 0;
+    // scratch
+    int64_t cap_recs = 0, cap_bins = 0;
+    int64_t req_recs = 0, req_bins = 0;  // user reservation (0 = automatic)
+    int n_slots = 0;
+    int64_t slot_tiles = 0;
+    char *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    GGViewBatch views;
+    int32_t *d_winner = nullptr;  // [F] last-pixel winner per face (dense, unfused aggregation)
+    int64_t winner_cap = 0;
+    int32_t *d_raster = nullptr;  // internal n x H x W raster when the caller does not want pix2face back
+    int64_t raster_cap = 0;
+    int last_batch_n = 0;
+    int sm_count = 148;
+};
+
+void gg_set_error(const std::string &msg);
+int gg_cuda_fail(cudaError_t e, const char *what);
+
+#define GG_CUDA(call)                                            \
+    do {                                                         \
+        cudaError_t _e = (call);                                 \
+        if (_e != cudaSuccess) return gg_cuda_fail(_e, #call);   \
+    } while (0)
+
+// gg_raster.cu
+int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H);
+int gg_launch_mesh_blocks(gg_context *ctx, cudaStream_t st);
+int gg_launch_project(gg_context *ctx, const gg_camera *cams, int n, int32_t *dX, int32_t *dY, float *dinvz,
+                      uint8_t *dvalid, cudaStream_t st);
+int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *d_pix2face, float *d_depth,
+                        cudaStream_t st);
+// gg_aggregate.cu
+int gg_launch_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred,
+                        int pred_kind, int C, int mode, int compat, double *d_sum, int32_t *d_count,
+                        cudaStream_t st);
+int gg_launch_finalize(gg_context *ctx, double *d_sum, const int32_t *d_count, int64_t F, int C, double *d_avg,
+                       double *d_argmax, cudaStream_t st);
+int gg_launch_render_flat(gg_context *ctx, const int32_t *d_pix2face, int64_t P, const double *d_tex, int D,
+                          void *d_out, int out_dtype, cudaStream_t st);

@@ -1,0 +1,141 @@
+/*
+ * geograypher_b200.h -- C ABI of the B200-native multiview-projection library (libgeograypher_b200.so).
+ *
+ * The reference (open-forest-observatory/geograypher v0.4.0, pure Python) has NO native interface; its
+ * extension point for this path is method override on TexturedPhotogrammetryMesh
+ * (geograypher/meshes/derived_meshes.py:642 overrides pix2face; :222 and :415 override
+ * aggregate_projected_images).  Each entry point below names the reference method(s) whose arithmetic it
+ * replaces; geograypher_b200/meshes/meshes.py binds them with ctypes behind the reference's signatures.
+ * INTEGRATION.md shows the stub a geograypher maintainer would add.
+ *
+ * Conventions
+ *   - every d_* pointer is a DEVICE pointer owned by the caller (e.g. torch tensor storage); h_* pointers
+ *     are host memory read before the call returns;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is enqueued on it
+ *     and the call returns without synchronising unless stated;
+ *   - return value: 0 on success, negative gg_status on failure; gg_last_error() gives the message of the
+ *     last failure on the calling thread; nothing throws across the ABI;
+ *   - a gg_context is bound to one device, owns the mesh copy + scratch, and is not thread-safe (one
+ *     context per mesh per device, like the reference's one pix2face_plotter per mesh, meshes.py:111-114).
+ *   - there is no CPU fallback: without a CUDA device gg_create fails.
+ */
+#ifndef GEOGRAYPHER_B200_H
+#define GEOGRAYPHER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_ABI_VERSION 1
+#define GG_MAX_VIEWS_PER_CALL 32
+
+typedef struct gg_context gg_context;
+
+typedef enum {
+    GG_OK = 0,
+    GG_ERR_INVALID = -1,  /* bad argument */
+    GG_ERR_CUDA = -2,     /* CUDA runtime error (message has the cudaError string) */
+    GG_ERR_NO_MESH = -3,  /* gg_set_mesh has not been called */
+    GG_ERR_OVERFLOW = -4, /* scratch capacity exceeded in the last batch: call gg_reserve and retry */
+    GG_ERR_NO_DEVICE = -5
+} gg_status;
+
+/*
+ * One pinhole view of the rasterization contract.  Built on the host in float64 from
+ * PhotogrammetryCamera (cameras/cameras.py:56-102, get_camera_properties :136-152) and rounded once:
+ *   m  = rows 0..2 of world_to_cam (= inv(cam_to_world), cameras.py:84), with the mesh origin shift folded in
+ *   f  = focal length in pixels, px = W/2 + cx, py = H/2 + cy  (derived_meshes.py:772-780)
+ *   W,H = raster size (get_image_size(scale), cameras.py:179-200)
+ */
+typedef struct {
+    float m[12];
+    float f, px, py;
+    int32_t W, H;
+    float znear;
+} gg_camera;
+
+/* prediction image layouts accepted by the aggregation entry points */
+typedef enum {
+    GG_PRED_F32 = 0,       /* (H,W,C) float32, NaN = null                                  */
+    GG_PRED_F64 = 1,       /* (H,W,C) float64 (what PhotogrammetryCamera.get_image yields) */
+    GG_PRED_U8 = 2,        /* (H,W,C) uint8 / bool (LookUpSegmentor one-hot)               */
+    GG_PRED_INDEX_U8 = 3   /* (H,W) uint8 class index; expanded on the fly exactly like
+                              Segmentor.inds_to_one_hot (predictors/segmentor.py:37-69): value c<C -> one-hot,
+                              anything else (255 = ignore) -> all-zero row                  */
+} gg_pred_kind;
+
+typedef enum {
+    GG_MODE_LAST_PIXEL = 0, /* reference parity: per view the LAST pixel (row-major) of each face sets the
+                               face's row (meshes.py:2001), rows are summed over views with NaN->0 and a face
+                               counts once per view in which any channel is finite (meshes.py:2057-2067) */
+    GG_MODE_PIXEL_SUM = 1,  /* non-reference: every pixel adds its scores, count = number of pixels */
+    GG_MODE_VOTE = 2        /* TexturedPhotogrammetryMeshIndexPredictions (derived_meshes.py:480-520): the
+                               face's last pixel holds a class index (C == 1 image, NaN = null); counts[f]+=1,
+                               sum[f, class] += 1 */
+} gg_agg_mode;
+
+typedef enum { GG_OUT_F64 = 0, GG_OUT_F32 = 1, GG_OUT_U8 = 2 } gg_out_dtype;
+
+/* ---- lifetime ------------------------------------------------------------------------------------- */
+int gg_abi_version(void);
+const char *gg_last_error(void);
+int gg_create(int device, gg_context **out);
+void gg_destroy(gg_context *ctx);
+/* Synchronise `stream` and report a deferred failure of the work enqueued so far (GG_ERR_OVERFLOW, CUDA). */
+int gg_sync(gg_context *ctx, void *stream);
+/* Scratch sizing: max face records per view (0 = number of faces) and max (tile, face) pairs per view. */
+int gg_reserve(gg_context *ctx, int64_t max_faces_per_view, int64_t max_bin_entries_per_view);
+/* Counters of the most recent rasterization batch, valid after gg_sync: per view [n_visible_blocks,
+   n_face_records, n_bin_entries, overflow_flag].  out must hold 4*n int64. */
+int gg_last_batch_stats(gg_context *ctx, int n, int64_t *h_out);
+
+/* ---- mesh (replaces the per-call pv.PolyData / pytorch3d Meshes construction, meshes.py:1806-1817,
+        derived_meshes.py:592-640).  d_verts: V x 3 float32 in the camera set's local frame (after
+        get_mesh_in_cameras_coords, meshes.py:1641-1676, minus the origin shift); d_faces: F x 3 int32.
+        Copies the mesh, builds the per-block bounds used for frustum culling.  Synchronous. -------- */
+int gg_set_mesh(gg_context *ctx, const float *d_verts, int64_t V, const int32_t *d_faces, int64_t F,
+                void *stream);
+
+/* ---- stage 1: batched camera projection of all vertices (contract C1+C2).  Outputs are n x V. ------- */
+int gg_project(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_X, int32_t *d_Y, float *d_invz,
+               uint8_t *d_valid, void *stream);
+
+/* ---- stage 1+2: pix2face (meshes.py:1678-1856 / derived_meshes.py:642-737).  n <= GG_MAX_VIEWS_PER_CALL
+        views of identical W x H.  d_pix2face: n x H x W int32, -1 = no face.  d_depth (optional, may be
+        NULL): n x H x W float32 1/z_cam of the winning face (0 where none). ---------------------------- */
+int gg_rasterize(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_pix2face, float *d_depth,
+                 void *stream);
+
+/* ---- stage 3: per-face aggregation of ONE view's prediction image given its pix2face raster
+        (project_images + the accumulation of aggregate_projected_images, meshes.py:1988-2001, 2056-2067;
+        vote mode: derived_meshes.py:480-520).  d_sum: F x C float64 (vote mode: F x n_classes),
+        d_count: F int32; both are accumulated into, so zero them before the first view.
+        compat_negative_index != 0 reproduces meshes.py:2000 (background pixels index face F-1). -------- */
+int gg_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred, int pred_kind,
+                 int C, int mode, int compat_negative_index, double *d_sum, int32_t *d_count, void *stream);
+
+/* ---- stage 1+2+3 fused over n views: rasterize and aggregate without a round trip of the rasters through
+        the host.  h_pred[i] is the device pointer of view i's prediction image.  d_pix2face may be NULL. -- */
+int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const void *const *h_pred,
+                         int pred_kind, int C, int mode, int compat_negative_index, double *d_sum,
+                         int32_t *d_count, int32_t *d_pix2face, void *stream);
+
+/* ---- epilogue of aggregate_projected_images (meshes.py:2069-2082) + find_argmax_nonzero_value
+        (utils/indexing.py:9-32): avg = sum / count (NaN rows where count == 0; d_sum rows with count == 0 are
+        set to NaN in place like meshes.py:2070), argmax as float64 with NaN for all-zero / non-finite rows.
+        d_avg and d_argmax may each be NULL. ----------------------------------------------------------------- */
+int gg_finalize(gg_context *ctx, double *d_sum, const int32_t *d_count, int64_t F, int C, double *d_avg,
+                double *d_argmax, void *stream);
+
+/* ---- stage 4: render_flat gather (meshes.py:1921-1937): out[p,:] = tex[pix2face[p],:] or NaN.
+        d_face_tex: F x D float64.  out_dtype GG_OUT_U8 applies save_renders' cast rule
+        (meshes.py:2323-2334: <0, >255, non-finite -> 0, then truncate). ------------------------------------ */
+int gg_render_flat(gg_context *ctx, const int32_t *d_pix2face, int64_t n_pixels, const double *d_face_tex,
+                   int D, void *d_out, int out_dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOGRAYPHER_B200_H */

@@ -1,0 +1,232 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors that
+the reference's own code produced.  Run on the B200 box:  pytest -m gpu."""
+import numpy as np
+import pytest
+
+from geograypher_b200 import synthetic as syn
+from oracle import oracle as ora
+
+pytestmark = pytest.mark.gpu
+
+EPS_DEPTH = 1e-5  # contract: IDs are bit-exact on every pixel whose relative depth margin exceeds this
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from geograypher_b200 import _lib
+
+    return _lib
+
+
+def _to_gg(lib, cam):
+    out = lib.GGCamera()
+    for k in range(12):
+        out.m[k] = cam.m[k]
+    out.f, out.px, out.py, out.W, out.H, out.znear = cam.f, cam.px, cam.py, cam.W, cam.H, cam.znear
+    return out
+
+
+def _scene(name, max_cameras=None):
+    verts, faces, c2ws, cfg = syn.make_survey(name, max_cameras)
+    origin = 0.5 * (verts.min(0) + verts.max(0))
+    v32 = (verts - origin).astype(np.float32)
+    W, H = cfg.image_size
+    cams = [ora.make_camera(T, cfg.f, cfg.cx, cfg.cy, W, H, origin=origin) for T in c2ws]
+    return v32, faces, cams, cfg
+
+
+def _context(torch, lib, v32, faces):
+    ctx = lib.Context(0)
+    ctx.set_mesh(torch.from_numpy(v32).cuda(), torch.from_numpy(faces.astype(np.int32)).cuda())
+    return ctx
+
+
+def _assert_ids_match(gpu, ref, margin, label):
+    diff = gpu != ref
+    unsafe = margin <= EPS_DEPTH
+    bad = diff & ~unsafe
+    assert not bad.any(), (
+        f"{label}: {bad.sum()} pixels differ outside the depth-margin mask "
+        f"(first at {np.argwhere(bad)[0]}, gpu={gpu[bad][0]}, oracle={ref[bad][0]})"
+    )
+    return diff.sum(), unsafe.sum()
+
+
+@pytest.mark.parametrize("name", ["tiny", "c1"])
+def test_projection_bit_exact(torch, lib, name):
+    v32, faces, cams, _ = _scene(name, 4)
+    ctx = _context(torch, lib, v32, faces)
+    X, Y, invz, valid = ctx.project([_to_gg(lib, c) for c in cams])
+    for k, cam in enumerate(cams):
+        oX, oY, oinvz, ovalid = ora.project(v32, cam)
+        np.testing.assert_array_equal(valid[k].cpu().numpy().astype(bool), ovalid)
+        np.testing.assert_array_equal(X[k].cpu().numpy(), oX)
+        np.testing.assert_array_equal(Y[k].cpu().numpy(), oY)
+        np.testing.assert_array_equal(invz[k].cpu().numpy().view(np.uint32), oinvz.view(np.uint32))
+
+
+@pytest.mark.parametrize("name,ncam", [("tiny", 4), ("c1", 10)])
+def test_pix2face_matches_oracle(torch, lib, name, ncam):
+    v32, faces, cams, _ = _scene(name, ncam)
+    ctx = _context(torch, lib, v32, faces)
+    p2f, depth = ctx.rasterize([_to_gg(lib, c) for c in cams], want_depth=True)
+    p2f = p2f.cpu().numpy()
+    depth = depth.cpu().numpy()
+    n_diff = n_unsafe = 0
+    for k, cam in enumerate(cams):
+        ref, ref_w, margin = ora.rasterize(v32, faces, cam, want_depth=True, want_margin=True)
+        d, u = _assert_ids_match(p2f[k], ref, margin, f"{name} view {k}")
+        n_diff += d
+        n_unsafe += u
+        hit = ref >= 0
+        np.testing.assert_allclose(depth[k][hit & (p2f[k] == ref)], ref_w[hit & (p2f[k] == ref)], rtol=2e-5)
+        assert (p2f[k] >= 0).sum() > 0
+    # the mask must stay a vanishing fraction of the image
+    assert n_unsafe <= 1e-3 * p2f.size, (n_unsafe, p2f.size)
+
+
+def test_pix2face_golden_scene(torch, lib, golden_scene):
+    g = golden_scene
+    f, cx, cy, W, H = g["intrinsics"]
+    v32 = (g["verts"] - g["origin"]).astype(np.float32)
+    cams = [ora.make_camera(T, f, cx, cy, int(W), int(H), origin=g["origin"]) for T in g["c2ws"]]
+    ctx = _context(torch, lib, v32, g["faces"])
+    p2f = ctx.rasterize([_to_gg(lib, c) for c in cams]).cpu().numpy()
+    for k, cam in enumerate(cams):
+        _, _, margin = ora.rasterize(v32, g["faces"], cam, want_margin=True)
+        _assert_ids_match(p2f[k], g["pix2face"][k].astype(np.int64), margin, f"golden view {k}")
+
+
+def test_plane_known_answer(torch, lib):
+    """The reference's render_flat known-answer test (tests/test_derived_meshes.py:23-76) on the GPU path."""
+    from test_oracle_reference_pins import N, downward_view, pixel_idx, plane_mesh
+
+    fill = np.array([[10, 20], [15, 190], [195, 5], [50, 100], [150, 120]])
+    empty = np.array([[30, 40], [160, 180], [120, 40], [100, 150], [180, 100]])
+    verts, faces = plane_mesh()
+    colors = np.full((N * N, 3), 80, dtype=np.uint8)
+    for p in fill:
+        pixel_idx(colors, *p, stride=N, color=[255, 0, 0], buffer=1)
+    tex = ora.vert_to_face_texture_mean(colors, faces)
+    cam = ora.make_camera(downward_view(4, 100, 200), 100, 0, 0, 200, 200)
+    ctx = _context(torch, lib, verts.astype(np.float32), faces)
+    p2f = ctx.rasterize([_to_gg(lib, cam)])
+    render = ctx.render_flat(p2f[0], torch.from_numpy(tex).cuda()).cpu().numpy()
+    assert render.shape == (200, 200, 3)
+    assert np.allclose(render[fill[:, 0], fill[:, 1]], [255, 0, 0])
+    assert np.allclose(render[empty[:, 0], empty[:, 1]], [80, 80, 80])
+    np.testing.assert_array_equal(p2f[0].cpu().numpy(), ora.rasterize(verts.astype(np.float32), faces, cam))
+
+
+def _agg(torch, lib, ctx, p2f, preds, kind, C, mode, flags, F):
+    d_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda")
+    d_count = torch.zeros((F,), dtype=torch.int32, device="cuda")
+    for k in range(len(preds)):
+        ctx.aggregate(p2f[k], preds[k], kind, C, mode, flags, d_sum, d_count)
+    avg, argmax = ctx.finalize(d_sum, d_count)
+    torch.cuda.synchronize()
+    return avg.cpu().numpy(), d_count.cpu().numpy(), d_sum.cpu().numpy(), argmax.cpu().numpy()
+
+
+def _eq(a, b):
+    np.testing.assert_array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
+
+
+def test_aggregate_golden(torch, lib, golden_scene, golden_aggregate):
+    """Stage 3 + epilogue against the outputs of the reference's own aggregate_projected_images."""
+    g, a = golden_scene, golden_aggregate
+    F = g["faces"].shape[0]
+    v32 = (g["verts"] - g["origin"]).astype(np.float32)
+    ctx = _context(torch, lib, v32, g["faces"])
+    p2f = torch.from_numpy(g["pix2face"]).cuda()
+    C = a["avg1"].shape[1]
+    compat = lib.FLAG_COMPAT_NEGATIVE_INDEX
+    # (1) class-index image expanded on the fly == the reference's one-hot path
+    idx = [torch.from_numpy(i).cuda() for i in a["idx_imgs"]]
+    avg, cnt, summed, am = _agg(torch, lib, ctx, p2f, idx, lib.PRED_INDEX_U8, C, lib.MODE_LAST_PIXEL, compat, F)
+    _eq(avg, a["avg1"]); _eq(cnt, a["counts1"]); _eq(summed, a["summed1"]); _eq(am, a["argmax1"])
+    # (1b) explicit (H,W,C) bool one-hot
+    oh = [torch.from_numpy(ora.inds_to_one_hot(i, C).view(np.uint8)).cuda() for i in a["idx_imgs"]]
+    avg, cnt, summed, _ = _agg(torch, lib, ctx, p2f, oh, lib.PRED_U8, C, lib.MODE_LAST_PIXEL, compat, F)
+    _eq(avg, a["avg1"]); _eq(cnt, a["counts1"]); _eq(summed, a["summed1"])
+    # (2) float32 scores with NaN holes, three views: bit-exact float64 sums in view order
+    soft = [torch.from_numpy(s).cuda() for s in a["soft"]]
+    avg, cnt, summed, am = _agg(torch, lib, ctx, p2f, soft, lib.PRED_F32, C, lib.MODE_LAST_PIXEL, compat, F)
+    _eq(avg, a["avg2"]); _eq(cnt, a["counts2"]); _eq(summed, a["summed2"]); _eq(am, a["argmax2"][:, 0])
+    # (2b) same as float64 input
+    soft64 = [s.double() for s in soft]
+    avg, cnt, summed, _ = _agg(torch, lib, ctx, p2f, soft64, lib.PRED_F64, C, lib.MODE_LAST_PIXEL, compat, F)
+    _eq(avg, a["avg2"]); _eq(cnt, a["counts2"])
+    # (2c) single view keeps per-channel NaNs (meshes.py:2056-2057)
+    avg, cnt, summed, _ = _agg(torch, lib, ctx, p2f[:1], soft[:1], lib.PRED_F32, C, lib.MODE_LAST_PIXEL,
+                               compat | lib.FLAG_KEEP_NAN, F)
+    _eq(avg, a["avg2s"]); _eq(cnt, a["counts2s"]); _eq(summed, a["summed2s"])
+    # (3) one-hot votes
+    nv = int(a["n_vote_classes"])
+    votes = [torch.from_numpy(v).cuda() for v in a["vote_imgs"]]
+    avg, cnt, summed, _ = _agg(torch, lib, ctx, p2f, votes, lib.PRED_F64, nv, lib.MODE_VOTE, compat, F)
+    _eq(cnt, a["counts3"]); _eq(summed, a["summed3"])
+    _eq(np.nan_to_num(avg, nan=0.0), a["avg3"])  # scipy's sparse product leaves unseen faces at 0, not NaN
+
+
+def test_render_flat_golden(torch, lib, golden_scene, golden_render):
+    g, r = golden_scene, golden_render
+    v32 = (g["verts"] - g["origin"]).astype(np.float32)
+    ctx = _context(torch, lib, v32, g["faces"])
+    p2f = torch.from_numpy(g["pix2face"]).cuda()
+    for key_t, key_r in [("tex1", "render1"), ("tex3", "render3")]:
+        out = ctx.render_flat(p2f, torch.from_numpy(r[key_t]).cuda()).cpu().numpy()
+        _eq(out, r[key_r])
+        u8 = ctx.render_flat(p2f, torch.from_numpy(r[key_t]).cuda(), out_dtype=lib.OUT_U8).cpu().numpy()
+        for k in range(len(u8)):
+            np.testing.assert_array_equal(np.squeeze(u8[k]), ora.cast_render_to_uint8(r[key_r][k]))
+
+
+def test_pixel_sum_mode_matches_numpy(torch, lib, golden_scene, golden_aggregate):
+    g, a = golden_scene, golden_aggregate
+    F = g["faces"].shape[0]
+    v32 = (g["verts"] - g["origin"]).astype(np.float32)
+    ctx = _context(torch, lib, v32, g["faces"])
+    p2f_np = g["pix2face"].astype(np.int64)
+    p2f = torch.from_numpy(g["pix2face"]).cuda()
+    soft = a["soft"].copy()
+    C = soft.shape[-1]
+    preds = [torch.from_numpy(s).cuda() for s in soft]
+    avg, cnt, summed, _ = _agg(torch, lib, ctx, p2f, preds, lib.PRED_F32, C, lib.MODE_PIXEL_SUM, 0, F)
+    ref_sum = np.zeros((F, C))
+    ref_cnt = np.zeros(F, dtype=np.int64)
+    for k in range(len(soft)):
+        ids = p2f_np[k].ravel()
+        keep = ids >= 0
+        vals = np.nan_to_num(soft[k].reshape(-1, C).astype(np.float64), nan=0.0)
+        np.add.at(ref_sum, ids[keep], vals[keep])
+        np.add.at(ref_cnt, ids[keep], 1)
+    np.testing.assert_array_equal(cnt, ref_cnt)
+    seen = ref_cnt > 0
+    np.testing.assert_allclose(summed[seen], ref_sum[seen], rtol=1e-9, atol=1e-12)
+
+
+def test_same_bits_across_runs(torch, lib):
+    v32, faces, cams, _ = _scene("c1", 3)
+    ctx = _context(torch, lib, v32, faces)
+    gg = [_to_gg(lib, c) for c in cams]
+    a = ctx.rasterize(gg).clone()
+    for _ in range(3):
+        assert torch.equal(a, ctx.rasterize(gg))
+
+
+def test_mixed_sizes_rejected(torch, lib):
+    v32, faces, cams, _ = _scene("tiny", 2)
+    ctx = _context(torch, lib, v32, faces)
+    gg = [_to_gg(lib, c) for c in cams]
+    gg[1].W = gg[1].W - 1
+    with pytest.raises(lib.GeograypherB200Error, match="same image size"):
+        ctx.rasterize(gg)
