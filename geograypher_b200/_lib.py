@@ -21,13 +21,14 @@ MAX_VIEWS_PER_CALL = 32
 PRED_F32, PRED_F64, PRED_U8, PRED_INDEX_U8 = 0, 1, 2, 3
 MODE_LAST_PIXEL, MODE_PIXEL_SUM, MODE_VOTE = 0, 1, 2
 OUT_F64, OUT_F32, OUT_U8 = 0, 1, 2
-FLAG_COMPAT_NEGATIVE_INDEX, FLAG_KEEP_NAN = 1, 2
+FLAG_COMPAT_NEGATIVE_INDEX, FLAG_KEEP_NAN, FLAG_ASSIGN = 1, 2, 4
 ERR_OVERFLOW = -4
 
 EXPORTS = [
     "gg_abi_version", "gg_last_error", "gg_create", "gg_destroy", "gg_sync", "gg_reserve",
     "gg_last_batch_stats", "gg_set_mesh", "gg_project", "gg_rasterize", "gg_aggregate",
-    "gg_project_aggregate", "gg_finalize", "gg_render_flat",
+    "gg_project_aggregate", "gg_finalize", "gg_render_flat", "gg_stage_count", "gg_stage_name", "gg_profile",
+    "gg_profile_read",
 ]
 
 
@@ -89,8 +90,12 @@ def load():
     lib.gg_project_aggregate.argtypes = [vp, camp, i32, ctypes.POINTER(vp), i32, i32, i32, i32, vp, vp, vp, vp]
     lib.gg_finalize.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
     lib.gg_render_flat.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp]
+    lib.gg_stage_name.argtypes = [i32]
+    lib.gg_stage_name.restype = ctypes.c_char_p
+    lib.gg_profile.argtypes = [vp, i32]
+    lib.gg_profile_read.argtypes = [vp, vp, vp, i32]
     for name in EXPORTS:
-        if name not in ("gg_last_error", "gg_destroy"):
+        if name not in ("gg_last_error", "gg_destroy", "gg_stage_name"):
             getattr(lib, name).restype = i32
     _lib = lib
     return lib
@@ -178,6 +183,18 @@ class Context:
 
     def reserve(self, max_faces_per_view=0, max_bin_entries_per_view=0):
         _check(self.lib.gg_reserve(self.handle, int(max_faces_per_view), int(max_bin_entries_per_view)))
+
+    def profile(self, enable: bool):
+        """Bracket every kernel launch with CUDA events on its stream (per-stage timing for bench.py)."""
+        _check(self.lib.gg_profile(self.handle, 1 if enable else 0))
+
+    def profile_read(self, reset: bool = True):
+        """{stage: (milliseconds, launches)} accumulated since the last reset; synchronises the device."""
+        n = self.lib.gg_stage_count()
+        ms = np.zeros(n, dtype=np.float64)
+        launches = np.zeros(n, dtype=np.int64)
+        _check(self.lib.gg_profile_read(self.handle, ms.ctypes.data, launches.ctypes.data, 1 if reset else 0))
+        return {self.lib.gg_stage_name(i).decode(): (float(ms[i]), int(launches[i])) for i in range(n)}
 
     def last_batch_stats(self, n):
         out = np.zeros((n, 4), dtype=np.int64)

@@ -1,0 +1,4 @@
+from geograypher_b200.cameras.cameras import PhotogrammetryCamera, PhotogrammetryCameraSet
+from geograypher_b200.cameras.segmentor import SegmentorPhotogrammetryCameraSet
+
+__all__ = ["PhotogrammetryCamera", "PhotogrammetryCameraSet", "SegmentorPhotogrammetryCameraSet"]

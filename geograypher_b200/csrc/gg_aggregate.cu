@@ -13,8 +13,10 @@
 
 namespace {
 
-#define GG_FLAG_COMPAT_NEG 1  // meshes.py:2000: background pixels (-1) index face F-1
-#define GG_FLAG_KEEP_NAN 2    // single-view corner of meshes.py:2056-2057: the first projection keeps its NaNs
+// GG_FLAG_COMPAT_NEG (1): meshes.py:2000, background pixels (-1) index face F-1
+// GG_FLAG_KEEP_NAN (2): single-view corner of meshes.py:2056-2057, the first projection keeps its NaNs
+// GG_FLAG_ASSIGN (4): project_images (meshes.py:1991-2002), write the face's row instead of accumulating;
+//                     count[f] = 1 marks a row that was written
 
 // ---- pass A: last pixel (row-major) of every face in this raster -------------------------------------
 // One thread handles 4 consecutive pixels; it issues an atomicMax only for the last pixel of each run of equal
@@ -65,6 +67,11 @@ __global__ void __launch_bounds__(256) k_resolve_dense(int32_t *__restrict__ win
     if (p < 0) return;
     winner[f] = -1;
     bool any_finite = false;
+    if (flags & GG_FLAG_ASSIGN) {
+        for (int c = 0; c < C; ++c) sum[f * C + c] = load_score(pred, (int64_t)p * C + c);
+        count[f] = 1;
+        return;
+    }
     for (int c = 0; c < C; ++c) {
         const double v = load_score(pred, (int64_t)p * C + c);
         any_finite = any_finite || isfinite(v);
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(256) k_resolve_dense(int32_t *__restrict__ win
 }
 
 __global__ void __launch_bounds__(256) k_resolve_index(int32_t *__restrict__ winner, int64_t F,
-                                                       const uint8_t *__restrict__ pred, int C,
+                                                       const uint8_t *__restrict__ pred, int C, int flags,
                                                        double *__restrict__ sum, int32_t *__restrict__ count) {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
@@ -82,6 +89,11 @@ __global__ void __launch_bounds__(256) k_resolve_index(int32_t *__restrict__ win
     if (p < 0) return;
     winner[f] = -1;
     const int cls = pred[p];
+    if (flags & GG_FLAG_ASSIGN) {
+        for (int c = 0; c < C; ++c) sum[f * C + c] = (c == cls) ? 1.0 : 0.0;
+        count[f] = 1;
+        return;
+    }
     if (cls < C) sum[f * C + cls] += 1.0;
     count[f] += 1;  // a one-hot row is always finite, even the all-zero row of an ignored pixel
 }
@@ -199,8 +211,7 @@ static int ensure_winner(gg_context *ctx, cudaStream_t st) {
     }
     GG_CUDA(cudaMalloc(&ctx->d_winner, (size_t)ctx->F * 4));
     ctx->winner_cap = ctx->F;
-    k_fill_i32<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->d_winner, ctx->F, -1);
-    GG_CUDA(cudaGetLastError());
+    GG_LAUNCH(ctx, GG_ST_MISC, st, k_fill_i32<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->d_winner, ctx->F, -1));
     return GG_OK;
 }
 
@@ -215,52 +226,49 @@ int gg_launch_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W
     if (mode == GG_MODE_PIXEL_SUM) {
         const unsigned g = (unsigned)((P + 255) / 256);
         switch (pred_kind) {
-            case GG_PRED_F32: k_pixel_sum<float><<<g, 256, 0, st>>>(d_pix2face, P, (const float *)d_pred, C, 0, d_sum, d_count); break;
-            case GG_PRED_F64: k_pixel_sum<double><<<g, 256, 0, st>>>(d_pix2face, P, (const double *)d_pred, C, 0, d_sum, d_count); break;
-            case GG_PRED_U8: k_pixel_sum<uint8_t><<<g, 256, 0, st>>>(d_pix2face, P, (const uint8_t *)d_pred, C, 0, d_sum, d_count); break;
-            case GG_PRED_INDEX_U8: k_pixel_sum<uint8_t><<<g, 256, 0, st>>>(d_pix2face, P, (const uint8_t *)d_pred, C, 1, d_sum, d_count); break;
+            case GG_PRED_F32: GG_LAUNCH(ctx, GG_ST_PIXEL_SUM, st, k_pixel_sum<float><<<g, 256, 0, st>>>(d_pix2face, P, (const float *)d_pred, C, 0, d_sum, d_count)); break;
+            case GG_PRED_F64: GG_LAUNCH(ctx, GG_ST_PIXEL_SUM, st, k_pixel_sum<double><<<g, 256, 0, st>>>(d_pix2face, P, (const double *)d_pred, C, 0, d_sum, d_count)); break;
+            case GG_PRED_U8: GG_LAUNCH(ctx, GG_ST_PIXEL_SUM, st, k_pixel_sum<uint8_t><<<g, 256, 0, st>>>(d_pix2face, P, (const uint8_t *)d_pred, C, 0, d_sum, d_count)); break;
+            case GG_PRED_INDEX_U8: GG_LAUNCH(ctx, GG_ST_PIXEL_SUM, st, k_pixel_sum<uint8_t><<<g, 256, 0, st>>>(d_pix2face, P, (const uint8_t *)d_pred, C, 1, d_sum, d_count)); break;
             default: gg_set_error("gg_aggregate: bad pred_kind"); return GG_ERR_INVALID;
         }
-        GG_CUDA(cudaGetLastError());
         return GG_OK;
     }
     int rc = ensure_winner(ctx, st);
     if (rc != GG_OK) return rc;
     const int64_t threads = (P + 3) / 4;
-    k_last_pixel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_pix2face, P, (int32_t)(F - 1),
-                                                                    flags & GG_FLAG_COMPAT_NEG,
-                                                                    (((uintptr_t)d_pix2face) & 15) == 0, ctx->d_winner);
-    GG_CUDA(cudaGetLastError());
+    GG_LAUNCH(ctx, GG_ST_LAST_PIXEL, st,
+              k_last_pixel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_pix2face, P, (int32_t)(F - 1),
+                                                                              flags & GG_FLAG_COMPAT_NEG,
+                                                                              (((uintptr_t)d_pix2face) & 15) == 0,
+                                                                              ctx->d_winner));
     const unsigned gf = (unsigned)((F + 255) / 256);
     if (mode == GG_MODE_LAST_PIXEL) {
         switch (pred_kind) {
-            case GG_PRED_F32: k_resolve_dense<float><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const float *)d_pred, C, flags, d_sum, d_count); break;
-            case GG_PRED_F64: k_resolve_dense<double><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const double *)d_pred, C, flags, d_sum, d_count); break;
-            case GG_PRED_U8: k_resolve_dense<uint8_t><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const uint8_t *)d_pred, C, flags, d_sum, d_count); break;
-            case GG_PRED_INDEX_U8: k_resolve_index<<<gf, 256, 0, st>>>(ctx->d_winner, F, (const uint8_t *)d_pred, C, d_sum, d_count); break;
+            case GG_PRED_F32: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_dense<float><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const float *)d_pred, C, flags, d_sum, d_count)); break;
+            case GG_PRED_F64: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_dense<double><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const double *)d_pred, C, flags, d_sum, d_count)); break;
+            case GG_PRED_U8: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_dense<uint8_t><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const uint8_t *)d_pred, C, flags, d_sum, d_count)); break;
+            case GG_PRED_INDEX_U8: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_index<<<gf, 256, 0, st>>>(ctx->d_winner, F, (const uint8_t *)d_pred, C, flags, d_sum, d_count)); break;
             default: gg_set_error("gg_aggregate: bad pred_kind"); return GG_ERR_INVALID;
         }
     } else if (mode == GG_MODE_VOTE) {
         switch (pred_kind) {
-            case GG_PRED_F32: k_resolve_vote<float><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const float *)d_pred, C, d_sum, d_count); break;
-            case GG_PRED_F64: k_resolve_vote<double><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const double *)d_pred, C, d_sum, d_count); break;
+            case GG_PRED_F32: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_vote<float><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const float *)d_pred, C, d_sum, d_count)); break;
+            case GG_PRED_F64: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_vote<double><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const double *)d_pred, C, d_sum, d_count)); break;
             case GG_PRED_U8:
-            case GG_PRED_INDEX_U8: k_resolve_vote<uint8_t><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const uint8_t *)d_pred, C, d_sum, d_count); break;
+            case GG_PRED_INDEX_U8: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_vote<uint8_t><<<gf, 256, 0, st>>>(ctx->d_winner, F, (const uint8_t *)d_pred, C, d_sum, d_count)); break;
             default: gg_set_error("gg_aggregate: bad pred_kind"); return GG_ERR_INVALID;
         }
     } else {
         gg_set_error("gg_aggregate: bad mode");
         return GG_ERR_INVALID;
     }
-    GG_CUDA(cudaGetLastError());
     return GG_OK;
 }
 
 int gg_launch_finalize(gg_context *ctx, double *d_sum, const int32_t *d_count, int64_t F, int C, double *d_avg,
                        double *d_argmax, cudaStream_t st) {
-    (void)ctx;
-    k_finalize<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(d_sum, d_count, F, C, d_avg, d_argmax);
-    GG_CUDA(cudaGetLastError());
+    GG_LAUNCH(ctx, GG_ST_FINALIZE, st, k_finalize<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(d_sum, d_count, F, C, d_avg, d_argmax));
     return GG_OK;
 }
 
@@ -269,11 +277,10 @@ int gg_launch_render_flat(gg_context *ctx, const int32_t *d_pix2face, int64_t P,
     const int64_t want = (P + 255) / 256;
     const unsigned g = (unsigned)(want < (int64_t)ctx->sm_count * 32 ? (want > 0 ? want : 1) : ctx->sm_count * 32);
     switch (out_dtype) {
-        case GG_OUT_F64: k_render_flat<double><<<g, 256, 0, st>>>(d_pix2face, P, d_tex, D, (double *)d_out); break;
-        case GG_OUT_F32: k_render_flat<float><<<g, 256, 0, st>>>(d_pix2face, P, d_tex, D, (float *)d_out); break;
-        case GG_OUT_U8: k_render_flat<uint8_t><<<g, 256, 0, st>>>(d_pix2face, P, d_tex, D, (uint8_t *)d_out); break;
+        case GG_OUT_F64: GG_LAUNCH(ctx, GG_ST_RENDER_FLAT, st, k_render_flat<double><<<g, 256, 0, st>>>(d_pix2face, P, d_tex, D, (double *)d_out)); break;
+        case GG_OUT_F32: GG_LAUNCH(ctx, GG_ST_RENDER_FLAT, st, k_render_flat<float><<<g, 256, 0, st>>>(d_pix2face, P, d_tex, D, (float *)d_out)); break;
+        case GG_OUT_U8: GG_LAUNCH(ctx, GG_ST_RENDER_FLAT, st, k_render_flat<uint8_t><<<g, 256, 0, st>>>(d_pix2face, P, d_tex, D, (uint8_t *)d_out)); break;
         default: gg_set_error("gg_render_flat: bad out_dtype"); return GG_ERR_INVALID;
     }
-    GG_CUDA(cudaGetLastError());
     return GG_OK;
 }

@@ -99,6 +99,11 @@ void gg_destroy(gg_context *ctx) {
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_winner);
     cudaFree(ctx->d_raster);
+    for (auto &p : ctx->prof.pending) {
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    for (auto e : ctx->prof.pool) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -118,6 +123,43 @@ int gg_sync(gg_context *ctx, void *stream) {
                      i, c[1], (long long)ctx->cap_recs, c[2], (long long)ctx->cap_bins);
             gg_set_error(buf);
             return GG_ERR_OVERFLOW;
+        }
+    }
+    return GG_OK;
+}
+
+static const char *k_stage_names[GG_ST_COUNT] = {"mesh_setup", "project", "cull_blocks", "setup_faces", "scan_tiles",
+                                                   "fill_bins", "raster_tiles", "last_pixel", "resolve", "pixel_sum",
+                                                   "finalize", "render_flat", "misc"};
+
+int gg_stage_count(void) { return GG_ST_COUNT; }
+
+const char *gg_stage_name(int stage) { return (stage >= 0 && stage < GG_ST_COUNT) ? k_stage_names[stage] : ""; }
+
+int gg_profile(gg_context *ctx, int enable) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    ctx->prof.on = enable != 0;
+    return GG_OK;
+}
+
+int gg_profile_read(gg_context *ctx, double *h_ms, int64_t *h_launches, int reset) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    GG_CUDA(cudaDeviceSynchronize());
+    for (auto &p : ctx->prof.pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->prof.ms[p.stage] += ms;
+        ctx->prof.pool.push_back(p.a);
+        ctx->prof.pool.push_back(p.b);
+    }
+    ctx->prof.pending.clear();
+    for (int i = 0; i < GG_ST_COUNT; ++i) {
+        if (h_ms) h_ms[i] = ctx->prof.ms[i];
+        if (h_launches) h_launches[i] = ctx->prof.launches[i];
+        if (reset) {
+            ctx->prof.ms[i] = 0;
+            ctx->prof.launches[i] = 0;
         }
     }
     return GG_OK;
@@ -177,8 +219,8 @@ int gg_set_mesh(gg_context *ctx, const float *d_verts, int64_t V, const int32_t 
     GG_CUDA(cudaMalloc(&d_bad, sizeof(int)));
     GG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
     const int64_t n = V > F ? V : F;
-    k_pack_mesh<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_verts, V, d_faces, F, ctx->d_verts, ctx->d_faces, d_bad);
-    GG_CUDA(cudaGetLastError());
+    GG_LAUNCH(ctx, GG_ST_MESH, st,
+              k_pack_mesh<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_verts, V, d_faces, F, ctx->d_verts, ctx->d_faces, d_bad));
     int bad = 0;
     GG_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     GG_CUDA(cudaStreamSynchronize(st));

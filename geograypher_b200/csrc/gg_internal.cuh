@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/geograypher_b200.h"
 
@@ -46,8 +47,38 @@ struct GGViewBatch {
     GGViewScratch v[GG_MAX_VIEWS_PER_CALL];
 };
 
+// ---- per-stage launch counting and (optional) CUDA-event timing ------------------------------------------
+enum GGStage {
+    GG_ST_MESH = 0, GG_ST_PROJECT, GG_ST_CULL, GG_ST_SETUP, GG_ST_SCAN, GG_ST_FILL, GG_ST_RASTER, GG_ST_LAST_PIXEL,
+    GG_ST_RESOLVE, GG_ST_PIXEL_SUM, GG_ST_FINALIZE, GG_ST_RENDER_FLAT, GG_ST_MISC, GG_ST_COUNT
+};
+
+struct GGProfPending {
+    int stage;
+    cudaEvent_t a, b;
+};
+
+struct GGProfiler {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    std::vector<GGProfPending> pending;
+    double ms[GG_ST_COUNT] = {0};
+    int64_t launches[GG_ST_COUNT] = {0};
+    cudaEvent_t get() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
 struct gg_context {
     int device = 0;
+    GGProfiler prof;
     // mesh
     int64_t V = 0, F = 0;
     float4 *d_verts = nullptr;   // [V] xyz + pad
@@ -73,6 +104,25 @@ struct gg_context {
 
 void gg_set_error(const std::string &msg);
 int gg_cuda_fail(cudaError_t e, const char *what);
+
+// Launch a kernel (or any stream operation) under a stage label: counts it, and brackets it with events when
+// profiling is enabled.  Usage: GG_LAUNCH(ctx, GG_ST_RASTER, st, k_raster<<<g, b, 0, st>>>(...));
+#define GG_LAUNCH(ctx, stage, st, ...)                                      \
+    do {                                                                    \
+        GGProfPending _p{stage, nullptr, nullptr};                          \
+        if ((ctx)->prof.on) {                                               \
+            _p.a = (ctx)->prof.get();                                       \
+            _p.b = (ctx)->prof.get();                                       \
+            cudaEventRecord(_p.a, st);                                      \
+        }                                                                   \
+        __VA_ARGS__;                                                        \
+        (ctx)->prof.launches[stage] += 1;                                   \
+        if ((ctx)->prof.on) {                                               \
+            cudaEventRecord(_p.b, st);                                      \
+            (ctx)->prof.pending.push_back(_p);                              \
+        }                                                                   \
+        GG_CUDA(cudaGetLastError());                                        \
+    } while (0)
 
 #define GG_CUDA(call)                                            \
     do {                                                         \

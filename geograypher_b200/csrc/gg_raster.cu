@@ -578,9 +578,9 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
 }
 
 int gg_launch_mesh_blocks(gg_context *ctx, cudaStream_t st) {
-    k_mesh_blocks<<<(unsigned)ctx->n_blocks, GG_BLOCK_FACES, 0, st>>>(ctx->d_verts, ctx->d_faces, ctx->F,
-                                                                       ctx->d_block_lo, ctx->d_block_hi);
-    GG_CUDA(cudaGetLastError());
+    GG_LAUNCH(ctx, GG_ST_MESH, st,
+              k_mesh_blocks<<<(unsigned)ctx->n_blocks, GG_BLOCK_FACES, 0, st>>>(ctx->d_verts, ctx->d_faces, ctx->F,
+                                                                                 ctx->d_block_lo, ctx->d_block_hi));
     return GG_OK;
 }
 
@@ -590,8 +590,7 @@ int gg_launch_project(gg_context *ctx, const gg_camera *cams, int n, int32_t *dX
     for (int i = 0; i < n; ++i) cb.cam[i] = cams[i];
     const int64_t want = (ctx->V + 255) / 256;
     const unsigned gx = (unsigned)(want < (int64_t)ctx->sm_count * 16 ? (want > 0 ? want : 1) : ctx->sm_count * 16);
-    k_project<<<dim3(gx, n), 256, 0, st>>>(ctx->d_verts, ctx->V, cb, dX, dY, dinvz, dvalid);
-    GG_CUDA(cudaGetLastError());
+    GG_LAUNCH(ctx, GG_ST_PROJECT, st, k_project<<<dim3(gx, n), 256, 0, st>>>(ctx->d_verts, ctx->V, cb, dX, dY, dinvz, dvalid));
     return GG_OK;
 }
 
@@ -611,17 +610,15 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
     }
     ctx->last_batch_n = n;
     const int nb = (int)ctx->n_blocks;
-    k_cull_blocks<<<dim3((nb + 255) / 256, n), 256, 0, st>>>(ctx->d_block_lo, ctx->d_block_hi, nb, cb, ctx->views);
-    GG_CUDA(cudaGetLastError());
+    GG_LAUNCH(ctx, GG_ST_CULL, st,
+              k_cull_blocks<<<dim3((nb + 255) / 256, n), 256, 0, st>>>(ctx->d_block_lo, ctx->d_block_hi, nb, cb, ctx->views));
     const int gsetup = nb < ctx->sm_count * 8 ? nb : ctx->sm_count * 8;
-    k_setup_faces<<<dim3(gsetup, n), GG_BLOCK_FACES, 0, st>>>(ctx->d_verts, ctx->d_faces, ctx->F, ctx->cap_recs, cb,
-                                                              ctx->views);
-    GG_CUDA(cudaGetLastError());
-    k_scan_tiles<<<n, 1024, 0, st>>>(n_tiles, ctx->cap_recs, ctx->cap_bins, ctx->views);
-    GG_CUDA(cudaGetLastError());
-    k_fill_bins<<<dim3(ctx->sm_count * 4, n), 256, 0, st>>>(cb, ctx->views);
-    GG_CUDA(cudaGetLastError());
-    k_raster_tiles<<<dim3(tiles_x, tiles_y, n), GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, d_pix2face, d_depth);
-    GG_CUDA(cudaGetLastError());
+    GG_LAUNCH(ctx, GG_ST_SETUP, st,
+              k_setup_faces<<<dim3(gsetup, n), GG_BLOCK_FACES, 0, st>>>(ctx->d_verts, ctx->d_faces, ctx->F, ctx->cap_recs,
+                                                                        cb, ctx->views));
+    GG_LAUNCH(ctx, GG_ST_SCAN, st, k_scan_tiles<<<n, 1024, 0, st>>>(n_tiles, ctx->cap_recs, ctx->cap_bins, ctx->views));
+    GG_LAUNCH(ctx, GG_ST_FILL, st, k_fill_bins<<<dim3(ctx->sm_count * 4, n), 256, 0, st>>>(cb, ctx->views));
+    GG_LAUNCH(ctx, GG_ST_RASTER, st,
+              k_raster_tiles<<<dim3(tiles_x, tiles_y, n), GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, d_pix2face, d_depth));
     return GG_OK;
 }

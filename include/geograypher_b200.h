@@ -91,6 +91,14 @@ int gg_reserve(gg_context *ctx, int64_t max_faces_per_view, int64_t max_bin_entr
    n_face_records, n_bin_entries, overflow_flag].  out must hold 4*n int64. */
 int gg_last_batch_stats(gg_context *ctx, int n, int64_t *h_out);
 
+/* ---- instrumentation: every kernel launch is counted per stage; with gg_profile(ctx, 1) each launch is also
+        bracketed by CUDA events on its stream.  gg_profile_read synchronises the device and returns the
+        accumulated milliseconds and launch counts per stage (arrays of gg_stage_count() entries). ---------- */
+int gg_stage_count(void);
+const char *gg_stage_name(int stage);
+int gg_profile(gg_context *ctx, int enable);
+int gg_profile_read(gg_context *ctx, double *h_ms, int64_t *h_launches, int reset);
+
 /* ---- mesh (replaces the per-call pv.PolyData / pytorch3d Meshes construction, meshes.py:1806-1817,
         derived_meshes.py:592-640).  d_verts: V x 3 float32 in the camera set's local frame (after
         get_mesh_in_cameras_coords, meshes.py:1641-1676, minus the origin shift); d_faces: F x 3 int32.
@@ -112,7 +120,14 @@ int gg_rasterize(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_pix
         (project_images + the accumulation of aggregate_projected_images, meshes.py:1988-2001, 2056-2067;
         vote mode: derived_meshes.py:480-520).  d_sum: F x C float64 (vote mode: F x n_classes),
         d_count: F int32; both are accumulated into, so zero them before the first view.
-        compat_negative_index != 0 reproduces meshes.py:2000 (background pixels index face F-1). -------- */
+        `compat_negative_index` is a bit mask: GG_FLAG_COMPAT_NEG reproduces meshes.py:2000 (background
+        pixels index face F-1); GG_FLAG_KEEP_NAN keeps NaN scores instead of turning them into 0 (what the
+        reference does when the whole aggregation has a single view, meshes.py:2056-2057); GG_FLAG_ASSIGN
+        writes the face rows instead of accumulating (project_images' per-view output; count[f]=1 marks
+        written rows). ------------------------------------------------------------------------------------ */
+#define GG_FLAG_COMPAT_NEG 1
+#define GG_FLAG_KEEP_NAN 2
+#define GG_FLAG_ASSIGN 4
 int gg_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred, int pred_kind,
                  int C, int mode, int compat_negative_index, double *d_sum, int32_t *d_count, void *stream);
 

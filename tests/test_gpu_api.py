@@ -1,0 +1,143 @@
+"""GPU tests through the reference-facing Python API (TexturedPhotogrammetryMesh & co)."""
+from itertools import product
+
+import numpy as np
+import pytest
+
+import geograypher_b200 as gg
+from oracle import oracle as ora
+
+pytestmark = pytest.mark.gpu
+
+
+def _eq(a, b):
+    np.testing.assert_array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
+
+
+@pytest.fixture(scope="module")
+def scene(golden_scene):
+    g = golden_scene
+    f, cx, cy, W, H = g["intrinsics"]
+    cams = gg.PhotogrammetryCameraSet(
+        cameras=[gg.PhotogrammetryCamera(f"/golden/{i:04d}.png", T, f, cx, cy, int(W), int(H))
+                 for i, T in enumerate(g["c2ws"])],
+        local_to_epsg_4978_transform=np.eye(4),
+    )
+    return g, cams
+
+
+def test_pix2face_contract(scene):
+    g, cams = scene
+    mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]))
+    p2f = mesh.pix2face(cams, apply_distortion=False)
+    assert p2f.dtype == np.int64 and p2f.shape == g["pix2face"].shape
+    np.testing.assert_array_equal(p2f, g["pix2face"])
+    one = mesh.pix2face(cams[1], apply_distortion=False)
+    assert one.shape == g["pix2face"].shape[1:]
+    np.testing.assert_array_equal(one, g["pix2face"][1])
+    assert mesh.pix2face(cams[0:1], apply_distortion=False).shape == (1,) + one.shape  # length-1 set keeps the dim
+    with pytest.raises(TypeError):
+        mesh.pix2face([1, 2, 3])
+    with pytest.raises(NotImplementedError):  # reference tests/test_derived_cameras.py:318-337
+        mesh.pix2face(cameras=cams, cache_folder=None, distortion_set=cams, apply_distortion=True)
+
+
+def test_local_frame_transform(scene):
+    """get_mesh_in_cameras_coords: an ECEF-like mesh + a similarity local->ECEF transform give the same rasters."""
+    g, cams0 = scene
+    f, cx, cy, W, H = g["intrinsics"]
+    ang = 0.3
+    R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1.0]])
+    T = np.eye(4)
+    T[:3, :3] = 12.354 * R
+    T[:3, 3] = [-2.6e6, -4.3e6, 3.9e6]  # ECEF-sized offset
+    ecef = g["verts"] @ T[:3, :3].T + T[:3, 3]
+    cams = gg.PhotogrammetryCameraSet(
+        cameras=[gg.PhotogrammetryCamera(None, Tc, f, cx, cy, int(W), int(H)) for Tc in g["c2ws"]],
+        local_to_epsg_4978_transform=T,
+    )
+    mesh = gg.TexturedPhotogrammetryMesh((ecef, g["faces"]), input_CRS="EPSG:4978")
+    p2f = mesh.pix2face(cams, apply_distortion=False)
+    # float64 round trip through a 4e6-sized offset moves vertices by ~1e-9 local units: allow a few flips at edges
+    assert (p2f != g["pix2face"]).mean() < 2e-3
+
+
+def test_aggregate_matches_reference_outputs(scene, golden_aggregate):
+    g, cams = scene
+    a = golden_aggregate
+    C = a["avg1"].shape[1]
+    mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), compat_negative_index=True, views_per_batch=2)
+    # class-index segmentor -> on-the-fly one-hot on the GPU
+    seg = gg.SegmentorPhotogrammetryCameraSet(cams, gg.ArraySegmentor(list(a["idx_imgs"]), num_classes=C, one_hot=True))
+    avg, info = mesh.aggregate_projected_images(seg, return_argmax=True)
+    _eq(avg, a["avg1"]); _eq(info["projection_counts"], a["counts1"]); _eq(info["summed_projections"], a["summed1"])
+    _eq(info["argmax"], a["argmax1"])
+    assert info["projection_counts"].dtype == float
+    # float predictions with NaNs
+    seg2 = gg.SegmentorPhotogrammetryCameraSet(cams, gg.ArraySegmentor(list(a["soft"]), num_classes=C))
+    avg, info = mesh.aggregate_projected_images(seg2, return_all=True)
+    _eq(avg, a["avg2"]); _eq(info["projection_counts"], a["counts2"]); _eq(info["summed_projections"], a["summed2"])
+    for k, proj in enumerate(info["all_projections"]):
+        _eq(proj, a["projs2"][k])
+    _eq(gg.find_argmax_nonzero_value(avg, keepdims=True), a["argmax2"])
+    # a single view keeps per-channel NaNs
+    avg, info = mesh.aggregate_projected_images(seg2.get_subset_cameras([0]))
+    _eq(avg, a["avg2s"]); _eq(info["summed_projections"], a["summed2s"])
+    # default (bug-free) mode differs from the reference on the last face only
+    mesh2 = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]))
+    avg, info = mesh2.aggregate_projected_images(seg2)
+    _eq(avg[:-1], a["avg2"][:-1]); _eq(info["projection_counts"][:-1], a["counts2"][:-1])
+
+
+def test_votes_match_reference_outputs(scene, golden_aggregate):
+    g, cams = scene
+    a = golden_aggregate
+    nv = int(a["n_vote_classes"])
+    mesh = gg.TexturedPhotogrammetryMeshIndexPredictions((g["verts"], g["faces"]), compat_negative_index=True)
+    seg = gg.SegmentorPhotogrammetryCameraSet(cams, gg.ArraySegmentor(list(a["vote_imgs"])))
+    avg, info = mesh.aggregate_projected_images(seg, n_classes=nv)
+    _eq(avg.toarray(), a["avg3"])
+    _eq(info["projection_counts"].toarray()[:, 0], a["counts3"])
+    _eq(info["summed_projections"].toarray(), a["summed3"])
+
+
+def test_render_flat_matches_reference_outputs(scene, golden_render):
+    g, cams = scene
+    r = golden_render
+    for key_t, key_r in [("tex1", "render1"), ("tex3", "render3")]:
+        mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), texture=r[key_t])
+        renders = list(mesh.render_flat(cams, apply_distortion=False))
+        assert len(renders) == len(cams)
+        for k, img in enumerate(renders):
+            assert img.dtype == np.float64
+            _eq(img, r[key_r][k])
+        img, cam = next(mesh.render_flat(cams, return_camera=True))
+        assert cam is cams[0]
+        u8 = next(mesh.render_flat_device(cams, out_dtype="uint8")).cpu().numpy()
+        np.testing.assert_array_equal(np.squeeze(u8[0]), ora.cast_render_to_uint8(r[key_r][0]))
+    with pytest.raises(TypeError):
+        list(mesh.render_flat("cameras"))
+
+
+@pytest.mark.parametrize("render_img_scale", [0.5, 0.7, 0.9, 1.0])
+def test_reference_structural_pins(render_img_scale):
+    """tests/test_derived_cameras.py:339-415 of the reference, undistorted half."""
+    from test_oracle_reference_pins import downward_view, plane_mesh
+
+    sensor = 2**8 + 1
+    verts, faces = plane_mesh()
+    cam = gg.PhotogrammetryCamera(None, downward_view(4, 100, sensor), 100, 0, 0, sensor, sensor)
+    cams = gg.PhotogrammetryCameraSet([cam])
+    mesh = gg.TexturedPhotogrammetryMesh((verts, faces))
+    ideal = mesh.pix2face(cameras=cams, cache_folder=None, render_img_scale=render_img_scale, apply_distortion=False)
+    assert len(ideal) == 1
+    ideal = ideal[0]
+    scaled = int(sensor * render_img_scale)
+    assert isinstance(ideal, np.ndarray) and ideal.dtype == np.int64 and ideal.shape == (scaled, scaled)
+    assert ideal.min() >= -1 and ideal.max() < len(faces) and ideal.max() > 0.95 * len(faces)
+    for corner in product([slice(None, 10), slice(-10, None)], repeat=2):
+        assert len(np.unique(ideal[corner])) > 1
+    np.testing.assert_array_equal(
+        ideal, ora.rasterize(verts.astype(np.float32) - 0, faces,
+                             ora.make_camera(cam.cam_to_world_transform, 100, 0, 0, sensor, sensor, render_img_scale,
+                                             origin=np.zeros(3))))
