@@ -105,7 +105,10 @@ def test_render_flat_matches_reference_outputs(scene, golden_render):
     g, cams = scene
     r = golden_render
     for key_t, key_r in [("tex1", "render1"), ("tex3", "render3")]:
-        mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), texture=r[key_t])
+        # set_texture stores the array as is; passing it to the constructor would remap a one-column texture to
+        # class IDs exactly like the reference's load_texture does (meshes.py:383-473)
+        mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]))
+        mesh.set_texture(r[key_t], is_vertex_texture=False)
         renders = list(mesh.render_flat(cams, apply_distortion=False))
         assert len(renders) == len(cams)
         for k, img in enumerate(renders):
