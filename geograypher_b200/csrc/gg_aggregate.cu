@@ -114,6 +114,52 @@ __global__ void __launch_bounds__(256) k_resolve_vote(int32_t *__restrict__ winn
     if (cls >= 0 && cls < C) sum[f * C + cls] += 1.0;
 }
 
+// ---- fused path: consume the per-record winners that k_raster_tiles<true> left for one view ---------------
+// One thread per face record of the view (grid-stride; the record count lives on the device).  The extra index
+// r == n_recs handles the meshes.py:2000 quirk when face F-1 has no record of its own.
+template <typename T>
+__global__ void __launch_bounds__(256) k_resolve_recs(GGViewScratch vs, int64_t F, const T *__restrict__ pred, int C,
+                                                      int pred_kind, int mode, int flags, double *__restrict__ sum,
+                                                      int32_t *__restrict__ count) {
+    const int n_recs = vs.counters[1];
+    const bool compat = (flags & GG_FLAG_COMPAT_NEG) != 0;
+    const int bg = compat ? vs.counters[4] : -1;
+    const int last_rec = vs.counters[5];
+    const int n = n_recs + ((compat && last_rec < 0) ? 1 : 0);
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        int p;
+        int64_t f;
+        if (r < n_recs) {
+            p = vs.winner[r];
+            f = vs.recs[r].face;
+            if (compat && r == last_rec) p = max(p, bg);
+        } else {
+            p = bg;
+            f = F - 1;
+        }
+        if (p < 0) continue;
+        if (mode == GG_MODE_VOTE) {
+            const double v = (double)pred[p];
+            if (!isfinite(v)) continue;
+            count[f] += 1;
+            const long long cls = (long long)v;
+            if (cls >= 0 && cls < C) sum[f * C + cls] += 1.0;
+        } else if (pred_kind == GG_PRED_INDEX_U8) {
+            const int cls = (int)pred[p];
+            if (cls < C) sum[f * C + cls] += 1.0;
+            count[f] += 1;
+        } else {
+            bool any_finite = false;
+            for (int c = 0; c < C; ++c) {
+                const double v = (double)pred[(int64_t)p * C + c];
+                any_finite = any_finite || isfinite(v);
+                if (!isnan(v) || (flags & GG_FLAG_KEEP_NAN)) sum[f * C + c] += v;
+            }
+            if (any_finite) count[f] += 1;
+        }
+    }
+}
+
 // ---- non-reference dense mode, unfused: every pixel adds its scores -------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) k_pixel_sum(const int32_t *__restrict__ p2f, int64_t P,
@@ -262,6 +308,21 @@ int gg_launch_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W
     } else {
         gg_set_error("gg_aggregate: bad mode");
         return GG_ERR_INVALID;
+    }
+    return GG_OK;
+}
+
+int gg_launch_resolve_view(gg_context *ctx, int view, const void *d_pred, int pred_kind, int C, int mode, int flags,
+                           double *d_sum, int32_t *d_count, cudaStream_t st) {
+    const GGViewScratch vs = ctx->views.v[view];
+    const unsigned g = (unsigned)(ctx->sm_count * 2);
+    const int64_t F = ctx->F;
+    switch (pred_kind) {
+        case GG_PRED_F32: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<float><<<g, 256, 0, st>>>(vs, F, (const float *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_F64: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<double><<<g, 256, 0, st>>>(vs, F, (const double *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_U8:
+        case GG_PRED_INDEX_U8: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<uint8_t><<<g, 256, 0, st>>>(vs, F, (const uint8_t *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        default: gg_set_error("gg_project_aggregate: bad pred_kind"); return GG_ERR_INVALID;
     }
     return GG_OK;
 }

@@ -257,24 +257,24 @@ int gg_rasterize(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_pix
         gg_set_error("gg_rasterize: d_pix2face is null");
         return GG_ERR_INVALID;
     }
-    return gg_launch_rasterize(ctx, h_cams, n, d_pix2face, d_depth, (cudaStream_t)stream);
+    return gg_launch_rasterize(ctx, h_cams, n, d_pix2face, d_depth, 0, 0, (cudaStream_t)stream);
 }
 
 int gg_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred, int pred_kind, int C,
-                 int mode, int compat_negative_index, double *d_sum, int32_t *d_count, void *stream) {
+                 int mode, int flags, double *d_sum, int32_t *d_count, void *stream) {
     int rc = check_ctx(ctx, true);
     if (rc != GG_OK) return rc;
     if (!d_pix2face || !d_pred || !d_sum || !d_count || H < 1 || W < 1 || C < 1) {
         gg_set_error("gg_aggregate: bad arguments");
         return GG_ERR_INVALID;
     }
-    return gg_launch_aggregate(ctx, d_pix2face, H, W, d_pred, pred_kind, C, mode, compat_negative_index, d_sum, d_count,
+    return gg_launch_aggregate(ctx, d_pix2face, H, W, d_pred, pred_kind, C, mode, flags, d_sum, d_count,
                                (cudaStream_t)stream);
 }
 
 int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const void *const *h_pred, int pred_kind,
-                         int C, int mode, int compat_negative_index, double *d_sum, int32_t *d_count,
-                         int32_t *d_pix2face, void *stream) {
+                         int C, int mode, int flags, double *d_sum, int32_t *d_count, int32_t *d_pix2face,
+                         void *stream) {
     int rc = check_ctx(ctx, true);
     if (rc != GG_OK) return rc;
     rc = check_cams(h_cams, n);
@@ -286,6 +286,22 @@ int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const 
     cudaStream_t st = (cudaStream_t)stream;
     const int W = h_cams[0].W, H = h_cams[0].H;
     const int64_t P = (int64_t)W * H;
+    if (P >= (1LL << 31)) {
+        gg_set_error("gg_project_aggregate: raster larger than 2^31 pixels");
+        return GG_ERR_INVALID;
+    }
+    if (mode == GG_MODE_LAST_PIXEL || mode == GG_MODE_VOTE) {
+        // Fused: the rasterizer leaves every face record's last pixel in scratch; the rasters never touch HBM
+        // unless the caller asked for them.  Views are resolved one after the other so that every face's float64
+        // sum is accumulated in view order (bit-identical to the reference's loop, meshes.py:2056-2062).
+        rc = gg_launch_rasterize(ctx, h_cams, n, d_pix2face, nullptr, 1, flags & GG_FLAG_COMPAT_NEG, st);
+        if (rc != GG_OK) return rc;
+        for (int i = 0; i < n; ++i) {
+            rc = gg_launch_resolve_view(ctx, i, h_pred[i], pred_kind, C, mode, flags, d_sum, d_count, st);
+            if (rc != GG_OK) return rc;
+        }
+        return GG_OK;
+    }
     int32_t *raster = d_pix2face;
     if (!raster) {
         const int64_t need = P * n;
@@ -300,11 +316,10 @@ int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const 
         }
         raster = ctx->d_raster;
     }
-    rc = gg_launch_rasterize(ctx, h_cams, n, raster, nullptr, st);
+    rc = gg_launch_rasterize(ctx, h_cams, n, raster, nullptr, 0, 0, st);
     if (rc != GG_OK) return rc;
     for (int i = 0; i < n; ++i) {
-        rc = gg_launch_aggregate(ctx, raster + P * i, H, W, h_pred[i], pred_kind, C, mode, compat_negative_index, d_sum,
-                                 d_count, st);
+        rc = gg_launch_aggregate(ctx, raster + P * i, H, W, h_pred[i], pred_kind, C, mode, flags, d_sum, d_count, st);
         if (rc != GG_OK) return rc;
     }
     return GG_OK;

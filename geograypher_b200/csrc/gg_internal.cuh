@@ -21,13 +21,17 @@
 #define GG_CHUNK 64            // faces staged in shared memory per pass
 #define GG_BLOCK_FACES 128     // faces per cull block
 
-struct GGFaceRec {             // one surviving face of one view, orientation-normalised (area2 > 0); 48 B
-    int32_t x0, y0, x1, y1, x2, y2;  // fixed-point screen coordinates (1/256 px)
-    float w0, w1, w2;                // 1/z_cam at the vertices
-    int32_t face;                    // face ID
-    uint16_t jmin, jmax, imin, imax; // pixel-centre index range, clamped to the raster
+#define GG_MAXL 1024           // tile-list positions whose face / record / winner live in shared memory
+
+struct GGFaceRec {  // one surviving face of one view, orientation-normalised (area2 > 0); 96 B
+    int32_t A[3], B[3];    // edge gradients in sub-pixel units: E_k(P) = A_k*Px + B_k*Py + const, A = -dy, B = dx
+    long long C[3];        // E_k at the centre of pixel (0,0), top-left bias folded in (>= 0 <=> inside)
+    double w00, gx, gy;    // 1/z plane per pixel: w(j, i) = w00 + gx*j + gy*i
+    float w0, w1, w2;      // 1/z_cam at the vertices (exact-depth path)
+    int32_t face;          // face ID
+    uint16_t jmin, jmax, imin, imax;  // pixel-centre index range, clamped to the raster
 };
-static_assert(sizeof(GGFaceRec) == 48, "GGFaceRec layout");
+static_assert(sizeof(GGFaceRec) == 96, "GGFaceRec layout");
 
 struct GGCamBatch {  // passed by value as a __grid_constant__ kernel parameter (<= 4 KB)
     gg_camera cam[GG_MAX_VIEWS_PER_CALL];
@@ -39,6 +43,7 @@ struct GGViewScratch {  // device pointers of one batch slot
     int32_t *tile_count;   // [n_tiles]   (reused as fill cursor)
     int32_t *tile_offset;  // [n_tiles + 1]
     int32_t *bins;         // [cap_bins]  record indices grouped by tile
+    int32_t *winner;       // [cap_recs]  last (row-major) pixel won by each record in this view, -1 = none
     int32_t *counters;     // [8]: 0 n_vis_blocks, 1 n_recs, 2 n_bin_entries, 3 overflow flag, 4 bg winner,
                            //      5 rec index of face F-1 (or -1)
 };
@@ -136,7 +141,10 @@ int gg_launch_mesh_blocks(gg_context *ctx, cudaStream_t st);
 int gg_launch_project(gg_context *ctx, const gg_camera *cams, int n, int32_t *dX, int32_t *dY, float *dinvz,
                       uint8_t *dvalid, cudaStream_t st);
 int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *d_pix2face, float *d_depth,
-                        cudaStream_t st);
+                        int want_winners, int compat_bg, cudaStream_t st);
+// gg_aggregate.cu: consume the per-record winners of view `view` of the last rasterization batch
+int gg_launch_resolve_view(gg_context *ctx, int view, const void *d_pred, int pred_kind, int C, int mode, int flags,
+                           double *d_sum, int32_t *d_count, cudaStream_t st);
 // gg_aggregate.cu
 int gg_launch_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred,
                         int pred_kind, int C, int mode, int compat, double *d_sum, int32_t *d_count,

@@ -244,12 +244,27 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__
                     imax = min(imax, c.H - 1);
                     if (jmin <= jmax && imin <= imax) {
                         keep = true;
-                        r.x0 = p0.X;
-                        r.y0 = p0.Y;
-                        r.x1 = p1.X;
-                        r.y1 = p1.Y;
-                        r.x2 = p2.X;
-                        r.y2 = p2.Y;
+                        const long long X[3] = {p0.X, p1.X, p2.X}, Y[3] = {p0.Y, p1.Y, p2.Y};
+                        long long Ak[3], Bk[3], E0[3];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const int k1 = (k + 1) % 3;
+                            Ak[k] = -(Y[k1] - Y[k]);
+                            Bk[k] = (X[k1] - X[k]);
+                            E0[k] = Bk[k] * (GG_HALF - Y[k]) + Ak[k] * (GG_HALF - X[k]);  // at pixel (0,0) centre
+                            // contract C3 (top-left rule): E == 0 is inside only on left / top edges
+                            const bool inclusive = (Ak[k] > 0) || (Ak[k] == 0 && Bk[k] > 0);
+                            r.A[k] = (int)Ak[k];
+                            r.B[k] = (int)Bk[k];
+                            r.C[k] = E0[k] - (inclusive ? 0 : 1);
+                        }
+                        const long long a2 = area2 < 0 ? -area2 : area2;
+                        const double inv_area = 1.0 / (double)a2;
+                        const double w0 = p0.invz, w1 = p1.invz, w2 = p2.invz;
+                        // barycentric weights: E1 -> v0, E2 -> v1, E0 -> v2
+                        r.w00 = ((double)E0[1] * w0 + (double)E0[2] * w1 + (double)E0[0] * w2) * inv_area;
+                        r.gx = (double)GG_SUBPIX * ((double)Ak[1] * w0 + (double)Ak[2] * w1 + (double)Ak[0] * w2) * inv_area;
+                        r.gy = (double)GG_SUBPIX * ((double)Bk[1] * w0 + (double)Bk[2] * w1 + (double)Bk[0] * w2) * inv_area;
                         r.w0 = p0.invz;
                         r.w1 = p1.invz;
                         r.w2 = p2.invz;
@@ -266,6 +281,7 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__
         if (keep) {
             if (idx < cap_recs) {
                 vs.recs[idx] = r;
+                vs.winner[idx] = -1;
                 if (r.face == (int32_t)(F - 1)) vs.counters[5] = idx;
                 const int tx0 = r.jmin / GG_TILE_W, tx1 = r.jmax / GG_TILE_W;
                 const int ty0 = r.imin / GG_TILE_H, ty1 = r.imax / GG_TILE_H;
@@ -353,70 +369,74 @@ __global__ void __launch_bounds__(256) k_fill_bins(const __grid_constant__ GGCam
 // ------------------------------------------------------------------------------------------------------
 // Tile rasterizer.
 // ------------------------------------------------------------------------------------------------------
-struct TileFace {
-    long long e[3];   // edge functions at the tile-origin pixel centre, top-left bias folded in (>= 0 inside)
-    long long sx[3];  // step per pixel in x
-    long long sy[3];  // step per pixel in y
-    double inv_area;  // 1 / area2 (exact-depth path)
-    float w_org, gx, gy;  // 1/z plane relative to the tile origin (fast path)
-    float w0, w1, w2;
+struct __align__(16) TileFace {  // a face record re-expressed relative to one tile; 80 B
+    int e[3], sx[3], sy[3];  // fast path: biased edge functions at the tile-origin pixel centre + per-pixel steps
+    float w_org, gx, gy;     // fast path: 1/z plane relative to the tile origin
+    unsigned rowmask;        // bit r: tile row r intersects the face's pixel range
+    unsigned masks;          // bits 0..7: 8-px column strips, bits 8..15: warps (32x8 px regions), bit 16: fast path
     int face;
-    int flags;  // bit0: 32-bit edges + plane depth are safe; bits 1..3: bias of edge k
-    short bx0, bx1, by0, by1;  // pixel range inside the tile (inclusive)
+    int pad[5];
 };
+static_assert(sizeof(TileFace) == 80, "TileFace layout");
 
-#define TF_FAST 1
+#define TF_FAST (1u << 16)
 
 __device__ __forceinline__ void setup_tile_face(TileFace &tf, const GGFaceRec &r, int tile_x0, int tile_y0) {
-    const long long Px = (long long)GG_SUBPIX * tile_x0 + GG_HALF, Py = (long long)GG_SUBPIX * tile_y0 + GG_HALF;
-    const long long X[3] = {r.x0, r.x1, r.x2}, Y[3] = {r.y0, r.y1, r.y2};
-    long long A[3], B[3], E[3];
-    int flags = 0;
-    long long ebound = 0;
+    bool fits = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const int k1 = (k + 1) % 3;
-        A[k] = -(Y[k1] - Y[k]);
-        B[k] = (X[k1] - X[k]);
-        E[k] = B[k] * (Py - Y[k]) + A[k] * (Px - X[k]);
-        const bool inclusive = (A[k] > 0) || (A[k] == 0 && B[k] > 0);  // contract C3 (top-left rule)
-        const long long bias = inclusive ? 0 : 1;
-        flags |= (int)bias << (1 + k);
-        tf.e[k] = E[k] - bias;
-        tf.sx[k] = A[k] * GG_SUBPIX;
-        tf.sy[k] = B[k] * GG_SUBPIX;
-        const long long bound = llabs(tf.e[k]) + (GG_TILE_W - 1) * llabs(tf.sx[k]) + (GG_TILE_H - 1) * llabs(tf.sy[k]);
-        ebound = max(ebound, bound);
+        const long long sx = (long long)r.A[k] * GG_SUBPIX, sy = (long long)r.B[k] * GG_SUBPIX;
+        const long long e = r.C[k] + sx * tile_x0 + sy * tile_y0;
+        const long long bound = llabs(e) + (GG_TILE_W - 1) * llabs(sx) + (GG_TILE_H - 1) * llabs(sy);
+        fits = fits && (bound < 2147483647LL);
+        tf.e[k] = (int)e;
+        tf.sx[k] = (int)sx;
+        tf.sy[k] = (int)sy;
     }
-    const long long area2 = (X[1] - X[0]) * (Y[2] - Y[0]) - (X[2] - X[0]) * (Y[1] - Y[0]);
-    const double inv_area = 1.0 / (double)area2;
-    const double w0 = r.w0, w1 = r.w1, w2 = r.w2;
-    // barycentric weights: E1 -> v0, E2 -> v1, E0 -> v2
-    const double w_org = ((double)E[1] * w0 + (double)E[2] * w1 + (double)E[0] * w2) * inv_area;
-    const double gx = (double)GG_SUBPIX * ((double)A[1] * w0 + (double)A[2] * w1 + (double)A[0] * w2) * inv_area;
-    const double gy = (double)GG_SUBPIX * ((double)B[1] * w0 + (double)B[2] * w1 + (double)B[0] * w2) * inv_area;
-    tf.inv_area = inv_area;
+    const double w_org = r.w00 + r.gx * (double)tile_x0 + r.gy * (double)tile_y0;
     tf.w_org = (float)w_org;
-    tf.gx = (float)gx;
-    tf.gy = (float)gy;
-    tf.w0 = r.w0;
-    tf.w1 = r.w1;
-    tf.w2 = r.w2;
+    tf.gx = (float)r.gx;
+    tf.gy = (float)r.gy;
+    const double wmin = fmin((double)r.w0, fmin((double)r.w1, (double)r.w2));
+    const double spread = fabs(w_org) + (GG_TILE_W - 1) * fabs(r.gx) + (GG_TILE_H - 1) * fabs(r.gy);
+    fits = fits && (spread <= 16.0 * wmin);
+    const int bx0 = max((int)r.jmin - tile_x0, 0), bx1 = min((int)r.jmax - tile_x0, GG_TILE_W - 1);
+    const int by0 = max((int)r.imin - tile_y0, 0), by1 = min((int)r.imax - tile_y0, GG_TILE_H - 1);
+    const unsigned rowmask = (0xffffffffu >> (31 - by1)) & (0xffffffffu << by0);
+    const unsigned strips = (0xffu >> (7 - (bx1 >> 3))) & (0xffu << (bx0 >> 3));
+    unsigned warps = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const unsigned wrows = 0xffu << ((w >> 1) * 8), wstrips = 0xfu << ((w & 1) * 4);
+        if ((rowmask & wrows) && (strips & wstrips)) warps |= 1u << w;
+    }
+    tf.rowmask = rowmask;
+    tf.masks = strips | (warps << 8) | (fits ? TF_FAST : 0u);
     tf.face = r.face;
-    const double wmin = fmin(w0, fmin(w1, w2));
-    const double spread = fabs(w_org) + (GG_TILE_W - 1) * fabs(gx) + (GG_TILE_H - 1) * fabs(gy);
-    if (ebound < 2147483647LL && spread <= 16.0 * wmin) flags |= TF_FAST;
-    tf.flags = flags;
-    tf.bx0 = (short)max((int)r.jmin - tile_x0, 0);
-    tf.bx1 = (short)min((int)r.jmax - tile_x0, GG_TILE_W - 1);
-    tf.by0 = (short)max((int)r.imin - tile_y0, 0);
-    tf.by1 = (short)min((int)r.imax - tile_y0, GG_TILE_H - 1);
 }
 
-__global__ void __launch_bounds__(GG_RASTER_THREADS) k_raster_tiles(const __grid_constant__ GGCamBatch cams,
+// Exact evaluation of one face at one pixel (slow path: long edges or steep depth planes).
+__device__ __forceinline__ bool exact_cover(const GGFaceRec &r, int j, int i, float &w) {
+    long long E[3];
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        E[k] = r.C[k] + (long long)r.A[k] * GG_SUBPIX * j + (long long)r.B[k] * GG_SUBPIX * i;
+        inside = inside && (E[k] >= 0);
+        const bool inclusive = (r.A[k] > 0) || (r.A[k] == 0 && r.B[k] > 0);
+        E[k] += inclusive ? 0 : 1;  // undo the fill-rule bias for the depth interpolation
+    }
+    if (!inside) return false;
+    const double area = (double)(E[0] + E[1] + E[2]);
+    w = (float)(((double)E[1] * (double)r.w0 + (double)E[2] * (double)r.w1 + (double)E[0] * (double)r.w2) / area);
+    return true;
+}
+
+template <bool WINNERS>
+__global__ void __launch_bounds__(GG_RASTER_THREADS, 4) k_raster_tiles(const __grid_constant__ GGCamBatch cams,
                                                                     const __grid_constant__ GGViewBatch views,
                                                                     int32_t *__restrict__ pix2face,
-                                                                    float *__restrict__ depth) {
+                                                                    float *__restrict__ depth, int compat_bg) {
     const int view = blockIdx.z;
     const gg_camera &c = cams.cam[view];
     const GGViewScratch &vs = views.v[view];
@@ -425,49 +445,69 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS) k_raster_tiles(const __grid
     const int tile = blockIdx.y * tiles_x + blockIdx.x;
     const int tile_x0 = blockIdx.x * GG_TILE_W, tile_y0 = blockIdx.y * GG_TILE_H;
 
-    __shared__ TileFace s_faces[GG_CHUNK];
+    __shared__ __align__(16) TileFace s_faces[GG_CHUNK];
+    __shared__ int s_rec[GG_CHUNK];          // record index of the staged faces (slow path)
+    __shared__ int s_listface[GG_MAXL];      // face ID by tile-list position
+    __shared__ int s_listwin[WINNERS ? GG_MAXL : 1];
+    __shared__ int s_bgwin;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wx0 = (warp & 1) * 32, wy0 = (warp >> 1) * 8;  // warp region: 32 x 8 px
-    const int tx0 = wx0 + (lane & 3) * 8;                     // this thread: 8 px of row ty
-    const int ty = wy0 + (lane >> 2);
+    const int strip = (warp & 1) * 4 + (lane & 3);  // 8-px column strip of this thread
+    const int tx0 = strip * 8;
+    const int ty = (warp >> 1) * 8 + (lane >> 2);
 
     float bw[8];
-    int bf[8];
+    int bk[8];  // tile-list position of the winning face, -1 = none
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         bw[i] = 0.f;
-        bf[i] = -1;
+        bk[i] = -1;
     }
 
     const bool overflow = vs.counters[3] != 0;
     const int beg = overflow ? 0 : vs.tile_offset[tile];
     const int end = overflow ? 0 : vs.tile_offset[tile + 1];
+    const int len = end - beg;
 
-    for (int base = beg; base < end; base += GG_CHUNK) {
-        const int n = min(GG_CHUNK, end - base);
-        if (threadIdx.x < n) setup_tile_face(s_faces[threadIdx.x], vs.recs[vs.bins[base + threadIdx.x]], tile_x0, tile_y0);
+    if (WINNERS) {
+        for (int k = threadIdx.x; k < min(len, GG_MAXL); k += GG_RASTER_THREADS) s_listwin[k] = -1;
+        if (threadIdx.x == 0) s_bgwin = -1;
+    }
+
+    auto face_of = [&](int k) -> int { return k < GG_MAXL ? s_listface[k] : vs.recs[vs.bins[beg + k]].face; };
+
+    for (int base = 0; base < len; base += GG_CHUNK) {
+        const int n = min(GG_CHUNK, len - base);
+        if (threadIdx.x < n) {
+            const int rec = vs.bins[beg + base + threadIdx.x];
+            const GGFaceRec &r = vs.recs[rec];
+            setup_tile_face(s_faces[threadIdx.x], r, tile_x0, tile_y0);
+            s_rec[threadIdx.x] = rec;
+            if (base + threadIdx.x < GG_MAXL) s_listface[base + threadIdx.x] = r.face;
+        }
         __syncthreads();
         for (int k = 0; k < n; ++k) {
-            const TileFace &tf = s_faces[k];
-            // warp-uniform reject, then per-thread reject
-            if (tf.bx1 < wx0 || tf.bx0 > wx0 + 31 || tf.by1 < wy0 || tf.by0 > wy0 + 7) continue;
-            if (ty < tf.by0 || ty > tf.by1 || tf.bx1 < tx0 || tf.bx0 > tx0 + 7) continue;
-            const int face = tf.face;
-            if (tf.flags & TF_FAST) {
-                const int s0 = (int)tf.sx[0], s1 = (int)tf.sx[1], s2 = (int)tf.sx[2];
-                int e0 = (int)tf.e[0] + s0 * tx0 + (int)tf.sy[0] * ty;
-                int e1 = (int)tf.e[1] + s1 * tx0 + (int)tf.sy[1] * ty;
-                int e2 = (int)tf.e[2] + s2 * tx0 + (int)tf.sy[2] * ty;
-                const float wrow = fmaf(tf.gy, (float)ty, tf.w_org);
-                const float gx = tf.gx;
+            const unsigned masks = s_faces[k].masks;
+            if (!((masks >> (8 + warp)) & 1u)) continue;                      // warp-uniform reject
+            if (!(((s_faces[k].rowmask >> ty) & (masks >> strip)) & 1u)) continue;  // per-thread reject
+            const int pos = base + k;
+            if (masks & TF_FAST) {
+                const int4 q0 = *reinterpret_cast<const int4 *>(&s_faces[k].e[0]);   // e0 e1 e2 sx0
+                const int4 q1 = *reinterpret_cast<const int4 *>(&s_faces[k].sx[1]);  // sx1 sx2 sy0 sy1
+                const int4 q2 = *reinterpret_cast<const int4 *>(&s_faces[k].sy[2]);  // sy2 w_org gx gy
+                const int s0 = q0.w, s1 = q1.x, s2 = q1.y;
+                int e0 = q0.x + s0 * tx0 + q1.z * ty;
+                int e1 = q0.y + s1 * tx0 + q1.w * ty;
+                int e2 = q0.z + s2 * tx0 + q2.x * ty;
+                const float gx = __int_as_float(q2.z);
+                const float wrow = fmaf(__int_as_float(q2.w), (float)ty, __int_as_float(q2.y));
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if ((e0 | e1 | e2) >= 0) {
                         const float w = fmaf(gx, (float)(tx0 + i), wrow);
-                        if (w > bw[i] || (w == bw[i] && face < bf[i])) {
+                        if (w > bw[i] || (w == bw[i] && s_faces[k].face < face_of(bk[i]))) {
                             bw[i] = w;
-                            bf[i] = face;
+                            bk[i] = pos;
                         }
                     }
                     e0 += s0;
@@ -475,33 +515,30 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS) k_raster_tiles(const __grid
                     e2 += s2;
                 }
             } else {
-                long long e0 = tf.e[0] + tf.sx[0] * tx0 + tf.sy[0] * ty;
-                long long e1 = tf.e[1] + tf.sx[1] * tx0 + tf.sy[1] * ty;
-                long long e2 = tf.e[2] + tf.sx[2] * tx0 + tf.sy[2] * ty;
-                const long long b0 = (tf.flags >> 1) & 1, b1 = (tf.flags >> 2) & 1, b2 = (tf.flags >> 3) & 1;
+                const GGFaceRec &r = vs.recs[s_rec[k]];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if ((e0 | e1 | e2) >= 0) {
-                        const double wd = ((double)(e1 + b1) * (double)tf.w0 + (double)(e2 + b2) * (double)tf.w1 +
-                                           (double)(e0 + b0) * (double)tf.w2) * tf.inv_area;
-                        const float w = (float)wd;
-                        if (w > bw[i] || (w == bw[i] && face < bf[i])) {
+                for (int i = 0; i < 8; ++i) {  // unrolled so that bw / bk stay in registers
+                    float w;
+                    if (exact_cover(r, tile_x0 + tx0 + i, tile_y0 + ty, w)) {
+                        if (w > bw[i] || (w == bw[i] && r.face < face_of(bk[i]))) {
                             bw[i] = w;
-                            bf[i] = face;
+                            bk[i] = pos;
                         }
                     }
-                    e0 += tf.sx[0];
-                    e1 += tf.sx[1];
-                    e2 += tf.sx[2];
                 }
             }
         }
         __syncthreads();
     }
 
-    // ---- write the 8 pixels of this thread ----
+    // ---- epilogue: face IDs of this thread's 8 pixels ----
+    int bf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bf[i] = bk[i] >= 0 ? face_of(bk[i]) : -1;
+
     const int row = tile_y0 + ty, col = tile_x0 + tx0;
-    if (row < H && col < W) {
+    const bool row_ok = row < H;
+    if (row_ok && col < W) {
         const int64_t o = ((int64_t)view * H + row) * W + col;
         if (col + 7 < W && ((o & 3) == 0)) {
             if (pix2face) {
@@ -523,6 +560,41 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS) k_raster_tiles(const __grid
                 }
             }
         }
+    }
+
+    if (WINNERS) {
+        // Last pixel (row-major) won by every face: only the end of each run of equal winners in this thread's
+        // 8 pixels can be a face's last pixel in this row; the run is dropped when the next strip continues it.
+        const int next_first = __shfl_down_sync(0xffffffffu, bk[0], 1);
+        const bool has_next = (lane & 3) != 3;  // lane+1 is the next strip of the same row
+        int bgmax = -1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool in_img = row_ok && (col + i < W);
+            const int pix = row * W + col + i;
+            const int nxt = (i < 7) ? ((col + i + 1 < W) ? bk[i + 1] : -2) : (has_next && (col + 8 < W) ? next_first : -2);
+            if (in_img) {
+                if (bk[i] >= 0) {
+                    if (bk[i] != nxt) {
+                        if (bk[i] < GG_MAXL) atomicMax(&s_listwin[bk[i]], pix);
+                        else atomicMax(&vs.winner[vs.bins[beg + bk[i]]], pix);
+                    }
+                } else {
+                    bgmax = pix;  // pixel index grows with i
+                }
+            }
+        }
+        if (compat_bg) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bgmax = max(bgmax, __shfl_xor_sync(0xffffffffu, bgmax, o));
+            if (lane == 0 && bgmax >= 0) atomicMax(&s_bgwin, bgmax);
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < min(len, GG_MAXL); k += GG_RASTER_THREADS) {
+            const int p = s_listwin[k];
+            if (p >= 0) atomicMax(&vs.winner[vs.bins[beg + k]], p);
+        }
+        if (compat_bg && threadIdx.x == 0 && s_bgwin >= 0) atomicMax(&vs.counters[4], s_bgwin);
     }
 }
 
@@ -551,8 +623,9 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
     const size_t b_cnt = align_up((size_t)slot_tiles * 4, 256);
     const size_t b_off = align_up((size_t)(slot_tiles + 1) * 4, 256);
     const size_t b_bin = align_up((size_t)cap_bins * 4, 256);
+    const size_t b_win = align_up((size_t)cap_recs * 4, 256);
     const size_t b_ctr = 256;
-    const size_t per_slot = b_vis + b_rec + b_cnt + b_off + b_bin + b_ctr;
+    const size_t per_slot = b_vis + b_rec + b_cnt + b_off + b_bin + b_win + b_ctr;
     GG_CUDA(cudaMalloc(&ctx->d_scratch, per_slot * slots));
     ctx->scratch_bytes = per_slot * slots;
     for (int s = 0; s < slots; ++s) {
@@ -568,6 +641,8 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
         p += b_off;
         v.bins = (int32_t *)p;
         p += b_bin;
+        v.winner = (int32_t *)p;
+        p += b_win;
         v.counters = (int32_t *)p;
     }
     ctx->n_slots = slots;
@@ -595,7 +670,7 @@ int gg_launch_project(gg_context *ctx, const gg_camera *cams, int n, int32_t *dX
 }
 
 int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *d_pix2face, float *d_depth,
-                        cudaStream_t st) {
+                        int want_winners, int compat_bg, cudaStream_t st) {
     const int W = cams[0].W, H = cams[0].H;
     int rc = gg_ensure_scratch(ctx, n, W, H);
     if (rc != GG_OK) return rc;
@@ -618,7 +693,13 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
                                                                         cb, ctx->views));
     GG_LAUNCH(ctx, GG_ST_SCAN, st, k_scan_tiles<<<n, 1024, 0, st>>>(n_tiles, ctx->cap_recs, ctx->cap_bins, ctx->views));
     GG_LAUNCH(ctx, GG_ST_FILL, st, k_fill_bins<<<dim3(ctx->sm_count * 4, n), 256, 0, st>>>(cb, ctx->views));
-    GG_LAUNCH(ctx, GG_ST_RASTER, st,
-              k_raster_tiles<<<dim3(tiles_x, tiles_y, n), GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, d_pix2face, d_depth));
+    if (want_winners)
+        GG_LAUNCH(ctx, GG_ST_RASTER, st,
+                  k_raster_tiles<true><<<dim3(tiles_x, tiles_y, n), GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, d_pix2face,
+                                                                                                d_depth, compat_bg));
+    else
+        GG_LAUNCH(ctx, GG_ST_RASTER, st,
+                  k_raster_tiles<false><<<dim3(tiles_x, tiles_y, n), GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, d_pix2face,
+                                                                                                 d_depth, 0));
     return GG_OK;
 }

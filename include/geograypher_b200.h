@@ -120,7 +120,7 @@ int gg_rasterize(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_pix
         (project_images + the accumulation of aggregate_projected_images, meshes.py:1988-2001, 2056-2067;
         vote mode: derived_meshes.py:480-520).  d_sum: F x C float64 (vote mode: F x n_classes),
         d_count: F int32; both are accumulated into, so zero them before the first view.
-        `compat_negative_index` is a bit mask: GG_FLAG_COMPAT_NEG reproduces meshes.py:2000 (background
+        `flags` is a bit mask: GG_FLAG_COMPAT_NEG reproduces meshes.py:2000 (background
         pixels index face F-1); GG_FLAG_KEEP_NAN keeps NaN scores instead of turning them into 0 (what the
         reference does when the whole aggregation has a single view, meshes.py:2056-2057); GG_FLAG_ASSIGN
         writes the face rows instead of accumulating (project_images' per-view output; count[f]=1 marks
@@ -129,13 +129,13 @@ int gg_rasterize(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_pix
 #define GG_FLAG_KEEP_NAN 2
 #define GG_FLAG_ASSIGN 4
 int gg_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred, int pred_kind,
-                 int C, int mode, int compat_negative_index, double *d_sum, int32_t *d_count, void *stream);
+                 int C, int mode, int flags, double *d_sum, int32_t *d_count, void *stream);
 
 /* ---- stage 1+2+3 fused over n views: rasterize and aggregate without a round trip of the rasters through
         the host.  h_pred[i] is the device pointer of view i's prediction image.  d_pix2face may be NULL. -- */
 int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const void *const *h_pred,
-                         int pred_kind, int C, int mode, int compat_negative_index, double *d_sum,
-                         int32_t *d_count, int32_t *d_pix2face, void *stream);
+                         int pred_kind, int C, int mode, int flags, double *d_sum, int32_t *d_count,
+                         int32_t *d_pix2face, void *stream);
 
 /* ---- epilogue of aggregate_projected_images (meshes.py:2069-2082) + find_argmax_nonzero_value
         (utils/indexing.py:9-32): avg = sum / count (NaN rows where count == 0; d_sum rows with count == 0 are

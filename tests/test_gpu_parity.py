@@ -93,6 +93,59 @@ def test_pix2face_matches_oracle(torch, lib, name, ncam):
     assert n_unsafe <= 1e-3 * p2f.size, (n_unsafe, p2f.size)
 
 
+@pytest.mark.parametrize("seed,n_faces,W,H", [(0, 300, 640, 480), (1, 40, 1500, 1100), (2, 5000, 333, 217)])
+def test_triangle_soup_matches_oracle(torch, lib, seed, n_faces, W, H):
+    """Random triangles of every size: edges longer than the 32-bit fast path allows, slivers, faces that cross the
+    near plane or lie behind the camera, exact duplicates (tie -> lowest ID) and degenerate faces."""
+    rng = np.random.default_rng(seed)
+    centers = rng.uniform([-30, -30, -5], [30, 30, 60], size=(n_faces, 1, 3))
+    size = rng.choice([0.3, 3.0, 40.0], size=(n_faces, 1, 1), p=[0.4, 0.4, 0.2])
+    tri = centers + rng.normal(0, 1, size=(n_faces, 3, 3)) * size
+    verts = tri.reshape(-1, 3)
+    faces = np.arange(3 * n_faces, dtype=np.int32).reshape(-1, 3)
+    faces[5] = faces[3]            # duplicate of face 3 -> exact depth tie, lowest ID must win
+    faces[7] = [21, 21, 22]        # degenerate
+    v32 = verts.astype(np.float32)
+    c2w = np.eye(4)
+    c2w[:3, 3] = [0.5, -0.25, -20.0]
+    cam = ora.make_camera(c2w, 0.8 * W, 3.0, -2.0, W, H)
+    ctx = _context(torch, lib, v32, faces)
+    p2f = ctx.rasterize([_to_gg(lib, cam)]).cpu().numpy()[0]
+    ref, _, margin = ora.rasterize(v32, faces, cam, want_depth=True, want_margin=True)
+    n_diff, n_unsafe = _assert_ids_match(p2f, ref, margin, f"soup {seed}")
+    assert (ref >= 0).mean() > 0.2
+    assert not (p2f == 5).any()  # the duplicate never wins over face 3
+    assert n_diff <= n_unsafe
+
+
+def test_fused_project_aggregate_equals_unfused(torch, lib):
+    """gg_project_aggregate (winners kept in scratch, no raster in HBM) == gg_rasterize + gg_aggregate, bit for bit,
+    with and without the -1 -> last-face quirk."""
+    from geograypher_b200 import synthetic as syn
+
+    v32, faces, cams, cfg = _scene("c1", 5)
+    W, H = cfg.image_size
+    F, C = len(faces), cfg.n_classes
+    ctx = _context(torch, lib, v32, faces)
+    gg = [_to_gg(lib, c) for c in cams]
+    idx = [torch.from_numpy(syn.class_index_image(k, H, W, C)).cuda() for k in range(len(cams))]
+    soft = [torch.from_numpy(syn.softmax_predictions(k, H, W, C, grid=(5, 7))).cuda() for k in range(len(cams))]
+    for s in soft:
+        s[::7, ::5, 1] = float("nan")
+    p2f = ctx.rasterize(gg)
+    for preds, kind in [(idx, lib.PRED_INDEX_U8), (soft, lib.PRED_F32)]:
+        for flags in (0, lib.FLAG_COMPAT_NEGATIVE_INDEX):
+            ref = _agg(torch, lib, ctx, p2f, preds, kind, C, lib.MODE_LAST_PIXEL, flags, F)
+            d_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda")
+            d_count = torch.zeros((F,), dtype=torch.int32, device="cuda")
+            out = torch.empty_like(p2f)
+            ctx.project_aggregate(gg[:3], preds[:3], kind, C, lib.MODE_LAST_PIXEL, flags, d_sum, d_count, pix2face_out=out[:3])
+            ctx.project_aggregate(gg[3:], preds[3:], kind, C, lib.MODE_LAST_PIXEL, flags, d_sum, d_count)
+            avg, argmax = ctx.finalize(d_sum, d_count)
+            assert torch.equal(out[:3], p2f[:3])
+            _eq(avg.cpu().numpy(), ref[0]); _eq(d_count.cpu().numpy(), ref[1]); _eq(argmax.cpu().numpy(), ref[3])
+
+
 def test_pix2face_golden_scene(torch, lib, golden_scene):
     g = golden_scene
     f, cx, cy, W, H = g["intrinsics"]
