@@ -15,13 +15,15 @@
 #define GG_COORD_CLAMP 536870912.0f  // 2^29 sub-pixel units
 
 // ---- tiling ------------------------------------------------------------------------------------------
-#define GG_TILE_W 64
-#define GG_TILE_H 32
-#define GG_RASTER_THREADS 256  // 8 warps; warp = 32 x 8 px region, lane = 8 consecutive px of one row
-#define GG_CHUNK 64            // faces staged in shared memory per pass
+#define GG_TILE_W 32           // one warp rasterizes one 32 x 8 px tile; lane = 8 consecutive px of one row
+#define GG_TILE_H 8
+#define GG_RASTER_WARPS 4      // independent warps (tiles) per CTA
+#define GG_RASTER_THREADS (32 * GG_RASTER_WARPS)
+#ifndef GG_RASTER_MIN_BLOCKS
+#define GG_RASTER_MIN_BLOCKS 6
+#endif
+#define GG_CHUNK 32            // faces staged per warp per pass (one per lane)
 #define GG_BLOCK_FACES 128     // faces per cull block
-
-#define GG_MAXL 1024           // tile-list positions whose face / record / winner live in shared memory
 
 struct GGFaceRec {  // one surviving face of one view, orientation-normalised (area2 > 0); 96 B
     int32_t A[3], B[3];    // edge gradients in sub-pixel units: E_k(P) = A_k*Px + B_k*Py + const, A = -dy, B = dx
@@ -30,8 +32,10 @@ struct GGFaceRec {  // one surviving face of one view, orientation-normalised (a
     float w0, w1, w2;      // 1/z_cam at the vertices (exact-depth path)
     int32_t face;          // face ID
     uint16_t jmin, jmax, imin, imax;  // pixel-centre index range, clamped to the raster
+    unsigned long long tmask;  // which tiles of the bounding box the triangle can touch (bit = row-major index in the
+                               // box), or ~0 when the box has more than 64 tiles (the fill pass then re-tests)
 };
-static_assert(sizeof(GGFaceRec) == 96, "GGFaceRec layout");
+static_assert(sizeof(GGFaceRec) == 104, "GGFaceRec layout");
 
 struct GGCamBatch {  // passed by value as a __grid_constant__ kernel parameter (<= 4 KB)
     gg_camera cam[GG_MAX_VIEWS_PER_CALL];
@@ -40,8 +44,8 @@ struct GGCamBatch {  // passed by value as a __grid_constant__ kernel parameter 
 struct GGViewScratch {  // device pointers of one batch slot
     int32_t *vis_blocks;   // [n_blocks]
     GGFaceRec *recs;       // [cap_recs]
-    int32_t *tile_count;   // [n_tiles]   (reused as fill cursor)
-    int32_t *tile_offset;  // [n_tiles + 1]
+    int32_t *tile_count;   // [n_tiles]   faces per tile (zeroed by the reserve pass, rebuilt by the fill pass)
+    int32_t *tile_offset;  // [n_tiles]   start of the tile's list in bins (lists are not in tile order)
     int32_t *bins;         // [cap_bins]  record indices grouped by tile
     int32_t *winner;       // [cap_recs]  last (row-major) pixel won by each record in this view, -1 = none
     int32_t *counters;     // [8]: 0 n_vis_blocks, 1 n_recs, 2 n_bin_entries, 3 overflow flag, 4 bg winner,

@@ -199,6 +199,20 @@ __global__ void __launch_bounds__(256) k_cull_blocks(const float *__restrict__ l
     if (pos >= 0) vs.vis_blocks[pos] = b;
 }
 
+// Conservative triangle / tile test: the tile is skipped when all its pixel centres lie on the outer side of one
+// edge (the edge function is linear, so its maximum over the tile is at the corner chosen by the gradient signs).
+__device__ __forceinline__ bool tile_may_touch(const GGFaceRec &r, int tx, int ty) {
+    const int x0 = tx * GG_TILE_W, y0 = ty * GG_TILE_H;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int xc = r.A[k] > 0 ? x0 + GG_TILE_W - 1 : x0;
+        const int yc = r.B[k] > 0 ? y0 + GG_TILE_H - 1 : y0;
+        const long long e = r.C[k] + (long long)r.A[k] * GG_SUBPIX * xc + (long long)r.B[k] * GG_SUBPIX * yc;
+        if (e < 0) return false;
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Face setup: one thread per face of a visible block.
 // ------------------------------------------------------------------------------------------------------
@@ -280,13 +294,21 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__
         const int idx = warp_append(&vs.counters[1], keep);
         if (keep) {
             if (idx < cap_recs) {
+                const int tx0 = r.jmin / GG_TILE_W, tx1 = r.jmax / GG_TILE_W;
+                const int ty0 = r.imin / GG_TILE_H, ty1 = r.imax / GG_TILE_H;
+                const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
+                unsigned long long tmask = 0;
+                const bool small = ntx * nty <= 64;
+                for (int ty = ty0; ty <= ty1; ++ty)
+                    for (int tx = tx0; tx <= tx1; ++tx) {
+                        if (!tile_may_touch(r, tx, ty)) continue;
+                        atomicAdd(&vs.tile_count[ty * tiles_x + tx], 1);
+                        if (small) tmask |= 1ull << ((ty - ty0) * ntx + (tx - tx0));
+                    }
+                r.tmask = small ? tmask : ~0ull;
                 vs.recs[idx] = r;
                 vs.winner[idx] = -1;
                 if (r.face == (int32_t)(F - 1)) vs.counters[5] = idx;
-                const int tx0 = r.jmin / GG_TILE_W, tx1 = r.jmax / GG_TILE_W;
-                const int ty0 = r.imin / GG_TILE_H, ty1 = r.imax / GG_TILE_H;
-                for (int ty = ty0; ty <= ty1; ++ty)
-                    for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&vs.tile_count[ty * tiles_x + tx], 1);
             } else {
                 atomicOr(&vs.counters[3], 1);
             }
@@ -295,61 +317,41 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Exclusive scan of tile counts (one CTA per view); leaves tile_count zeroed for use as the fill cursor.
+// Reserve list space per tile.  Lists need not be stored in tile order, so instead of a scan every warp sums its
+// 32 counts and claims a range with one atomicAdd.  Zeroes tile_count for use as the fill cursor (the fill pass
+// brings it back to the list length).
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_scan_tiles(int n_tiles, int64_t cap_recs, int64_t cap_bins,
-                                                     const __grid_constant__ GGViewBatch views) {
-    const GGViewScratch &vs = views.v[blockIdx.x];
-    __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    if (threadIdx.x == 0) {
-        s_carry = 0;
-        if (vs.counters[1] > cap_recs) vs.counters[1] = (int)cap_recs;  // records beyond capacity were dropped
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int base = 0; base < n_tiles; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = (i < n_tiles) ? vs.tile_count[i] : 0;
-        int x = v;
+__global__ void __launch_bounds__(256) k_reserve_tiles(int n_tiles, int64_t cap_recs,
+                                                       const __grid_constant__ GGViewBatch views) {
+    const GGViewScratch &vs = views.v[blockIdx.y];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (t == 0 && vs.counters[1] > cap_recs) vs.counters[1] = (int)cap_recs;  // records beyond capacity were dropped
+    const int v = (t < n_tiles) ? vs.tile_count[t] : 0;
+    int x = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s_warp[w] = x;
-        __syncthreads();
-        if (w == 0) {
-            int s = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane >= o) s += y;
-            }
-            s_warp[lane] = s;
-        }
-        __syncthreads();
-        const int carry = s_carry;
-        const int excl = carry + (w > 0 ? s_warp[w - 1] : 0) + x - v;
-        if (i < n_tiles) {
-            vs.tile_offset[i] = excl;
-            vs.tile_count[i] = 0;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
     }
-    if (threadIdx.x == 0) {
-        vs.tile_offset[n_tiles] = s_carry;
-        vs.counters[2] = s_carry;
-        if ((int64_t)s_carry > cap_bins) atomicOr(&vs.counters[3], 2);
+    const int total = __shfl_sync(0xffffffffu, x, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(&vs.counters[2], total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (t < n_tiles) {
+        vs.tile_offset[t] = base + x - v;
+        vs.tile_count[t] = 0;
     }
 }
 
-__global__ void __launch_bounds__(256) k_fill_bins(const __grid_constant__ GGCamBatch cams,
+__global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __grid_constant__ GGCamBatch cams,
                                                    const __grid_constant__ GGViewBatch views) {
     const int view = blockIdx.y;
     const GGViewScratch &vs = views.v[view];
+    if ((int64_t)vs.counters[2] > cap_bins) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&vs.counters[3], 2);
+        return;
+    }
     if (vs.counters[3] != 0) return;
     const int n_recs = vs.counters[1];
     const int tiles_x = (cams.cam[view].W + GG_TILE_W - 1) / GG_TILE_W;
@@ -357,31 +359,41 @@ __global__ void __launch_bounds__(256) k_fill_bins(const __grid_constant__ GGCam
         const GGFaceRec &rec = vs.recs[r];
         const int tx0 = rec.jmin / GG_TILE_W, tx1 = rec.jmax / GG_TILE_W;
         const int ty0 = rec.imin / GG_TILE_H, ty1 = rec.imax / GG_TILE_H;
-        for (int ty = ty0; ty <= ty1; ++ty)
-            for (int tx = tx0; tx <= tx1; ++tx) {
-                const int t = ty * tiles_x + tx;
-                const int pos = vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1);
-                vs.bins[pos] = r;
+        const int ntx = tx1 - tx0 + 1;
+        const unsigned long long tmask = rec.tmask;
+        if (tmask != ~0ull) {
+            unsigned long long m = tmask;
+            while (m) {
+                const int b = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const int t = (ty0 + b / ntx) * tiles_x + tx0 + b % ntx;
+                vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)] = r;
             }
+        } else {
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int tx = tx0; tx <= tx1; ++tx) {
+                    if (!tile_may_touch(rec, tx, ty)) continue;
+                    const int t = ty * tiles_x + tx;
+                    vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)] = r;
+                }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Tile rasterizer.
+// Tile rasterizer: one WARP per 32 x 8 px tile, no block-level synchronisation.
 // ------------------------------------------------------------------------------------------------------
-struct __align__(16) TileFace {  // a face record re-expressed relative to one tile; 80 B
-    int e[3], sx[3], sy[3];  // fast path: biased edge functions at the tile-origin pixel centre + per-pixel steps
-    float w_org, gx, gy;     // fast path: 1/z plane relative to the tile origin
-    unsigned rowmask;        // bit r: tile row r intersects the face's pixel range
-    unsigned masks;          // bits 0..7: 8-px column strips, bits 8..15: warps (32x8 px regions), bit 16: fast path
+struct __align__(16) TileFace {  // a face record re-expressed relative to one tile; 64 B
+    int e[3], sx[3], sy[3];      // fast path: biased edge functions at the tile-origin pixel centre + per-pixel steps
+    float w_org, gx, gy;         // fast path: 1/z plane relative to the tile origin
+    unsigned lanemask;           // lanes (8-px strips) whose pixels intersect the face's pixel range
     int face;
-    int pad[5];
+    int rec;                     // record index (winner slot; source of the exact path)
+    unsigned fast;               // 1: 32-bit edges and the float plane are safe for this tile
 };
-static_assert(sizeof(TileFace) == 80, "TileFace layout");
+static_assert(sizeof(TileFace) == 64, "TileFace layout");
 
-#define TF_FAST (1u << 16)
-
-__device__ __forceinline__ void setup_tile_face(TileFace &tf, const GGFaceRec &r, int tile_x0, int tile_y0) {
+__device__ __forceinline__ void setup_tile_face(TileFace &tf, const GGFaceRec &r, int rec, int tile_x0, int tile_y0) {
     bool fits = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -402,17 +414,14 @@ __device__ __forceinline__ void setup_tile_face(TileFace &tf, const GGFaceRec &r
     fits = fits && (spread <= 16.0 * wmin);
     const int bx0 = max((int)r.jmin - tile_x0, 0), bx1 = min((int)r.jmax - tile_x0, GG_TILE_W - 1);
     const int by0 = max((int)r.imin - tile_y0, 0), by1 = min((int)r.imax - tile_y0, GG_TILE_H - 1);
-    const unsigned rowmask = (0xffffffffu >> (31 - by1)) & (0xffffffffu << by0);
-    const unsigned strips = (0xffu >> (7 - (bx1 >> 3))) & (0xffu << (bx0 >> 3));
-    unsigned warps = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        const unsigned wrows = 0xffu << ((w >> 1) * 8), wstrips = 0xfu << ((w & 1) * 4);
-        if ((rowmask & wrows) && (strips & wstrips)) warps |= 1u << w;
-    }
-    tf.rowmask = rowmask;
-    tf.masks = strips | (warps << 8) | (fits ? TF_FAST : 0u);
+    // lane = row * 4 + strip: rows by0..by1, strips (bx0 >> 3)..(bx1 >> 3)
+    const unsigned strips = (0xfu >> (3 - (bx1 >> 3))) & (0xfu << (bx0 >> 3)) & 0xfu;
+    unsigned m = 0;
+    for (int row = by0; row <= by1; ++row) m |= strips << (row * 4);
+    tf.lanemask = m;
     tf.face = r.face;
+    tf.rec = rec;
+    tf.fast = fits ? 1u : 0u;
 }
 
 // Exact evaluation of one face at one pixel (slow path: long edges or steep depth planes).
@@ -433,65 +442,51 @@ __device__ __forceinline__ bool exact_cover(const GGFaceRec &r, int j, int i, fl
 }
 
 template <bool WINNERS>
-__global__ void __launch_bounds__(GG_RASTER_THREADS, 4) k_raster_tiles(const __grid_constant__ GGCamBatch cams,
-                                                                    const __grid_constant__ GGViewBatch views,
-                                                                    int32_t *__restrict__ pix2face,
-                                                                    float *__restrict__ depth, int compat_bg) {
-    const int view = blockIdx.z;
+__global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_raster_tiles(const __grid_constant__ GGCamBatch cams,
+                                                                       const __grid_constant__ GGViewBatch views,
+                                                                       int n_tiles, int32_t *__restrict__ pix2face,
+                                                                       float *__restrict__ depth, int compat_bg) {
+    const int view = blockIdx.y;
     const gg_camera &c = cams.cam[view];
     const GGViewScratch &vs = views.v[view];
     const int W = c.W, H = c.H;
     const int tiles_x = (W + GG_TILE_W - 1) / GG_TILE_W;
-    const int tile = blockIdx.y * tiles_x + blockIdx.x;
-    const int tile_x0 = blockIdx.x * GG_TILE_W, tile_y0 = blockIdx.y * GG_TILE_H;
-
-    __shared__ __align__(16) TileFace s_faces[GG_CHUNK];
-    __shared__ int s_rec[GG_CHUNK];          // record index of the staged faces (slow path)
-    __shared__ int s_listface[GG_MAXL];      // face ID by tile-list position
-    __shared__ int s_listwin[WINNERS ? GG_MAXL : 1];
-    __shared__ int s_bgwin;
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int strip = (warp & 1) * 4 + (lane & 3);  // 8-px column strip of this thread
-    const int tx0 = strip * 8;
-    const int ty = (warp >> 1) * 8 + (lane >> 2);
+    const int tile = blockIdx.x * GG_RASTER_WARPS + warp;
+    if (tile >= n_tiles) return;  // whole warp leaves; no block-level barriers below
+    const int tile_x0 = (tile % tiles_x) * GG_TILE_W, tile_y0 = (tile / tiles_x) * GG_TILE_H;
+
+    __shared__ TileFace s_all[GG_RASTER_WARPS][GG_CHUNK];
+    TileFace *s_faces = s_all[warp];
+
+    const int tx0 = (lane & 3) * 8;  // this lane: pixels tx0..tx0+7 of row ty
+    const int ty = lane >> 2;
 
     float bw[8];
-    int bk[8];  // tile-list position of the winning face, -1 = none
+    int bf[8], br[8];  // winning face ID and its record index, -1 = none
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         bw[i] = 0.f;
-        bk[i] = -1;
+        bf[i] = -1;
+        br[i] = -1;
     }
 
     const bool overflow = vs.counters[3] != 0;
-    const int beg = overflow ? 0 : vs.tile_offset[tile];
-    const int end = overflow ? 0 : vs.tile_offset[tile + 1];
-    const int len = end - beg;
-
-    if (WINNERS) {
-        for (int k = threadIdx.x; k < min(len, GG_MAXL); k += GG_RASTER_THREADS) s_listwin[k] = -1;
-        if (threadIdx.x == 0) s_bgwin = -1;
-    }
-
-    auto face_of = [&](int k) -> int { return k < GG_MAXL ? s_listface[k] : vs.recs[vs.bins[beg + k]].face; };
+    const int beg = vs.tile_offset[tile];
+    const int len = overflow ? 0 : vs.tile_count[tile];
 
     for (int base = 0; base < len; base += GG_CHUNK) {
         const int n = min(GG_CHUNK, len - base);
-        if (threadIdx.x < n) {
-            const int rec = vs.bins[beg + base + threadIdx.x];
-            const GGFaceRec &r = vs.recs[rec];
-            setup_tile_face(s_faces[threadIdx.x], r, tile_x0, tile_y0);
-            s_rec[threadIdx.x] = rec;
-            if (base + threadIdx.x < GG_MAXL) s_listface[base + threadIdx.x] = r.face;
+        if (lane < n) {
+            const int rec = vs.bins[beg + base + lane];
+            setup_tile_face(s_faces[lane], vs.recs[rec], rec, tile_x0, tile_y0);
         }
-        __syncthreads();
+        __syncwarp();
         for (int k = 0; k < n; ++k) {
-            const unsigned masks = s_faces[k].masks;
-            if (!((masks >> (8 + warp)) & 1u)) continue;                      // warp-uniform reject
-            if (!(((s_faces[k].rowmask >> ty) & (masks >> strip)) & 1u)) continue;  // per-thread reject
-            const int pos = base + k;
-            if (masks & TF_FAST) {
+            const int4 q3 = *reinterpret_cast<const int4 *>(&s_faces[k].lanemask);  // lanemask face rec fast
+            if (!((((unsigned)q3.x) >> lane) & 1u)) continue;
+            const int face = q3.y;
+            if (q3.w) {
                 const int4 q0 = *reinterpret_cast<const int4 *>(&s_faces[k].e[0]);   // e0 e1 e2 sx0
                 const int4 q1 = *reinterpret_cast<const int4 *>(&s_faces[k].sx[1]);  // sx1 sx2 sy0 sy1
                 const int4 q2 = *reinterpret_cast<const int4 *>(&s_faces[k].sy[2]);  // sy2 w_org gx gy
@@ -505,9 +500,10 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, 4) k_raster_tiles(const __g
                 for (int i = 0; i < 8; ++i) {
                     if ((e0 | e1 | e2) >= 0) {
                         const float w = fmaf(gx, (float)(tx0 + i), wrow);
-                        if (w > bw[i] || (w == bw[i] && s_faces[k].face < face_of(bk[i]))) {
+                        if (w > bw[i] || (w == bw[i] && face < bf[i])) {
                             bw[i] = w;
-                            bk[i] = pos;
+                            bf[i] = face;
+                            br[i] = q3.z;
                         }
                     }
                     e0 += s0;
@@ -515,27 +511,24 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, 4) k_raster_tiles(const __g
                     e2 += s2;
                 }
             } else {
-                const GGFaceRec &r = vs.recs[s_rec[k]];
+                const GGFaceRec &r = vs.recs[q3.z];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {  // unrolled so that bw / bk stay in registers
+                for (int i = 0; i < 8; ++i) {  // unrolled so that bw / bf / br stay in registers
                     float w;
                     if (exact_cover(r, tile_x0 + tx0 + i, tile_y0 + ty, w)) {
-                        if (w > bw[i] || (w == bw[i] && r.face < face_of(bk[i]))) {
+                        if (w > bw[i] || (w == bw[i] && face < bf[i])) {
                             bw[i] = w;
-                            bk[i] = pos;
+                            bf[i] = face;
+                            br[i] = q3.z;
                         }
                     }
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 
-    // ---- epilogue: face IDs of this thread's 8 pixels ----
-    int bf[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) bf[i] = bk[i] >= 0 ? face_of(bk[i]) : -1;
-
+    // ---- write the 8 pixels of this lane ----
     const int row = tile_y0 + ty, col = tile_x0 + tx0;
     const bool row_ok = row < H;
     if (row_ok && col < W) {
@@ -563,38 +556,46 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, 4) k_raster_tiles(const __g
     }
 
     if (WINNERS) {
-        // Last pixel (row-major) won by every face: only the end of each run of equal winners in this thread's
-        // 8 pixels can be a face's last pixel in this row; the run is dropped when the next strip continues it.
-        const int next_first = __shfl_down_sync(0xffffffffu, bk[0], 1);
-        const bool has_next = (lane & 3) != 3;  // lane+1 is the next strip of the same row
+        // Last pixel (row-major) won by every face record.  Only the end of a run of equal winners inside this lane's
+        // 8 pixels can be the face's last pixel of the row; a run continued by the next strip is left to that strip.
+        // Lanes holding a run-end of the same record are then grouped with match.any: pixel indices grow with the lane
+        // index (lane = row * 4 + strip), so the highest lane of each group issues the only atomicMax.
+        const int next_first = __shfl_down_sync(0xffffffffu, br[0], 1);
+        const bool has_next = (lane & 3) != 3;
         int bgmax = -1;
+        int run_rec[8], run_pix[8];
+        int n_runs = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const bool in_img = row_ok && (col + i < W);
             const int pix = row * W + col + i;
-            const int nxt = (i < 7) ? ((col + i + 1 < W) ? bk[i + 1] : -2) : (has_next && (col + 8 < W) ? next_first : -2);
-            if (in_img) {
-                if (bk[i] >= 0) {
-                    if (bk[i] != nxt) {
-                        if (bk[i] < GG_MAXL) atomicMax(&s_listwin[bk[i]], pix);
-                        else atomicMax(&vs.winner[vs.bins[beg + bk[i]]], pix);
-                    }
-                } else {
-                    bgmax = pix;  // pixel index grows with i
+            const int nxt = (i < 7) ? ((col + i + 1 < W) ? br[i + 1] : -2) : ((has_next && col + 8 < W) ? next_first : -2);
+            const bool emit = in_img && br[i] >= 0 && br[i] != nxt;
+            if (in_img && br[i] < 0) bgmax = pix;  // pixel index grows with i
+            // compact the run-ends to the front (predicated moves keep the arrays in registers)
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (emit && s == n_runs) {
+                    run_rec[s] = br[i];
+                    run_pix[s] = pix;
                 }
+            }
+            n_runs += emit ? 1 : 0;
+        }
+        const int max_runs = __reduce_max_sync(0xffffffffu, n_runs);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            if (s < max_runs) {  // warp-uniform
+                const bool have = s < n_runs;
+                const int key = have ? run_rec[s] : -1 - lane;  // distinct negative keys for idle lanes
+                const unsigned grp = __match_any_sync(0xffffffffu, key);
+                if (have && (31 - __clz(grp)) == lane) atomicMax(&vs.winner[key], run_pix[s]);
             }
         }
         if (compat_bg) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) bgmax = max(bgmax, __shfl_xor_sync(0xffffffffu, bgmax, o));
-            if (lane == 0 && bgmax >= 0) atomicMax(&s_bgwin, bgmax);
+            bgmax = __reduce_max_sync(0xffffffffu, bgmax);
+            if (lane == 0 && bgmax >= 0) atomicMax(&vs.counters[4], bgmax);
         }
-        __syncthreads();
-        for (int k = threadIdx.x; k < min(len, GG_MAXL); k += GG_RASTER_THREADS) {
-            const int p = s_listwin[k];
-            if (p >= 0) atomicMax(&vs.winner[vs.bins[beg + k]], p);
-        }
-        if (compat_bg && threadIdx.x == 0 && s_bgwin >= 0) atomicMax(&vs.counters[4], s_bgwin);
     }
 }
 
@@ -621,7 +622,7 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
     const size_t b_vis = align_up((size_t)ctx->n_blocks * 4, 256);
     const size_t b_rec = align_up((size_t)cap_recs * sizeof(GGFaceRec), 256);
     const size_t b_cnt = align_up((size_t)slot_tiles * 4, 256);
-    const size_t b_off = align_up((size_t)(slot_tiles + 1) * 4, 256);
+    const size_t b_off = align_up((size_t)slot_tiles * 4, 256);
     const size_t b_bin = align_up((size_t)cap_bins * 4, 256);
     const size_t b_win = align_up((size_t)cap_recs * 4, 256);
     const size_t b_ctr = 256;
@@ -691,15 +692,16 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
     GG_LAUNCH(ctx, GG_ST_SETUP, st,
               k_setup_faces<<<dim3(gsetup, n), GG_BLOCK_FACES, 0, st>>>(ctx->d_verts, ctx->d_faces, ctx->F, ctx->cap_recs,
                                                                         cb, ctx->views));
-    GG_LAUNCH(ctx, GG_ST_SCAN, st, k_scan_tiles<<<n, 1024, 0, st>>>(n_tiles, ctx->cap_recs, ctx->cap_bins, ctx->views));
-    GG_LAUNCH(ctx, GG_ST_FILL, st, k_fill_bins<<<dim3(ctx->sm_count * 4, n), 256, 0, st>>>(cb, ctx->views));
+    GG_LAUNCH(ctx, GG_ST_SCAN, st,
+              k_reserve_tiles<<<dim3((n_tiles + 255) / 256, n), 256, 0, st>>>(n_tiles, ctx->cap_recs, ctx->views));
+    GG_LAUNCH(ctx, GG_ST_FILL, st, k_fill_bins<<<dim3(ctx->sm_count * 4, n), 256, 0, st>>>(ctx->cap_bins, cb, ctx->views));
+    const dim3 rgrid((n_tiles + GG_RASTER_WARPS - 1) / GG_RASTER_WARPS, n);
     if (want_winners)
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  k_raster_tiles<true><<<dim3(tiles_x, tiles_y, n), GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, d_pix2face,
-                                                                                                d_depth, compat_bg));
+                  k_raster_tiles<true><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, n_tiles, d_pix2face, d_depth,
+                                                                            compat_bg));
     else
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  k_raster_tiles<false><<<dim3(tiles_x, tiles_y, n), GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, d_pix2face,
-                                                                                                 d_depth, 0));
+                  k_raster_tiles<false><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, n_tiles, d_pix2face, d_depth, 0));
     return GG_OK;
 }
