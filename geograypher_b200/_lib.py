@@ -247,7 +247,7 @@ class Context:
 
     def _grow_after_overflow(self, n):
         stats = self.last_batch_stats(n)
-        self.reserve(0, int(stats[:, 2].max() * 1.25) + 1024)
+        self.reserve(0, int(stats[:, 2].max() * 1.5) + 4096)
 
     # -- stage 3 -------------------------------------------------------------------------------------------
     def aggregate(self, pix2face, pred, pred_kind, C, mode, flags, d_sum, d_count, stream=None):
@@ -259,13 +259,22 @@ class Context:
                           stream=None, check=True):
         n = len(cams)
         ptrs = (ctypes.c_void_p * n)(*[p.data_ptr() for p in preds])
-        _check(self.lib.gg_project_aggregate(self.handle, self._cam_array(cams), n, ptrs, pred_kind, C, mode,
-                                             flags, d_sum.data_ptr(), d_count.data_ptr(),
-                                             pix2face_out.data_ptr() if pix2face_out is not None else None,
-                                             _stream_ptr(stream)))
-        if check:
-            # GG_ERR_OVERFLOW here means the accumulators hold partial sums: reserve() and restart.
-            self.sync(stream)
+        for attempt in range(4):
+            _check(self.lib.gg_project_aggregate(self.handle, self._cam_array(cams), n, ptrs, pred_kind, C, mode,
+                                                 flags, d_sum.data_ptr(), d_count.data_ptr(),
+                                                 pix2face_out.data_ptr() if pix2face_out is not None else None,
+                                                 _stream_ptr(stream)))
+            if not check:
+                return
+            try:
+                self.sync(stream)
+                return
+            except GeograypherB200Error as e:
+                # In the fused modes an overflowing batch accumulates nothing (k_resolve_recs bails out), so it can be
+                # replayed after growing the scratch.  pixel_sum is not replayable.
+                if e.code != ERR_OVERFLOW or attempt == 3 or mode == MODE_PIXEL_SUM:
+                    raise
+                self._grow_after_overflow(n)
 
     def finalize(self, d_sum, d_count, want_avg=True, want_argmax=True, stream=None):
         t = self.torch

@@ -118,9 +118,15 @@ __global__ void __launch_bounds__(256) k_resolve_vote(int32_t *__restrict__ winn
 // One thread per face record of the view (grid-stride; the record count lives on the device).  The extra index
 // r == n_recs handles the meshes.py:2000 quirk when face F-1 has no record of its own.
 template <typename T>
-__global__ void __launch_bounds__(256) k_resolve_recs(GGViewScratch vs, int64_t F, const T *__restrict__ pred, int C,
-                                                      int pred_kind, int mode, int flags, double *__restrict__ sum,
+__global__ void __launch_bounds__(256) k_resolve_recs(const __grid_constant__ GGViewBatch views, int n_views, int view,
+                                                      int64_t F, const T *__restrict__ pred, int C, int pred_kind,
+                                                      int mode, int flags, double *__restrict__ sum,
                                                       int32_t *__restrict__ count) {
+    // A scratch overflow anywhere in the batch voids the whole batch: nothing is accumulated, so the host can grow
+    // the scratch and replay the same views in the same order.
+    for (int v = 0; v < n_views; ++v)
+        if (views.v[v].counters[3] != 0) return;
+    const GGViewScratch &vs = views.v[view];
     const int n_recs = vs.counters[1];
     const bool compat = (flags & GG_FLAG_COMPAT_NEG) != 0;
     const int bg = compat ? vs.counters[4] : -1;
@@ -314,14 +320,14 @@ int gg_launch_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W
 
 int gg_launch_resolve_view(gg_context *ctx, int view, const void *d_pred, int pred_kind, int C, int mode, int flags,
                            double *d_sum, int32_t *d_count, cudaStream_t st) {
-    const GGViewScratch vs = ctx->views.v[view];
     const unsigned g = (unsigned)(ctx->sm_count * 2);
+    const int nv = ctx->last_batch_n;
     const int64_t F = ctx->F;
     switch (pred_kind) {
-        case GG_PRED_F32: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<float><<<g, 256, 0, st>>>(vs, F, (const float *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
-        case GG_PRED_F64: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<double><<<g, 256, 0, st>>>(vs, F, (const double *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_F32: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<float><<<g, 256, 0, st>>>(ctx->views, nv, view, F, (const float *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_F64: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<double><<<g, 256, 0, st>>>(ctx->views, nv, view, F, (const double *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
         case GG_PRED_U8:
-        case GG_PRED_INDEX_U8: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<uint8_t><<<g, 256, 0, st>>>(vs, F, (const uint8_t *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_INDEX_U8: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<uint8_t><<<g, 256, 0, st>>>(ctx->views, nv, view, F, (const uint8_t *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
         default: gg_set_error("gg_project_aggregate: bad pred_kind"); return GG_ERR_INVALID;
     }
     return GG_OK;

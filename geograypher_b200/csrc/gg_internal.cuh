@@ -20,7 +20,7 @@
 #define GG_RASTER_WARPS 4      // independent warps (tiles) per CTA
 #define GG_RASTER_THREADS (32 * GG_RASTER_WARPS)
 #ifndef GG_RASTER_MIN_BLOCKS
-#define GG_RASTER_MIN_BLOCKS 6
+#define GG_RASTER_MIN_BLOCKS 8
 #endif
 #define GG_CHUNK 32            // faces staged per warp per pass (one per lane)
 #define GG_BLOCK_FACES 128     // faces per cull block
@@ -37,6 +37,16 @@ struct GGFaceRec {  // one surviving face of one view, orientation-normalised (a
 };
 static_assert(sizeof(GGFaceRec) == 104, "GGFaceRec layout");
 
+struct __align__(16) GGTileFace {  // a face record re-expressed relative to one 32 x 8 tile; 64 B
+    int e[3], sx[3], sy[3];        // fast path: biased edge functions at the tile-origin pixel centre + per-pixel steps
+    float w_org, gx, gy;           // fast path: 1/z plane relative to the tile origin
+    unsigned lanemask;             // lanes (8-px strips) whose pixels intersect the face's pixel range
+    int face;
+    int rec;                       // record index (winner slot; source of the exact path)
+    unsigned fast;                 // 1: 32-bit edges and the float plane are safe for this tile
+};
+static_assert(sizeof(GGTileFace) == 64, "GGTileFace layout");
+
 struct GGCamBatch {  // passed by value as a __grid_constant__ kernel parameter (<= 4 KB)
     gg_camera cam[GG_MAX_VIEWS_PER_CALL];
 };
@@ -46,7 +56,7 @@ struct GGViewScratch {  // device pointers of one batch slot
     GGFaceRec *recs;       // [cap_recs]
     int32_t *tile_count;   // [n_tiles]   faces per tile (zeroed by the reserve pass, rebuilt by the fill pass)
     int32_t *tile_offset;  // [n_tiles]   start of the tile's list in bins (lists are not in tile order)
-    int32_t *bins;         // [cap_bins]  record indices grouped by tile
+    GGTileFace *bins;      // [cap_bins]  per-(tile, face) setups grouped by tile
     int32_t *winner;       // [cap_recs]  last (row-major) pixel won by each record in this view, -1 = none
     int32_t *counters;     // [8]: 0 n_vis_blocks, 1 n_recs, 2 n_bin_entries, 3 overflow flag, 4 bg winner,
                            //      5 rec index of face F-1 (or -1)

@@ -344,6 +344,42 @@ __global__ void __launch_bounds__(256) k_reserve_tiles(int n_tiles, int64_t cap_
     }
 }
 
+// Tile-relative setup of one face: done once per (tile, face) pair by the fill pass so that the rasterizer only
+// streams ready-made 64-byte records.
+__device__ __forceinline__ void setup_tile_face(GGTileFace &tf, const GGFaceRec &r, int rec, int tile_x0, int tile_y0) {
+    bool fits = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const long long sx = (long long)r.A[k] * GG_SUBPIX, sy = (long long)r.B[k] * GG_SUBPIX;
+        const long long e = r.C[k] + sx * tile_x0 + sy * tile_y0;
+        // conservative float bound of |E| over the tile (2x head-room under 2^31)
+        const float bound = fabsf((float)e) + (float)(GG_TILE_W - 1) * fabsf((float)sx) + (float)(GG_TILE_H - 1) * fabsf((float)sy);
+        fits = fits && (bound < 1073741824.0f);
+        tf.e[k] = (int)e;
+        tf.sx[k] = (int)sx;
+        tf.sy[k] = (int)sy;
+    }
+    const double w_org = r.w00 + r.gx * (double)tile_x0 + r.gy * (double)tile_y0;
+    tf.w_org = (float)w_org;
+    tf.gx = (float)r.gx;
+    tf.gy = (float)r.gy;
+    const float wmin = fminf(r.w0, fminf(r.w1, r.w2));
+    const float spread = fabsf(tf.w_org) + (float)(GG_TILE_W - 1) * fabsf(tf.gx) + (float)(GG_TILE_H - 1) * fabsf(tf.gy);
+    fits = fits && (spread <= 16.0f * wmin);
+    const int bx0 = max((int)r.jmin - tile_x0, 0), bx1 = min((int)r.jmax - tile_x0, GG_TILE_W - 1);
+    const int by0 = max((int)r.imin - tile_y0, 0), by1 = min((int)r.imax - tile_y0, GG_TILE_H - 1);
+    // lane = row * 4 + strip: rows by0..by1, strips (bx0 >> 3)..(bx1 >> 3)
+    const unsigned strips = (0xfu >> (3 - (bx1 >> 3))) & (0xfu << (bx0 >> 3)) & 0xfu;
+    unsigned rows = (0xffu >> (7 - by1)) & (0xffu << by0) & 0xffu;  // bit r = row r
+    rows = (rows | (rows << 12)) & 0x000f000fu;                      // spread the 8 row bits to one bit per nibble
+    rows = (rows | (rows << 6)) & 0x03030303u;
+    rows = (rows | (rows << 3)) & 0x11111111u;
+    tf.lanemask = rows * strips;
+    tf.face = r.face;
+    tf.rec = rec;
+    tf.fast = fits ? 1u : 0u;
+}
+
 __global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __grid_constant__ GGCamBatch cams,
                                                    const __grid_constant__ GGViewBatch views) {
     const int view = blockIdx.y;
@@ -356,7 +392,7 @@ __global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __gri
     const int n_recs = vs.counters[1];
     const int tiles_x = (cams.cam[view].W + GG_TILE_W - 1) / GG_TILE_W;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_recs; r += gridDim.x * blockDim.x) {
-        const GGFaceRec &rec = vs.recs[r];
+        const GGFaceRec rec = vs.recs[r];
         const int tx0 = rec.jmin / GG_TILE_W, tx1 = rec.jmax / GG_TILE_W;
         const int ty0 = rec.imin / GG_TILE_H, ty1 = rec.imax / GG_TILE_H;
         const int ntx = tx1 - tx0 + 1;
@@ -366,15 +402,18 @@ __global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __gri
             while (m) {
                 const int b = __ffsll((long long)m) - 1;
                 m &= m - 1;
-                const int t = (ty0 + b / ntx) * tiles_x + tx0 + b % ntx;
-                vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)] = r;
+                const int tx = tx0 + b % ntx, ty = ty0 + b / ntx;
+                const int t = ty * tiles_x + tx;
+                setup_tile_face(vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)], rec, r, tx * GG_TILE_W,
+                                ty * GG_TILE_H);
             }
         } else {
             for (int ty = ty0; ty <= ty1; ++ty)
                 for (int tx = tx0; tx <= tx1; ++tx) {
                     if (!tile_may_touch(rec, tx, ty)) continue;
                     const int t = ty * tiles_x + tx;
-                    vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)] = r;
+                    setup_tile_face(vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)], rec, r,
+                                    tx * GG_TILE_W, ty * GG_TILE_H);
                 }
         }
     }
@@ -383,49 +422,8 @@ __global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __gri
 // ------------------------------------------------------------------------------------------------------
 // Tile rasterizer: one WARP per 32 x 8 px tile, no block-level synchronisation.
 // ------------------------------------------------------------------------------------------------------
-struct __align__(16) TileFace {  // a face record re-expressed relative to one tile; 64 B
-    int e[3], sx[3], sy[3];      // fast path: biased edge functions at the tile-origin pixel centre + per-pixel steps
-    float w_org, gx, gy;         // fast path: 1/z plane relative to the tile origin
-    unsigned lanemask;           // lanes (8-px strips) whose pixels intersect the face's pixel range
-    int face;
-    int rec;                     // record index (winner slot; source of the exact path)
-    unsigned fast;               // 1: 32-bit edges and the float plane are safe for this tile
-};
-static_assert(sizeof(TileFace) == 64, "TileFace layout");
-
-__device__ __forceinline__ void setup_tile_face(TileFace &tf, const GGFaceRec &r, int rec, int tile_x0, int tile_y0) {
-    bool fits = true;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const long long sx = (long long)r.A[k] * GG_SUBPIX, sy = (long long)r.B[k] * GG_SUBPIX;
-        const long long e = r.C[k] + sx * tile_x0 + sy * tile_y0;
-        const long long bound = llabs(e) + (GG_TILE_W - 1) * llabs(sx) + (GG_TILE_H - 1) * llabs(sy);
-        fits = fits && (bound < 2147483647LL);
-        tf.e[k] = (int)e;
-        tf.sx[k] = (int)sx;
-        tf.sy[k] = (int)sy;
-    }
-    const double w_org = r.w00 + r.gx * (double)tile_x0 + r.gy * (double)tile_y0;
-    tf.w_org = (float)w_org;
-    tf.gx = (float)r.gx;
-    tf.gy = (float)r.gy;
-    const double wmin = fmin((double)r.w0, fmin((double)r.w1, (double)r.w2));
-    const double spread = fabs(w_org) + (GG_TILE_W - 1) * fabs(r.gx) + (GG_TILE_H - 1) * fabs(r.gy);
-    fits = fits && (spread <= 16.0 * wmin);
-    const int bx0 = max((int)r.jmin - tile_x0, 0), bx1 = min((int)r.jmax - tile_x0, GG_TILE_W - 1);
-    const int by0 = max((int)r.imin - tile_y0, 0), by1 = min((int)r.imax - tile_y0, GG_TILE_H - 1);
-    // lane = row * 4 + strip: rows by0..by1, strips (bx0 >> 3)..(bx1 >> 3)
-    const unsigned strips = (0xfu >> (3 - (bx1 >> 3))) & (0xfu << (bx0 >> 3)) & 0xfu;
-    unsigned m = 0;
-    for (int row = by0; row <= by1; ++row) m |= strips << (row * 4);
-    tf.lanemask = m;
-    tf.face = r.face;
-    tf.rec = rec;
-    tf.fast = fits ? 1u : 0u;
-}
-
 // Exact evaluation of one face at one pixel (slow path: long edges or steep depth planes).
-__device__ __forceinline__ bool exact_cover(const GGFaceRec &r, int j, int i, float &w) {
+__device__ __noinline__ bool exact_cover(const GGFaceRec &r, int j, int i, float &w) {
     long long E[3];
     bool inside = true;
 #pragma unroll
@@ -456,8 +454,8 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
     if (tile >= n_tiles) return;  // whole warp leaves; no block-level barriers below
     const int tile_x0 = (tile % tiles_x) * GG_TILE_W, tile_y0 = (tile / tiles_x) * GG_TILE_H;
 
-    __shared__ TileFace s_all[GG_RASTER_WARPS][GG_CHUNK];
-    TileFace *s_faces = s_all[warp];
+    __shared__ GGTileFace s_all[GG_RASTER_WARPS][GG_CHUNK];
+    GGTileFace *s_faces = s_all[warp];
 
     const int tx0 = (lane & 3) * 8;  // this lane: pixels tx0..tx0+7 of row ty
     const int ty = lane >> 2;
@@ -477,9 +475,14 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
 
     for (int base = 0; base < len; base += GG_CHUNK) {
         const int n = min(GG_CHUNK, len - base);
-        if (lane < n) {
-            const int rec = vs.bins[beg + base + lane];
-            setup_tile_face(s_faces[lane], vs.recs[rec], rec, tile_x0, tile_y0);
+        {  // stream n ready-made 64-byte setups into shared memory: 16 B per lane, 4 x (up to) 512 B per warp
+            const int4 *src = reinterpret_cast<const int4 *>(vs.bins + beg + base);
+            int4 *dst = reinterpret_cast<int4 *>(s_faces);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = q * 32 + lane;
+                if (idx < n * 4) dst[idx] = __ldg(src + idx);
+            }
         }
         __syncwarp();
         for (int k = 0; k < n; ++k) {
@@ -563,8 +566,6 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
         const int next_first = __shfl_down_sync(0xffffffffu, br[0], 1);
         const bool has_next = (lane & 3) != 3;
         int bgmax = -1;
-        int run_rec[8], run_pix[8];
-        int n_runs = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const bool in_img = row_ok && (col + i < W);
@@ -572,24 +573,10 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
             const int nxt = (i < 7) ? ((col + i + 1 < W) ? br[i + 1] : -2) : ((has_next && col + 8 < W) ? next_first : -2);
             const bool emit = in_img && br[i] >= 0 && br[i] != nxt;
             if (in_img && br[i] < 0) bgmax = pix;  // pixel index grows with i
-            // compact the run-ends to the front (predicated moves keep the arrays in registers)
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                if (emit && s == n_runs) {
-                    run_rec[s] = br[i];
-                    run_pix[s] = pix;
-                }
-            }
-            n_runs += emit ? 1 : 0;
-        }
-        const int max_runs = __reduce_max_sync(0xffffffffu, n_runs);
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            if (s < max_runs) {  // warp-uniform
-                const bool have = s < n_runs;
-                const int key = have ? run_rec[s] : -1 - lane;  // distinct negative keys for idle lanes
+            if (__any_sync(0xffffffffu, emit)) {   // warp-uniform
+                const int key = emit ? br[i] : -1 - lane;  // distinct negative keys for idle lanes
                 const unsigned grp = __match_any_sync(0xffffffffu, key);
-                if (have && (31 - __clz(grp)) == lane) atomicMax(&vs.winner[key], run_pix[s]);
+                if (emit && (31 - __clz(grp)) == lane) atomicMax(&vs.winner[key], pix);
             }
         }
         if (compat_bg) {
@@ -609,7 +596,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
     const int64_t tiles = (int64_t)((W + GG_TILE_W - 1) / GG_TILE_W) * ((H + GG_TILE_H - 1) / GG_TILE_H);
     const int64_t cap_recs = ctx->req_recs > 0 ? ctx->req_recs : ctx->F;
-    const int64_t cap_bins = ctx->req_bins > 0 ? ctx->req_bins : (4 * cap_recs > (1 << 20) ? 4 * cap_recs : (1 << 20));
+    const int64_t cap_bins = ctx->req_bins > 0 ? ctx->req_bins : (6 * tiles > (1 << 20) ? 6 * tiles : (1 << 20));
     if (n_views <= ctx->n_slots && tiles <= ctx->slot_tiles && cap_recs == ctx->cap_recs && cap_bins == ctx->cap_bins)
         return GG_OK;
     if (ctx->d_scratch) {
@@ -623,7 +610,7 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
     const size_t b_rec = align_up((size_t)cap_recs * sizeof(GGFaceRec), 256);
     const size_t b_cnt = align_up((size_t)slot_tiles * 4, 256);
     const size_t b_off = align_up((size_t)slot_tiles * 4, 256);
-    const size_t b_bin = align_up((size_t)cap_bins * 4, 256);
+    const size_t b_bin = align_up((size_t)cap_bins * sizeof(GGTileFace), 256);
     const size_t b_win = align_up((size_t)cap_recs * 4, 256);
     const size_t b_ctr = 256;
     const size_t per_slot = b_vis + b_rec + b_cnt + b_off + b_bin + b_win + b_ctr;
@@ -640,7 +627,7 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
         p += b_cnt;
         v.tile_offset = (int32_t *)p;
         p += b_off;
-        v.bins = (int32_t *)p;
+        v.bins = (GGTileFace *)p;
         p += b_bin;
         v.winner = (int32_t *)p;
         p += b_win;

@@ -284,3 +284,33 @@ def test_mixed_sizes_rejected(torch, lib):
     gg[1].W = gg[1].W - 1
     with pytest.raises(lib.GeograypherB200Error, match="same image size"):
         ctx.rasterize(gg)
+
+
+def test_scratch_overflow_is_detected_and_recovered(torch, lib):
+    """A deliberately tiny (tile, face) capacity: gg_sync reports GG_ERR_OVERFLOW, the wrapper grows the scratch and
+    replays; results equal the unconstrained run."""
+    from geograypher_b200 import synthetic as syn
+
+    v32, faces, cams, cfg = _scene("c1", 2)
+    W, H = cfg.image_size
+    F, C = len(faces), cfg.n_classes
+    gg = [_to_gg(lib, c) for c in cams]
+    idx = [torch.from_numpy(syn.class_index_image(k, H, W, C)).cuda() for k in range(len(cams))]
+    ctx = _context(torch, lib, v32, faces)
+    ref = ctx.rasterize(gg).clone()
+    ref_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda")
+    ref_cnt = torch.zeros((F,), dtype=torch.int32, device="cuda")
+    ctx.project_aggregate(gg, idx, lib.PRED_INDEX_U8, C, lib.MODE_LAST_PIXEL, 0, ref_sum, ref_cnt)
+
+    small = _context(torch, lib, v32, faces)
+    small.reserve(0, 1000)
+    out = torch.empty_like(ref)
+    with pytest.raises(lib.GeograypherB200Error, match="overflow"):
+        small.rasterize(gg, out=out, check=False)
+        small.sync()
+    assert torch.equal(small.rasterize(gg), ref)  # check=True grows and replays
+    small.reserve(0, 1000)
+    d_sum = torch.zeros_like(ref_sum)
+    d_cnt = torch.zeros_like(ref_cnt)
+    small.project_aggregate(gg, idx, lib.PRED_INDEX_U8, C, lib.MODE_LAST_PIXEL, 0, d_sum, d_cnt)
+    assert torch.equal(d_sum, ref_sum) and torch.equal(d_cnt, ref_cnt)
