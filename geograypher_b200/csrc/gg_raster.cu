@@ -455,19 +455,23 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
     const int tile_x0 = (tile % tiles_x) * GG_TILE_W, tile_y0 = (tile / tiles_x) * GG_TILE_H;
 
     __shared__ GGTileFace s_all[GG_RASTER_WARPS][GG_CHUNK];
+    __shared__ int s_win_all[WINNERS ? GG_RASTER_WARPS : 1][GG_CHUNK];
     GGTileFace *s_faces = s_all[warp];
+    int *s_win = s_win_all[WINNERS ? warp : 0];  // last pixel won by the first GG_CHUNK list positions
 
     const int tx0 = (lane & 3) * 8;  // this lane: pixels tx0..tx0+7 of row ty
     const int ty = lane >> 2;
 
     float bw[8];
-    int bf[8], br[8];  // winning face ID and its record index, -1 = none
+    int bf[8], bp[8];  // winning face ID and its position in the tile's list, -1 = none
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         bw[i] = 0.f;
         bf[i] = -1;
-        br[i] = -1;
+        bp[i] = -1;
     }
+    if (WINNERS) s_win[lane] = -1;
+    const float fty = (float)ty, ftx0 = (float)tx0;
 
     const bool overflow = vs.counters[3] != 0;
     const int beg = vs.tile_offset[tile];
@@ -489,6 +493,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
             const int4 q3 = *reinterpret_cast<const int4 *>(&s_faces[k].lanemask);  // lanemask face rec fast
             if (!((((unsigned)q3.x) >> lane) & 1u)) continue;
             const int face = q3.y;
+            const int pos = base + k;
             if (q3.w) {
                 const int4 q0 = *reinterpret_cast<const int4 *>(&s_faces[k].e[0]);   // e0 e1 e2 sx0
                 const int4 q1 = *reinterpret_cast<const int4 *>(&s_faces[k].sx[1]);  // sx1 sx2 sy0 sy1
@@ -498,15 +503,15 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                 int e1 = q0.y + s1 * tx0 + q1.w * ty;
                 int e2 = q0.z + s2 * tx0 + q2.x * ty;
                 const float gx = __int_as_float(q2.z);
-                const float wrow = fmaf(__int_as_float(q2.w), (float)ty, __int_as_float(q2.y));
+                const float wrow = fmaf(gx, ftx0, fmaf(__int_as_float(q2.w), fty, __int_as_float(q2.y)));
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if ((e0 | e1 | e2) >= 0) {
-                        const float w = fmaf(gx, (float)(tx0 + i), wrow);
+                        const float w = fmaf(gx, (float)i, wrow);
                         if (w > bw[i] || (w == bw[i] && face < bf[i])) {
                             bw[i] = w;
                             bf[i] = face;
-                            br[i] = q3.z;
+                            bp[i] = pos;
                         }
                     }
                     e0 += s0;
@@ -522,7 +527,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                         if (w > bw[i] || (w == bw[i] && face < bf[i])) {
                             bw[i] = w;
                             bf[i] = face;
-                            br[i] = q3.z;
+                            bp[i] = pos;
                         }
                     }
                 }
@@ -561,23 +566,29 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
     if (WINNERS) {
         // Last pixel (row-major) won by every face record.  Only the end of a run of equal winners inside this lane's
         // 8 pixels can be the face's last pixel of the row; a run continued by the next strip is left to that strip.
-        // Lanes holding a run-end of the same record are then grouped with match.any: pixel indices grow with the lane
-        // index (lane = row * 4 + strip), so the highest lane of each group issues the only atomicMax.
-        const int next_first = __shfl_down_sync(0xffffffffu, br[0], 1);
+        // Run-ends are max-reduced per list position in shared memory, then one atomicMax per (tile, face) goes to
+        // the view's winner array.
+        const int next_first = __shfl_down_sync(0xffffffffu, bp[0], 1);
         const bool has_next = (lane & 3) != 3;
         int bgmax = -1;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const bool in_img = row_ok && (col + i < W);
             const int pix = row * W + col + i;
-            const int nxt = (i < 7) ? ((col + i + 1 < W) ? br[i + 1] : -2) : ((has_next && col + 8 < W) ? next_first : -2);
-            const bool emit = in_img && br[i] >= 0 && br[i] != nxt;
-            if (in_img && br[i] < 0) bgmax = pix;  // pixel index grows with i
-            if (__any_sync(0xffffffffu, emit)) {   // warp-uniform
-                const int key = emit ? br[i] : -1 - lane;  // distinct negative keys for idle lanes
-                const unsigned grp = __match_any_sync(0xffffffffu, key);
-                if (emit && (31 - __clz(grp)) == lane) atomicMax(&vs.winner[key], pix);
+            const int nxt = (i < 7) ? ((col + i + 1 < W) ? bp[i + 1] : -2) : ((has_next && col + 8 < W) ? next_first : -2);
+            if (in_img) {
+                if (bp[i] < 0) {
+                    bgmax = pix;  // pixel index grows with i
+                } else if (bp[i] != nxt) {
+                    if (bp[i] < GG_CHUNK) atomicMax(&s_win[bp[i]], pix);
+                    else atomicMax(&vs.winner[vs.bins[beg + bp[i]].rec], pix);
+                }
             }
+        }
+        __syncwarp();
+        if (lane < len) {  // len > GG_CHUNK: the first chunk's setups were overwritten, fetch the record index again
+            const int p = s_win[lane];
+            if (p >= 0) atomicMax(&vs.winner[len <= GG_CHUNK ? s_faces[lane].rec : vs.bins[beg + lane].rec], p);
         }
         if (compat_bg) {
             bgmax = __reduce_max_sync(0xffffffffu, bgmax);
