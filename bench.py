@@ -38,12 +38,12 @@ METRIC = "views/s, pix2face+aggregate (Mpix/s in extras)"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c5", "tiny"])
     ap.add_argument("--mode", default="last_pixel", choices=["last_pixel", "pixel_sum"])
-    ap.add_argument("--views-per-step", type=int, default=8)
+    ap.add_argument("--views-per-step", type=int, default=10)
     ap.add_argument("--e2e-views", type=int, default=32, help="views per rank in the end-to-end (host buffer) run")
     ap.add_argument("--cpu-views", type=int, default=6, help="views in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -114,54 +114,81 @@ __global__ void __launch_bounds__(256) k_resolve_vote(int32_t *__restrict__ winn
     if (cls >= 0 && cls < C) sum[f * C + cls] += 1.0;
 }
 
-// ---- fused path: consume the per-record winners that k_raster_tiles<true> left for one view ---------------
-// One thread per face record of the view (grid-stride; the record count lives on the device).  The extra index
-// r == n_recs handles the meshes.py:2000 quirk when face F-1 has no record of its own.
+// ---- fused path: consume the per-face winners that k_raster_tiles<true> left for a batch of views -------------
+// blockIdx.y = view, grid-stride over that view's face records (the record count lives on the device).  A face seen
+// by several views of the batch is handled by the thread of the EARLIEST such view, which then walks the later
+// views in order: every face's float64 sum is accumulated in view order (bit-identical to the reference's loop,
+// meshes.py:2056-2062) with no atomics.  The extra index r == n_recs covers the meshes.py:2000 quirk when face F-1
+// has no record of its own but background pixels were written to its slot.
 template <typename T>
-__global__ void __launch_bounds__(256) k_resolve_recs(const __grid_constant__ GGViewBatch views, int n_views, int view,
-                                                      int64_t F, const T *__restrict__ pred, int C, int pred_kind,
-                                                      int mode, int flags, double *__restrict__ sum,
-                                                      int32_t *__restrict__ count) {
+__global__ void __launch_bounds__(256) k_resolve_batch(const __grid_constant__ GGViewBatch views, int n_views, int64_t F,
+                                                       const __grid_constant__ GGPredBatch preds, int C, int pred_kind,
+                                                       int mode, int flags, double *__restrict__ sum,
+                                                       int32_t *__restrict__ count) {
     // A scratch overflow anywhere in the batch voids the whole batch: nothing is accumulated, so the host can grow
     // the scratch and replay the same views in the same order.
     for (int v = 0; v < n_views; ++v)
         if (views.v[v].counters[3] != 0) return;
+    const int view = blockIdx.y;
     const GGViewScratch &vs = views.v[view];
     const int n_recs = vs.counters[1];
     const bool compat = (flags & GG_FLAG_COMPAT_NEG) != 0;
-    const int bg = compat ? vs.counters[4] : -1;
-    const int last_rec = vs.counters[5];
-    const int n = n_recs + ((compat && last_rec < 0) ? 1 : 0);
+    const int n = n_recs + ((compat && vs.counters[5] < 0) ? 1 : 0);
+    const bool keep_nan = (flags & GG_FLAG_KEEP_NAN) != 0;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        int p;
-        int64_t f;
-        if (r < n_recs) {
-            p = vs.winner[r];
-            f = vs.recs[r].face;
-            if (compat && r == last_rec) p = max(p, bg);
-        } else {
-            p = bg;
-            f = F - 1;
-        }
-        if (p < 0) continue;
+        const int64_t f = r < n_recs ? (int64_t)vs.recs[r].face : F - 1;
+        if (vs.winner[f] < 0) continue;
+        bool earlier = false;
+        for (int u = 0; u < view; ++u) earlier = earlier || (views.v[u].winner[f] >= 0);
+        if (earlier) continue;
         if (mode == GG_MODE_VOTE) {
-            const double v = (double)pred[p];
-            if (!isfinite(v)) continue;
-            count[f] += 1;
-            const long long cls = (long long)v;
-            if (cls >= 0 && cls < C) sum[f * C + cls] += 1.0;
-        } else if (pred_kind == GG_PRED_INDEX_U8) {
-            const int cls = (int)pred[p];
-            if (cls < C) sum[f * C + cls] += 1.0;
-            count[f] += 1;
-        } else {
-            bool any_finite = false;
-            for (int c = 0; c < C; ++c) {
-                const double v = (double)pred[(int64_t)p * C + c];
-                any_finite = any_finite || isfinite(v);
-                if (!isnan(v) || (flags & GG_FLAG_KEEP_NAN)) sum[f * C + c] += v;
+            int cnt = 0;
+            for (int u = view; u < n_views; ++u) {
+                const int p = views.v[u].winner[f];
+                if (p < 0) continue;
+                const double v = (double)((const T *)preds.p[u])[p];
+                if (!isfinite(v)) continue;
+                cnt += 1;
+                const long long cls = (long long)v;
+                if (cls >= 0 && cls < C) sum[f * C + cls] += 1.0;
             }
-            if (any_finite) count[f] += 1;
+            count[f] += cnt;
+        } else if (pred_kind == GG_PRED_INDEX_U8) {
+            int cnt = 0;
+            for (int u = view; u < n_views; ++u) {
+                const int p = views.v[u].winner[f];
+                if (p < 0) continue;
+                const int cls = (int)((const T *)preds.p[u])[p];
+                if (cls < C) sum[f * C + cls] += 1.0;
+                cnt += 1;  // a one-hot row is always finite, even the all-zero row of an ignored pixel
+            }
+            count[f] += cnt;
+        } else {
+            unsigned fin = 0;  // bit u: view u contributed a finite value
+            for (int c0 = 0; c0 < C; c0 += 8) {
+                double acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = (c0 + j < C) ? sum[f * C + c0 + j] : 0.0;
+                for (int u = view; u < n_views; ++u) {
+                    const int p = views.v[u].winner[f];
+                    if (p < 0) continue;
+                    const T *row = (const T *)preds.p[u] + (int64_t)p * C + c0;
+                    double vals[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) vals[j] = (c0 + j < C) ? (double)row[j] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (c0 + j < C) {
+                            if (isfinite(vals[j])) fin |= 1u << u;
+                            if (!isnan(vals[j]) || keep_nan) acc[j] += vals[j];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (c0 + j < C) sum[f * C + c0 + j] = acc[j];
+            }
+            count[f] += __popc(fin);
         }
     }
 }
@@ -318,16 +345,17 @@ int gg_launch_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W
     return GG_OK;
 }
 
-int gg_launch_resolve_view(gg_context *ctx, int view, const void *d_pred, int pred_kind, int C, int mode, int flags,
-                           double *d_sum, int32_t *d_count, cudaStream_t st) {
-    const unsigned g = (unsigned)(ctx->sm_count * 2);
-    const int nv = ctx->last_batch_n;
+int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, int pred_kind, int C, int mode, int flags,
+                            double *d_sum, int32_t *d_count, cudaStream_t st) {
+    GGPredBatch pb;
+    for (int i = 0; i < GG_MAX_VIEWS_PER_CALL; ++i) pb.p[i] = i < n ? h_pred[i] : nullptr;
+    const dim3 g((unsigned)(ctx->sm_count * 2), n);
     const int64_t F = ctx->F;
     switch (pred_kind) {
-        case GG_PRED_F32: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<float><<<g, 256, 0, st>>>(ctx->views, nv, view, F, (const float *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
-        case GG_PRED_F64: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<double><<<g, 256, 0, st>>>(ctx->views, nv, view, F, (const double *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_F32: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_batch<float><<<g, 256, 0, st>>>(ctx->views, n, F, pb, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_F64: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_batch<double><<<g, 256, 0, st>>>(ctx->views, n, F, pb, C, pred_kind, mode, flags, d_sum, d_count)); break;
         case GG_PRED_U8:
-        case GG_PRED_INDEX_U8: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_recs<uint8_t><<<g, 256, 0, st>>>(ctx->views, nv, view, F, (const uint8_t *)d_pred, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_INDEX_U8: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_batch<uint8_t><<<g, 256, 0, st>>>(ctx->views, n, F, pb, C, pred_kind, mode, flags, d_sum, d_count)); break;
         default: gg_set_error("gg_project_aggregate: bad pred_kind"); return GG_ERR_INVALID;
     }
     return GG_OK;

@@ -98,6 +98,7 @@ void gg_destroy(gg_context *ctx) {
     cudaFree(ctx->d_block_hi);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_winner);
+    cudaFree(ctx->d_wdense);
     cudaFree(ctx->d_raster);
     for (auto &p : ctx->prof.pending) {
         cudaEventDestroy(p.a);
@@ -203,6 +204,9 @@ int gg_set_mesh(gg_context *ctx, const float *d_verts, int64_t V, const int32_t 
     cudaFree(ctx->d_block_lo);
     cudaFree(ctx->d_block_hi);
     cudaFree(ctx->d_winner);
+    cudaFree(ctx->d_wdense);
+    ctx->d_wdense = nullptr;
+    ctx->wdense_cap = 0;
     ctx->d_verts = nullptr;
     ctx->d_faces = nullptr;
     ctx->d_block_lo = ctx->d_block_hi = nullptr;
@@ -296,11 +300,7 @@ int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const 
         // sum is accumulated in view order (bit-identical to the reference's loop, meshes.py:2056-2062).
         rc = gg_launch_rasterize(ctx, h_cams, n, d_pix2face, nullptr, 1, flags & GG_FLAG_COMPAT_NEG, st);
         if (rc != GG_OK) return rc;
-        for (int i = 0; i < n; ++i) {
-            rc = gg_launch_resolve_view(ctx, i, h_pred[i], pred_kind, C, mode, flags, d_sum, d_count, st);
-            if (rc != GG_OK) return rc;
-        }
-        return GG_OK;
+        return gg_launch_resolve_batch(ctx, n, h_pred, pred_kind, C, mode, flags, d_sum, d_count, st);
     }
     int32_t *raster = d_pix2face;
     if (!raster) {

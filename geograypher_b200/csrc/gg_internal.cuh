@@ -57,13 +57,17 @@ struct GGViewScratch {  // device pointers of one batch slot
     int32_t *tile_count;   // [n_tiles]   faces per tile (zeroed by the reserve pass, rebuilt by the fill pass)
     int32_t *tile_offset;  // [n_tiles]   start of the tile's list in bins (lists are not in tile order)
     GGTileFace *bins;      // [cap_bins]  per-(tile, face) setups grouped by tile
-    int32_t *winner;       // [cap_recs]  last (row-major) pixel won by each record in this view, -1 = none
+    int32_t *winner;       // [F]  last (row-major) pixel won by each FACE in this view, -1 = none (fused aggregation)
     int32_t *counters;     // [8]: 0 n_vis_blocks, 1 n_recs, 2 n_bin_entries, 3 overflow flag, 4 bg winner,
                            //      5 rec index of face F-1 (or -1)
 };
 
 struct GGViewBatch {
     GGViewScratch v[GG_MAX_VIEWS_PER_CALL];
+};
+
+struct GGPredBatch {  // device pointers of the views' prediction images
+    const void *p[GG_MAX_VIEWS_PER_CALL];
 };
 
 // ---- per-stage launch counting and (optional) CUDA-event timing ------------------------------------------
@@ -115,6 +119,8 @@ struct gg_context {
     GGViewBatch views;
     int32_t *d_winner = nullptr;  // [F] last-pixel winner per face (dense, unfused aggregation)
     int64_t winner_cap = 0;
+    int32_t *d_wdense = nullptr;  // [n_slots * F] per-view per-face winners of the fused aggregation
+    int64_t wdense_cap = 0;
     int32_t *d_raster = nullptr;  // internal n x H x W raster when the caller does not want pix2face back
     int64_t raster_cap = 0;
     int last_batch_n = 0;
@@ -156,9 +162,9 @@ int gg_launch_project(gg_context *ctx, const gg_camera *cams, int n, int32_t *dX
                       uint8_t *dvalid, cudaStream_t st);
 int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *d_pix2face, float *d_depth,
                         int want_winners, int compat_bg, cudaStream_t st);
-// gg_aggregate.cu: consume the per-record winners of view `view` of the last rasterization batch
-int gg_launch_resolve_view(gg_context *ctx, int view, const void *d_pred, int pred_kind, int C, int mode, int flags,
-                           double *d_sum, int32_t *d_count, cudaStream_t st);
+// gg_aggregate.cu: consume the per-face winners of the last rasterization batch (all views, in view order)
+int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, int pred_kind, int C, int mode, int flags,
+                            double *d_sum, int32_t *d_count, cudaStream_t st);
 // gg_aggregate.cu
 int gg_launch_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred,
                         int pred_kind, int C, int mode, int compat, double *d_sum, int32_t *d_count,

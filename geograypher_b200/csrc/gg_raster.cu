@@ -307,7 +307,6 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__
                     }
                 r.tmask = small ? tmask : ~0ull;
                 vs.recs[idx] = r;
-                vs.winner[idx] = -1;
                 if (r.face == (int32_t)(F - 1)) vs.counters[5] = idx;
             } else {
                 atomicOr(&vs.counters[3], 1);
@@ -391,7 +390,10 @@ __global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __gri
     if (vs.counters[3] != 0) return;
     const int n_recs = vs.counters[1];
     const int tiles_x = (cams.cam[view].W + GG_TILE_W - 1) / GG_TILE_W;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_recs; r += gridDim.x * blockDim.x) {
+    // 8 lanes share one record and split its tiles, so that the atomicAdd -> store chains of a face run in parallel
+    const int sub = threadIdx.x & 7;
+    const int groups = (gridDim.x * blockDim.x) >> 3;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n_recs; r += groups) {
         const GGFaceRec rec = vs.recs[r];
         const int tx0 = rec.jmin / GG_TILE_W, tx1 = rec.jmax / GG_TILE_W;
         const int ty0 = rec.imin / GG_TILE_H, ty1 = rec.imax / GG_TILE_H;
@@ -399,22 +401,24 @@ __global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __gri
         const unsigned long long tmask = rec.tmask;
         if (tmask != ~0ull) {
             unsigned long long m = tmask;
-            while (m) {
+            for (int idx = 0; m; ++idx) {
                 const int b = __ffsll((long long)m) - 1;
                 m &= m - 1;
+                if ((idx & 7) != sub) continue;
                 const int tx = tx0 + b % ntx, ty = ty0 + b / ntx;
                 const int t = ty * tiles_x + tx;
                 setup_tile_face(vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)], rec, r, tx * GG_TILE_W,
                                 ty * GG_TILE_H);
             }
         } else {
-            for (int ty = ty0; ty <= ty1; ++ty)
-                for (int tx = tx0; tx <= tx1; ++tx) {
-                    if (!tile_may_touch(rec, tx, ty)) continue;
-                    const int t = ty * tiles_x + tx;
-                    setup_tile_face(vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)], rec, r,
-                                    tx * GG_TILE_W, ty * GG_TILE_H);
-                }
+            const int total = ntx * (ty1 - ty0 + 1);
+            for (int i = sub; i < total; i += 8) {
+                const int tx = tx0 + i % ntx, ty = ty0 + i / ntx;
+                if (!tile_may_touch(rec, tx, ty)) continue;
+                const int t = ty * tiles_x + tx;
+                setup_tile_face(vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)], rec, r, tx * GG_TILE_W,
+                                ty * GG_TILE_H);
+            }
         }
     }
 }
@@ -581,18 +585,18 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                     bgmax = pix;  // pixel index grows with i
                 } else if (bp[i] != nxt) {
                     if (bp[i] < GG_CHUNK) atomicMax(&s_win[bp[i]], pix);
-                    else atomicMax(&vs.winner[vs.bins[beg + bp[i]].rec], pix);
+                    else atomicMax(&vs.winner[bf[i]], pix);
                 }
             }
         }
         __syncwarp();
-        if (lane < len) {  // len > GG_CHUNK: the first chunk's setups were overwritten, fetch the record index again
+        if (lane < len) {  // len > GG_CHUNK: the first chunk's setups were overwritten, fetch the face ID again
             const int p = s_win[lane];
-            if (p >= 0) atomicMax(&vs.winner[len <= GG_CHUNK ? s_faces[lane].rec : vs.bins[beg + lane].rec], p);
+            if (p >= 0) atomicMax(&vs.winner[len <= GG_CHUNK ? s_faces[lane].face : vs.bins[beg + lane].face], p);
         }
-        if (compat_bg) {
+        if (compat_bg) {  // meshes.py:2000: background pixels index the last face
             bgmax = __reduce_max_sync(0xffffffffu, bgmax);
-            if (lane == 0 && bgmax >= 0) atomicMax(&vs.counters[4], bgmax);
+            if (lane == 0 && bgmax >= 0) atomicMax(&vs.winner[compat_bg - 1], bgmax);
         }
     }
 }
@@ -622,9 +626,8 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
     const size_t b_cnt = align_up((size_t)slot_tiles * 4, 256);
     const size_t b_off = align_up((size_t)slot_tiles * 4, 256);
     const size_t b_bin = align_up((size_t)cap_bins * sizeof(GGTileFace), 256);
-    const size_t b_win = align_up((size_t)cap_recs * 4, 256);
     const size_t b_ctr = 256;
-    const size_t per_slot = b_vis + b_rec + b_cnt + b_off + b_bin + b_win + b_ctr;
+    const size_t per_slot = b_vis + b_rec + b_cnt + b_off + b_bin + b_ctr;
     GG_CUDA(cudaMalloc(&ctx->d_scratch, per_slot * slots));
     ctx->scratch_bytes = per_slot * slots;
     for (int s = 0; s < slots; ++s) {
@@ -640,8 +643,6 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
         p += b_off;
         v.bins = (GGTileFace *)p;
         p += b_bin;
-        v.winner = (int32_t *)p;
-        p += b_win;
         v.counters = (int32_t *)p;
     }
     ctx->n_slots = slots;
@@ -683,6 +684,19 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
         GG_CUDA(cudaMemsetAsync(ctx->views.v[i].counters + 4, 0xFF, 8, st));
     }
     ctx->last_batch_n = n;
+    if (want_winners) {
+        if (ctx->wdense_cap < (int64_t)n * ctx->F) {
+            if (ctx->d_wdense) {
+                GG_CUDA(cudaDeviceSynchronize());
+                GG_CUDA(cudaFree(ctx->d_wdense));
+                ctx->d_wdense = nullptr;
+            }
+            GG_CUDA(cudaMalloc(&ctx->d_wdense, (size_t)n * ctx->F * 4));
+            ctx->wdense_cap = (int64_t)n * ctx->F;
+        }
+        for (int i = 0; i < n; ++i) ctx->views.v[i].winner = ctx->d_wdense + (int64_t)i * ctx->F;
+        GG_CUDA(cudaMemsetAsync(ctx->d_wdense, 0xFF, (size_t)n * ctx->F * 4, st));
+    }
     const int nb = (int)ctx->n_blocks;
     GG_LAUNCH(ctx, GG_ST_CULL, st,
               k_cull_blocks<<<dim3((nb + 255) / 256, n), 256, 0, st>>>(ctx->d_block_lo, ctx->d_block_hi, nb, cb, ctx->views));
@@ -697,7 +711,7 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
     if (want_winners)
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
                   k_raster_tiles<true><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, n_tiles, d_pix2face, d_depth,
-                                                                            compat_bg));
+                                                                            compat_bg ? (int)ctx->F : 0));
     else
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
                   k_raster_tiles<false><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, n_tiles, d_pix2face, d_depth, 0));
