@@ -25,7 +25,7 @@
 #define GG_CHUNK 32            // faces staged per warp per pass (one per lane)
 #define GG_BLOCK_FACES 128     // faces per cull block
 
-struct GGFaceRec {  // one surviving face of one view, orientation-normalised (area2 > 0); 96 B
+struct __align__(16) GGFaceRec {  // one surviving face of one view, orientation-normalised (area2 > 0); 128 B
     int32_t A[3], B[3];    // edge gradients in sub-pixel units: E_k(P) = A_k*Px + B_k*Py + const, A = -dy, B = dx
     long long C[3];        // E_k at the centre of pixel (0,0), top-left bias folded in (>= 0 <=> inside)
     double w00, gx, gy;    // 1/z plane per pixel: w(j, i) = w00 + gx*j + gy*i
@@ -34,8 +34,9 @@ struct GGFaceRec {  // one surviving face of one view, orientation-normalised (a
     uint16_t jmin, jmax, imin, imax;  // pixel-centre index range, clamped to the raster
     unsigned long long tmask;  // which tiles of the bounding box the triangle can touch (bit = row-major index in the
                                // box), or ~0 when the box has more than 64 tiles (the fill pass then re-tests)
+    int pad[6];                // one 128-byte line per record: written and read as 8 x 16 B
 };
-static_assert(sizeof(GGFaceRec) == 104, "GGFaceRec layout");
+static_assert(sizeof(GGFaceRec) == 128, "GGFaceRec layout");
 
 struct __align__(16) GGTileFace {  // a face record re-expressed relative to one 32 x 8 tile; 64 B
     int e[3], sx[3], sy[3];        // fast path: biased edge functions at the tile-origin pixel centre + per-pixel steps

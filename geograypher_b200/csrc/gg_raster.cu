@@ -78,6 +78,26 @@ __device__ __forceinline__ int warp_append(int *counter, bool keep) {
     return keep ? base + __popc(m & ((1u << lane) - 1u)) : -1;
 }
 
+// Whole-struct stores / loads as 16-byte vectors (full 32-byte sectors, no partial-sector read-modify-write in L2).
+template <typename S>
+__device__ __forceinline__ void store_vec16(S *dst, const S &src) {
+    static_assert(sizeof(S) % 16 == 0, "16-byte multiple");
+    const int4 *s4 = reinterpret_cast<const int4 *>(&src);
+    int4 *d4 = reinterpret_cast<int4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(S) / 16); ++i) d4[i] = s4[i];
+}
+
+template <typename S>
+__device__ __forceinline__ S load_vec16(const S *src) {
+    S out;
+    const int4 *s4 = reinterpret_cast<const int4 *>(src);
+    int4 *d4 = reinterpret_cast<int4 *>(&out);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(S) / 16); ++i) d4[i] = __ldg(s4 + i);
+    return out;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Mesh preprocessing: bounding box of every block of GG_BLOCK_FACES consecutive faces.
 // ------------------------------------------------------------------------------------------------------
@@ -306,7 +326,7 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__
                         if (small) tmask |= 1ull << ((ty - ty0) * ntx + (tx - tx0));
                     }
                 r.tmask = small ? tmask : ~0ull;
-                vs.recs[idx] = r;
+                store_vec16(&vs.recs[idx], r);
                 if (r.face == (int32_t)(F - 1)) vs.counters[5] = idx;
             } else {
                 atomicOr(&vs.counters[3], 1);
@@ -345,7 +365,8 @@ __global__ void __launch_bounds__(256) k_reserve_tiles(int n_tiles, int64_t cap_
 
 // Tile-relative setup of one face: done once per (tile, face) pair by the fill pass so that the rasterizer only
 // streams ready-made 64-byte records.
-__device__ __forceinline__ void setup_tile_face(GGTileFace &tf, const GGFaceRec &r, int rec, int tile_x0, int tile_y0) {
+__device__ __forceinline__ GGTileFace setup_tile_face(const GGFaceRec &r, int rec, int tile_x0, int tile_y0) {
+    GGTileFace tf;
     bool fits = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -377,6 +398,7 @@ __device__ __forceinline__ void setup_tile_face(GGTileFace &tf, const GGFaceRec 
     tf.face = r.face;
     tf.rec = rec;
     tf.fast = fits ? 1u : 0u;
+    return tf;
 }
 
 __global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __grid_constant__ GGCamBatch cams,
@@ -394,7 +416,7 @@ __global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __gri
     const int sub = threadIdx.x & 7;
     const int groups = (gridDim.x * blockDim.x) >> 3;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n_recs; r += groups) {
-        const GGFaceRec rec = vs.recs[r];
+        const GGFaceRec rec = load_vec16(&vs.recs[r]);
         const int tx0 = rec.jmin / GG_TILE_W, tx1 = rec.jmax / GG_TILE_W;
         const int ty0 = rec.imin / GG_TILE_H, ty1 = rec.imax / GG_TILE_H;
         const int ntx = tx1 - tx0 + 1;
@@ -407,8 +429,8 @@ __global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __gri
                 if ((idx & 7) != sub) continue;
                 const int tx = tx0 + b % ntx, ty = ty0 + b / ntx;
                 const int t = ty * tiles_x + tx;
-                setup_tile_face(vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)], rec, r, tx * GG_TILE_W,
-                                ty * GG_TILE_H);
+                store_vec16(&vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)],
+                            setup_tile_face(rec, r, tx * GG_TILE_W, ty * GG_TILE_H));
             }
         } else {
             const int total = ntx * (ty1 - ty0 + 1);
@@ -416,8 +438,8 @@ __global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __gri
                 const int tx = tx0 + i % ntx, ty = ty0 + i / ntx;
                 if (!tile_may_touch(rec, tx, ty)) continue;
                 const int t = ty * tiles_x + tx;
-                setup_tile_face(vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)], rec, r, tx * GG_TILE_W,
-                                ty * GG_TILE_H);
+                store_vec16(&vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)],
+                            setup_tile_face(rec, r, tx * GG_TILE_W, ty * GG_TILE_H));
             }
         }
     }
