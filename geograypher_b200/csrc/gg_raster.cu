@@ -422,15 +422,18 @@ __global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __gri
         const int ntx = tx1 - tx0 + 1;
         const unsigned long long tmask = rec.tmask;
         if (tmask != ~0ull) {
+            // lane `sub` takes the set bits number sub, sub + 8, ...: skip ahead first so that all lanes of the warp
+            // reach the (expensive) setup code together
             unsigned long long m = tmask;
-            for (int idx = 0; m; ++idx) {
+            for (int s = 0; s < sub && m; ++s) m &= m - 1;
+            while (m) {
                 const int b = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                if ((idx & 7) != sub) continue;
-                const int tx = tx0 + b % ntx, ty = ty0 + b / ntx;
+                const int by = b / ntx;
+                const int tx = tx0 + (b - by * ntx), ty = ty0 + by;
                 const int t = ty * tiles_x + tx;
                 store_vec16(&vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)],
                             setup_tile_face(rec, r, tx * GG_TILE_W, ty * GG_TILE_H));
+                for (int s = 0; s < 8 && m; ++s) m &= m - 1;
             }
         } else {
             const int total = ntx * (ty1 - ty0 + 1);
