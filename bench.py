@@ -383,13 +383,21 @@ def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, my_cams, dev, w
     dt = float(dt.item())
     steps = -(-n_views // args.views_per_step)
     F = len(faces)
+    zero_copy = all(torch.from_numpy(h).is_pinned() for h in host)
+    seen_per_view = float(info["projection_counts"].sum()) / max(n_views, 1)
+    row_bytes = -(-C * 4 // 32) * 32  # PCIe reads are sector-granular
+    h2d = seen_per_view * row_bytes * n_views / steps if zero_copy else H * W * C * 4 * n_views / steps
     return {"value": n_views * world / dt, "unit": "views/s",
-            "h2d_bytes_per_step": int(H * W * C * 4 * n_views / steps),
+            "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int((F * C * 8 * 2 + F * 4) / steps),
             "views": n_views * world, "seconds": dt,
             "api": "TexturedPhotogrammetryMesh.aggregate_projected_images(SegmentorPhotogrammetryCameraSet)",
-            "note": "float32 (H,W,C) scores copied from pinned host memory every view; per-rank results are not "
-                    "all-reduced in this leg"}
+            "note": ("float32 (H,W,C) score images stay in pinned HOST memory; last-pixel aggregation needs one row per "
+                     "visible face, which the resolve kernel reads over PCIe through unified addressing (h2d bytes = "
+                     "rows actually fetched, estimated from the per-face counts); the per-face float64 averages, sums "
+                     "and counts are copied back at the end" if zero_copy else
+                     "float32 (H,W,C) score images uploaded from host memory every view") +
+                    "; per-rank results are not all-reduced in this leg"}
 
 
 def main():

@@ -1,0 +1,85 @@
+"""Camera-sharded multi-GPU aggregation.
+
+Views are independent; the only coupling between them is the per-face accumulator pair
+``(sum[F, C] float64, count[F] int32)``, a commutative sum over views (reference meshes.py:2057-2067; the
+reference's chunked variant already merges partial sums this way, derived_meshes.py:292-302).  So: one process per
+GPU, the mesh replicated, the cameras split into contiguous blocks, and ONE all-reduce of the accumulators at the
+end, followed by the mean / argmax epilogue.  ``render_flat`` has no coupling at all (replicas only).
+
+The functions take an initialised ``torch.distributed`` process group (NCCL on GPUs; the host-side logic is
+exercised with gloo on CPU tensors in tests/test_distributed_gloo.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_items: int, rank: int, world_size: int):
+    """Contiguous block of ``ceil(n / world)`` items for ``rank`` (neighbouring views share faces, which keeps a
+    rank's working set of the mesh hot in L2)."""
+    per = -(-n_items // world_size)
+    lo = min(n_items, rank * per)
+    return range(lo, min(n_items, lo + per))
+
+
+def shard_cameras(cameras, rank: int, world_size: int):
+    """The sub-set of a PhotogrammetryCameraSet (or of a SegmentorPhotogrammetryCameraSet) that ``rank`` owns."""
+    return cameras.get_subset_cameras(list(shard_range(len(cameras), rank, world_size)))
+
+
+def allreduce_accumulators(d_sum, d_count, group=None):
+    """In-place sum of the per-face accumulators over all ranks.  Counts (and one-hot / vote sums) are integers
+    and therefore identical for any number of ranks; float64 sums of real-valued scores differ from the single-GPU
+    result only by the association order of at most ``world_size`` partial sums (~1e-16 relative)."""
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return d_sum, d_count
+    dist.all_reduce(d_sum, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(d_count, op=dist.ReduceOp.SUM, group=group)
+    return d_sum, d_count
+
+
+def finalize_host(summed, counts):
+    """NumPy form of the epilogue of aggregate_projected_images (reference meshes.py:2069-2082), for accumulators
+    that were reduced on the host (gloo)."""
+    summed = np.array(summed, dtype=float, copy=True)
+    counts = np.asarray(counts, dtype=float)
+    summed[counts == 0] = np.nan
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return summed / counts[:, None], counts, summed
+
+
+def aggregate_projected_images_distributed(mesh, cameras, aggregate_img_scale: float = 1, return_argmax: bool = False,
+                                           group=None, **kwargs):
+    """``TexturedPhotogrammetryMesh.aggregate_projected_images`` over all ranks of ``group``.
+
+    Every rank passes the SAME full camera set and gets the same full result back; internally it only processes
+    its own block of cameras.  ``mesh.device`` must be this rank's GPU.
+    """
+    import torch.distributed as dist
+
+    from geograypher_b200 import _lib
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = shard_cameras(cameras, rank, world)
+    pix2face_kwargs = {k: v for k, v in kwargs.items() if k != "check_null_image"}
+    n_total = len(cameras)
+    if len(mine) > 0:
+        d_sum, d_count, C = mesh._accumulate_views(mine, aggregate_img_scale, _lib.MODE_LAST_PIXEL,
+                                                   pix2face_kwargs=pix2face_kwargs,
+                                                   single_view_total=(n_total == 1))
+    else:
+        import torch
+
+        C = cameras.n_image_channels()
+        dev = torch.device("cuda", mesh.device)
+        d_sum = torch.zeros((mesh.faces.shape[0], C), dtype=torch.float64, device=dev)
+        d_count = torch.zeros((mesh.faces.shape[0],), dtype=torch.int32, device=dev)
+    allreduce_accumulators(d_sum, d_count, group)
+    avg, argmax = mesh._get_context().finalize(d_sum, d_count, want_avg=True, want_argmax=return_argmax)
+    info = {"projection_counts": d_count.cpu().numpy().astype(float), "summed_projections": d_sum.cpu().numpy()}
+    if return_argmax:
+        info["argmax"] = argmax.cpu().numpy()
+    return avg.cpu().numpy(), info

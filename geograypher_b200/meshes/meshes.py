@@ -34,6 +34,16 @@ from geograypher_b200.constants import (
 from geograypher_b200.utils.indexing import determine_IDs_to_labels
 
 
+class _HostMapped:
+    """A pinned host tensor handed to the kernels by address (zero-copy)."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+    def data_ptr(self):
+        return self.tensor.data_ptr()
+
+
 class LocalMesh:
     """The mesh in a camera set's local frame (what the reference passes around as a transformed
     ``pv.PolyData``): float64 ``points`` (V, 3), ``faces`` (F, 3) and the device context that holds the float32
@@ -510,6 +520,19 @@ class TexturedPhotogrammetryMesh:
         p2f = p2f[None] if p2f.ndim == 2 else p2f
         return torch.from_numpy(p2f.astype(np.int32)).to(torch.device("cuda", self.device))
 
+    @staticmethod
+    def _to_device_or_mapped(arr, dev, zero_copy=True):
+        """Device tensor for a host prediction image.  The fused last-pixel / vote aggregation reads ONE pixel per
+        visible face, so an image that already sits in page-locked host memory is not copied at all: CUDA's unified
+        addressing lets the kernel fetch those few rows over PCIe straight from the host buffer.  Pageable arrays
+        are uploaded."""
+        import torch
+
+        t = torch.from_numpy(arr)
+        if zero_copy and t.is_pinned():
+            return _HostMapped(t)
+        return t.to(dev, non_blocking=True)
+
     def _fetch_prediction(self, cameras, k, scale, image_getter, index_getter):
         """(array, pred_kind, C) of view k: a caller-supplied getter, else the segmentor's class-index image when
         it offers one (expanded on the GPU), else whatever get_image_by_index returns."""
@@ -522,7 +545,7 @@ class TexturedPhotogrammetryMesh:
         return self._classify_image(cameras.get_image_by_index(k, scale))
 
     def _accumulate_views(self, cameras, aggregate_img_scale, mode, n_channels=None, pix2face_kwargs=None,
-                          image_getter=None):
+                          image_getter=None, single_view_total=None):
         """Shared driver of the aggregation variants: streams every view's prediction image to the GPU and runs
         rasterize + aggregate there.  Returns (d_sum, d_count, C) still on the device."""
         import torch
@@ -534,7 +557,8 @@ class TexturedPhotogrammetryMesh:
         F = self.faces.shape[0]
         apply_distortion = pix2face_kwargs.get("apply_distortion", True) and pix2face_kwargs.get("distortion_set") is not None
         n = len(cam_list)
-        flags = self._flags(_lib.FLAG_KEEP_NAN if (n == 1 and mode == _lib.MODE_LAST_PIXEL) else 0)
+        single = (n == 1) if single_view_total is None else single_view_total
+        flags = self._flags(_lib.FLAG_KEEP_NAN if (single and mode == _lib.MODE_LAST_PIXEL) else 0)
         d_sum = d_count = None
         C = n_channels
         B = 1 if apply_distortion else self.views_per_batch
@@ -556,7 +580,7 @@ class TexturedPhotogrammetryMesh:
                     kind = this_kind
                 elif kind != this_kind:
                     raise ValueError("all prediction images of a batch must share one dtype / layout")
-                preds.append(torch.from_numpy(arr).to(dev, non_blocking=True))
+                preds.append(self._to_device_or_mapped(arr, dev, zero_copy=not apply_distortion))
             if apply_distortion:
                 p2f = self._pix2face_for_aggregation(batch[0], mesh, aggregate_img_scale, pix2face_kwargs)
                 mesh.context.aggregate(p2f[0], preds[0], kind, C, mode, flags, d_sum, d_count)
