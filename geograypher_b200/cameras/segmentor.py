@@ -27,10 +27,18 @@ class SegmentorPhotogrammetryCameraSet(PhotogrammetryCameraSet):
         filename = self.base_camera_set.get_image_filename(index, absolute=True)
         fn = getattr(self.segmentor, method)
         kwargs = {"filename": filename, "image_scale": image_scale}
-        params = inspect.signature(fn).parameters
-        if "index" in params or any(p.kind == inspect.Parameter.VAR_KEYWORD for p in params.values()):
+        if self._takes_index(method, fn):
             kwargs["index"] = self._indices[index]  # reference-style segmentors only take filename / image_scale
         return fn(raw, **kwargs)
+
+    def _takes_index(self, method, fn):
+        cache = self.__dict__.setdefault("_takes_index_cache", {})
+        if method not in cache:
+            params = inspect.signature(fn).parameters
+            cache[method] = "index" in params or any(
+                p.kind == inspect.Parameter.VAR_KEYWORD for p in params.values()
+            )
+        return cache[method]
 
     def get_image_by_index(self, index: int, image_scale: float = 1) -> np.ndarray:
         return self._segment(index, image_scale, "segment_image")

@@ -533,6 +533,25 @@ class TexturedPhotogrammetryMesh:
             return _HostMapped(t)
         return t.to(dev, non_blocking=True)
 
+    def _to_host(self, *tensors):
+        """Device tensors -> fresh NumPy arrays owned by the caller.  The transfer goes through page-locked staging
+        buffers that the mesh keeps (full PCIe rate), followed by a multi-threaded host copy into new arrays."""
+        import torch
+
+        outs = []
+        stage = self.__dict__.setdefault("_pinned_stage", {})
+        for i, t in enumerate(tensors):
+            key = (i, t.dtype, tuple(t.shape))
+            if key not in stage:
+                for old in [k for k in stage if k[0] == i]:
+                    del stage[old]
+                stage[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            stage[key].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        for i, t in enumerate(tensors):
+            outs.append(torch.empty(t.shape, dtype=t.dtype).copy_(stage[(i, t.dtype, tuple(t.shape))]).numpy())
+        return outs
+
     def _fetch_prediction(self, cameras, k, scale, image_getter, index_getter):
         """(array, pred_kind, C) of view k: a caller-supplied getter, else the segmentor's class-index image when
         it offers one (expanded on the GPU), else whatever get_image_by_index returns."""
@@ -615,11 +634,12 @@ class TexturedPhotogrammetryMesh:
                                                    pix2face_kwargs=pix2face_kwargs)
         ctx = self._get_context()
         avg, argmax = ctx.finalize(d_sum, d_count, want_avg=True, want_argmax=return_argmax)
-        info["projection_counts"] = d_count.cpu().numpy().astype(float)
-        info["summed_projections"] = d_sum.cpu().numpy()
+        h_avg, h_sum, h_count = self._to_host(avg, d_sum, d_count.double())
+        info["projection_counts"] = h_count
+        info["summed_projections"] = h_sum
         if return_argmax:
             info["argmax"] = argmax.cpu().numpy()
-        return avg.cpu().numpy(), info
+        return h_avg, info
 
     # ------------------------------------------------------------------------------------------------
     # label_polygons
