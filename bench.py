@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c5", "tiny"])
     ap.add_argument("--mode", default="last_pixel", choices=["last_pixel", "pixel_sum"])
     ap.add_argument("--views-per-step", type=int, default=10)
-    ap.add_argument("--e2e-views", type=int, default=32, help="views per rank in the end-to-end (host buffer) run")
+    ap.add_argument("--e2e-views", type=int, default=500, help="views per rank in the end-to-end (host buffer) run")
     ap.add_argument("--cpu-views", type=int, default=6, help="views in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
