@@ -146,6 +146,11 @@ def cpu_predictions(cfg, n_distinct=2):
     return out
 
 
+def host_threads():
+    """All host cores, regardless of OMP_NUM_THREADS (torchrun sets it to 1)."""
+    return max(1, os.cpu_count() or 1)
+
+
 def cpu_views_per_second(verts, faces, c2ws, cfg, origin, view_ids, preds, on_step=None):
     """Oracle port of pix2face + aggregate_projected_images over `view_ids`; returns (seconds per view list,
     raster seconds, aggregate seconds)."""
@@ -161,7 +166,7 @@ def cpu_views_per_second(verts, faces, c2ws, cfg, origin, view_ids, preds, on_st
     for j, k in enumerate(view_ids):
         t0 = time.perf_counter()
         cam = ora.make_camera(c2ws[k], cfg.f, cfg.cx, cfg.cy, W, H, origin=origin)
-        p2f = ora.rasterize(v32, faces, cam)
+        p2f = ora.rasterize(v32, faces, cam, nthreads=host_threads())
         t1 = time.perf_counter()
         proj = ora.project_image(p2f, preds[j % len(preds)], F)  # meshes.py:1988-2001
         summed = proj.astype(float) if summed is None else np.nansum([summed, proj], axis=0)  # :2056-2062
@@ -191,7 +196,7 @@ def run_reference(args):
     timed = per_view[args.warmup:]
     total = float(sum(timed))
     value = len(timed) / total
-    cores = ora.num_threads()
+    cores = host_threads()
     sample = (f"{len(timed)} views of {args.config} (1 view per step), OpenMP C rasterizer on {cores} threads + "
               f"single-threaded NumPy aggregation as in the reference")
     line = {
@@ -328,7 +333,7 @@ def run_ours(args):
 
         ids = [(7 + 3 * i) % len(c2ws) for i in range(args.cpu_views)]
         per_view, t_r, t_a = cpu_views_per_second(verts, faces, c2ws, cfg, origin, ids, cpu_predictions(cfg))
-        cpu = {"value": len(per_view) / float(sum(per_view)), "unit": "views/s", "cores": ora.num_threads(),
+        cpu = {"value": len(per_view) / float(sum(per_view)), "unit": "views/s", "cores": host_threads(),
                "kind": "port",
                "sample": f"{len(per_view)} views of {args.config}; OpenMP C rasterizer on all cores + single-threaded "
                          f"NumPy aggregation (the reference's aggregation is single-threaded NumPy)",
