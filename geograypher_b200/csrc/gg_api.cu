@@ -302,6 +302,10 @@ int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const 
         if (rc != GG_OK) return rc;
         return gg_launch_resolve_batch(ctx, n, h_pred, pred_kind, C, mode, flags, d_sum, d_count, st);
     }
+    if (mode == GG_MODE_PIXEL_SUM && C <= 32) {
+        // Fused dense mode: the rasterizer's epilogue streams the score images and adds every pixel to its face.
+        return gg_launch_rasterize(ctx, h_cams, n, d_pix2face, nullptr, 0, 0, st, h_pred, pred_kind, C, d_sum, d_count);
+    }
     int32_t *raster = d_pix2face;
     if (!raster) {
         const int64_t need = P * n;

@@ -161,8 +161,10 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H);
 int gg_launch_mesh_blocks(gg_context *ctx, cudaStream_t st);
 int gg_launch_project(gg_context *ctx, const gg_camera *cams, int n, int32_t *dX, int32_t *dY, float *dinvz,
                       uint8_t *dvalid, cudaStream_t st);
+// h_pred != nullptr selects the fused dense per-pixel-sum epilogue (GG_MODE_PIXEL_SUM, C <= 32)
 int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *d_pix2face, float *d_depth,
-                        int want_winners, int compat_bg, cudaStream_t st);
+                        int want_winners, int compat_bg, cudaStream_t st, const void *const *h_pred = nullptr,
+                        int pred_kind = 0, int C = 0, double *d_sum = nullptr, int32_t *d_count = nullptr);
 // gg_aggregate.cu: consume the per-face winners of the last rasterization batch (all views, in view order)
 int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, int pred_kind, int C, int mode, int flags,
                             double *d_sum, int32_t *d_count, cudaStream_t st);

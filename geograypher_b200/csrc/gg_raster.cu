@@ -16,6 +16,8 @@
 //                   face ID (C4); writes int32 face IDs coalesced.
 // The result does not depend on the order in which faces land in a tile list, so the atomics used for
 // compaction do not make it non-deterministic.
+#include <cstring>
+
 #include "gg_internal.cuh"
 
 namespace {
@@ -468,11 +470,34 @@ __device__ __noinline__ bool exact_cover(const GGFaceRec &r, int j, int i, float
     return true;
 }
 
-template <bool WINNERS>
+// MODE 0: rasters only.  MODE 1: + last pixel of every face (fused last-pixel / vote aggregation).
+// MODE 2: + dense per-pixel score sums (GG_MODE_PIXEL_SUM), T = element type of the score images.
+#define GG_RM_PLAIN 0
+#define GG_RM_WINNERS 1
+#define GG_RM_DENSE 2
+
+struct GGDenseArgs {
+    GGPredBatch preds;
+    double *sum;     // [F][C]
+    int32_t *count;  // [F]
+    int C;
+    int index_kind;  // 1: (H,W) uint8 class index expanded on the fly
+};
+
+template <typename T>
+__device__ __forceinline__ float dense_load(const T *__restrict__ pred, int64_t pix, int C, int ch, int index_kind) {
+    if (index_kind) return ((int)pred[pix] == ch) ? 1.f : 0.f;
+    const float v = (float)pred[pix * C + ch];
+    return v == v ? v : 0.f;  // NaN = null -> contributes nothing
+}
+
+template <int MODE, typename T>
 __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_raster_tiles(const __grid_constant__ GGCamBatch cams,
                                                                        const __grid_constant__ GGViewBatch views,
                                                                        int n_tiles, int32_t *__restrict__ pix2face,
-                                                                       float *__restrict__ depth, int compat_bg) {
+                                                                       float *__restrict__ depth, int compat_bg,
+                                                                       const __grid_constant__ GGDenseArgs dense) {
+    constexpr bool WINNERS = (MODE == GG_RM_WINNERS);
     const int view = blockIdx.y;
     const gg_camera &c = cams.cam[view];
     const GGViewScratch &vs = views.v[view];
@@ -624,6 +649,102 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
             if (lane == 0 && bgmax >= 0) atomicMax(&vs.winner[compat_bg - 1], bgmax);
         }
     }
+
+    if (MODE == GG_RM_DENSE) {
+        // Per-pixel scatter-add of the view's (H, W, C) scores into per-face sums, without the raster ever leaving
+        // the SM.  The lanes are re-mapped from "8 pixels each" to (pixel group, channel): g = 32 / C consecutive
+        // pixels are read per step, one float per lane, so every load instruction covers g*C*4 contiguous bytes of
+        // the image row.  Each lane keeps a running sum for its channel while the winning face stays the same and
+        // flushes it to the tile's shared-memory accumulators (indexed by list position) when the face changes;
+        // the tile then issues one float64 atomicAdd per (face, channel).
+        extern __shared__ float s_dyn[];
+        __shared__ unsigned char s_pos_all[GG_RASTER_WARPS][GG_TILE_W * GG_TILE_H];
+        __shared__ int s_cnt_all[GG_RASTER_WARPS][GG_CHUNK];
+        const int C = dense.C;
+        float *s_acc = s_dyn + warp * (GG_CHUNK * C);
+        unsigned char *s_pos = s_pos_all[warp];
+        int *s_cnt = s_cnt_all[warp];
+        const T *__restrict__ pred = (const T *)dense.preds.p[view];
+        {
+            unsigned lo = 0, hi = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const unsigned b = bp[i] < 0 ? 255u : (bp[i] < GG_CHUNK ? (unsigned)bp[i] : 254u);
+                if (i < 4) lo |= b << (8 * i);
+                else hi |= b << (8 * (i - 4));
+            }
+            *reinterpret_cast<uint2 *>(&s_pos[ty * GG_TILE_W + tx0]) = make_uint2(lo, hi);
+        }
+        for (int i = lane; i < GG_CHUNK * C; i += 32) s_acc[i] = 0.f;
+        s_cnt[lane] = 0;
+        __syncwarp();
+        const int g = 32 / C;  // pixels per step (C <= 32 on this path)
+        const int grp = lane / C, ch = lane - grp * C;
+        if (grp < g) {
+            float acc = 0.f;
+            int cnt = 0;
+            unsigned cur = 255u;
+            for (int t0 = grp; t0 < GG_TILE_W * GG_TILE_H; t0 += 4 * g) {
+                float v[4];
+                unsigned ps[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {  // issue the loads of four steps before consuming them
+                    const int t = t0 + u * g;
+                    ps[u] = 255u;
+                    v[u] = 0.f;
+                    if (t < GG_TILE_W * GG_TILE_H) {
+                        const int r = tile_y0 + (t >> 5), cc = tile_x0 + (t & 31);
+                        if (r < H && cc < W) {
+                            ps[u] = s_pos[t];
+                            if (ps[u] < (unsigned)GG_CHUNK) v[u] = dense_load<T>(pred, (int64_t)r * W + cc, C, ch, dense.index_kind);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (ps[u] != cur) {
+                        if (cur < (unsigned)GG_CHUNK) {
+                            atomicAdd(&s_acc[cur * C + ch], acc);
+                            if (ch == 0) atomicAdd(&s_cnt[cur], cnt);
+                        }
+                        acc = 0.f;
+                        cnt = 0;
+                        cur = ps[u];
+                    }
+                    if (ps[u] < (unsigned)GG_CHUNK) {
+                        acc += v[u];
+                        cnt += 1;
+                    }
+                }
+            }
+            if (cur < (unsigned)GG_CHUNK) {
+                atomicAdd(&s_acc[cur * C + ch], acc);
+                if (ch == 0) atomicAdd(&s_cnt[cur], cnt);
+            }
+        }
+        __syncwarp();
+        const int nk = min(len, GG_CHUNK);
+        for (int idx = lane; idx < nk * C; idx += 32) {
+            const int k = idx / C, cch = idx - k * C;
+            if (s_cnt[k] > 0) {
+                const int64_t face = len <= GG_CHUNK ? s_faces[k].face : vs.bins[beg + k].face;
+                atomicAdd(&dense.sum[face * C + cch], (double)s_acc[idx]);
+                if (cch == 0) atomicAdd(&dense.count[face], s_cnt[k]);
+            }
+        }
+        // list positions beyond the shared-memory table (tiles with more than GG_CHUNK faces): direct atomics
+        if (len > GG_CHUNK) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (bp[i] >= GG_CHUNK && row_ok && col + i < W) {
+                    const int64_t pix = (int64_t)row * W + col + i;
+                    for (int cch = 0; cch < C; ++cch)
+                        atomicAdd(&dense.sum[(int64_t)bf[i] * C + cch], (double)dense_load<T>(pred, pix, C, cch, dense.index_kind));
+                    atomicAdd(&dense.count[bf[i]], 1);
+                }
+            }
+        }
+    }
 }
 
 }  // namespace
@@ -694,8 +815,19 @@ int gg_launch_project(gg_context *ctx, const gg_camera *cams, int n, int32_t *dX
     return GG_OK;
 }
 
+template <typename T>
+static int launch_dense(gg_context *ctx, const GGCamBatch &cb, dim3 rgrid, int n_tiles, int32_t *d_pix2face,
+                        const GGDenseArgs &da, cudaStream_t st) {
+    const size_t dyn = (size_t)GG_RASTER_WARPS * GG_CHUNK * da.C * sizeof(float);
+    GG_LAUNCH(ctx, GG_ST_RASTER, st,
+              (k_raster_tiles<GG_RM_DENSE, T><<<rgrid, GG_RASTER_THREADS, dyn, st>>>(cb, ctx->views, n_tiles, d_pix2face,
+                                                                                    nullptr, 0, da)));
+    return GG_OK;
+}
+
 int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *d_pix2face, float *d_depth,
-                        int want_winners, int compat_bg, cudaStream_t st) {
+                        int want_winners, int compat_bg, cudaStream_t st, const void *const *h_pred, int pred_kind,
+                        int C, double *d_sum, int32_t *d_count) {
     const int W = cams[0].W, H = cams[0].H;
     int rc = gg_ensure_scratch(ctx, n, W, H);
     if (rc != GG_OK) return rc;
@@ -733,12 +865,29 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
               k_reserve_tiles<<<dim3((n_tiles + 255) / 256, n), 256, 0, st>>>(n_tiles, ctx->cap_recs, ctx->views));
     GG_LAUNCH(ctx, GG_ST_FILL, st, k_fill_bins<<<dim3(ctx->sm_count * 4, n), 256, 0, st>>>(ctx->cap_bins, cb, ctx->views));
     const dim3 rgrid((n_tiles + GG_RASTER_WARPS - 1) / GG_RASTER_WARPS, n);
+    GGDenseArgs da;
+    memset(&da, 0, sizeof(da));
+    if (h_pred) {  // fused dense per-pixel sums
+        for (int i = 0; i < n; ++i) da.preds.p[i] = h_pred[i];
+        da.sum = d_sum;
+        da.count = d_count;
+        da.C = C;
+        da.index_kind = pred_kind == GG_PRED_INDEX_U8;
+        switch (pred_kind) {
+            case GG_PRED_F32: return launch_dense<float>(ctx, cb, rgrid, n_tiles, d_pix2face, da, st);
+            case GG_PRED_F64: return launch_dense<double>(ctx, cb, rgrid, n_tiles, d_pix2face, da, st);
+            case GG_PRED_U8:
+            case GG_PRED_INDEX_U8: return launch_dense<uint8_t>(ctx, cb, rgrid, n_tiles, d_pix2face, da, st);
+            default: gg_set_error("bad pred_kind"); return GG_ERR_INVALID;
+        }
+    }
     if (want_winners)
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  k_raster_tiles<true><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, n_tiles, d_pix2face, d_depth,
-                                                                            compat_bg ? (int)ctx->F : 0));
+                  (k_raster_tiles<GG_RM_WINNERS, float><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
+                      cb, ctx->views, n_tiles, d_pix2face, d_depth, compat_bg ? (int)ctx->F : 0, da)));
     else
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  k_raster_tiles<false><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, n_tiles, d_pix2face, d_depth, 0));
+                  (k_raster_tiles<GG_RM_PLAIN, float><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, n_tiles,
+                                                                                          d_pix2face, d_depth, 0, da)));
     return GG_OK;
 }

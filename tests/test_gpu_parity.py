@@ -314,3 +314,47 @@ def test_scratch_overflow_is_detected_and_recovered(torch, lib):
     d_cnt = torch.zeros_like(ref_cnt)
     small.project_aggregate(gg, idx, lib.PRED_INDEX_U8, C, lib.MODE_LAST_PIXEL, 0, d_sum, d_cnt)
     assert torch.equal(d_sum, ref_sum) and torch.equal(d_cnt, ref_cnt)
+
+
+@pytest.mark.parametrize("kind", ["f32", "index", "u8"])
+def test_fused_pixel_sum_matches_numpy(torch, lib, kind):
+    """gg_project_aggregate(GG_MODE_PIXEL_SUM): the rasterizer's dense epilogue (every pixel adds its scores) against
+    a NumPy scatter-add over the oracle's rasters.  Not a reference mode; tolerance 1e-5 relative (float32 partial
+    sums per tile, float64 across tiles)."""
+    from geograypher_b200 import synthetic as syn
+
+    v32, faces, cams, cfg = _scene("c1", 4)
+    W, H = cfg.image_size
+    F, C = len(faces), cfg.n_classes
+    ctx = _context(torch, lib, v32, faces)
+    gg = [_to_gg(lib, c) for c in cams]
+    p2f = ctx.rasterize(gg).cpu().numpy()
+    if kind == "f32":
+        host = [syn.softmax_predictions(k, H, W, C, grid=(5, 7)) for k in range(len(cams))]
+        for h in host:
+            h[::9, ::4, 2] = np.nan
+        dense = [np.nan_to_num(h.astype(np.float64), nan=0.0) for h in host]
+        code = lib.PRED_F32
+    elif kind == "index":
+        host = [syn.class_index_image(k, H, W, C) for k in range(len(cams))]
+        dense = [ora.inds_to_one_hot(h, C).astype(np.float64) for h in host]
+        code = lib.PRED_INDEX_U8
+    else:
+        host = [ora.inds_to_one_hot(syn.class_index_image(k, H, W, C), C).view(np.uint8) for k in range(len(cams))]
+        dense = [h.astype(np.float64) for h in host]
+        code = lib.PRED_U8
+    preds = [torch.from_numpy(h).cuda() for h in host]
+    d_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda")
+    d_count = torch.zeros((F,), dtype=torch.int32, device="cuda")
+    out = torch.empty((len(cams), H, W), dtype=torch.int32, device="cuda")
+    ctx.project_aggregate(gg, preds, code, C, lib.MODE_PIXEL_SUM, 0, d_sum, d_count, pix2face_out=out)
+    np.testing.assert_array_equal(out.cpu().numpy(), p2f)
+    ref_sum = np.zeros((F, C))
+    ref_cnt = np.zeros(F, dtype=np.int64)
+    for k in range(len(cams)):
+        ids = p2f[k].ravel()
+        keep = ids >= 0
+        np.add.at(ref_sum, ids[keep], dense[k].reshape(-1, C)[keep])
+        np.add.at(ref_cnt, ids[keep], 1)
+    np.testing.assert_array_equal(d_count.cpu().numpy(), ref_cnt)
+    np.testing.assert_allclose(d_sum.cpu().numpy(), ref_sum, rtol=1e-5, atol=1e-6)
