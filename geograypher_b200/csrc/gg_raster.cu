@@ -651,17 +651,18 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
     }
 
     if (MODE == GG_RM_DENSE) {
-        // Per-pixel scatter-add of the view's (H, W, C) scores into per-face sums, without the raster ever leaving
-        // the SM.  The lanes are re-mapped from "8 pixels each" to (pixel group, channel): g = 32 / C consecutive
-        // pixels are read per step, one float per lane, so every load instruction covers g*C*4 contiguous bytes of
-        // the image row.  Each lane keeps a running sum for its channel while the winning face stays the same and
-        // flushes it to the tile's shared-memory accumulators (indexed by list position) when the face changes;
-        // the tile then issues one float64 atomicAdd per (face, channel).
+        // Per-pixel scatter-add of the view's (H, W, C) scores into per-face sums; the raster never leaves the SM.
+        // The lanes are re-mapped from "8 pixels each" to (pixel group, channel): g = 32 / C pixels are read per
+        // step and lane l reads float  step * g*C + l  of the tile row, so every load instruction covers g*C*4
+        // contiguous bytes and a lane's channel never changes.  A lane sums in a register while the winning face
+        // stays the same and spills into its PRIVATE shared-memory slot s_acc[list position][lane] when it changes
+        // (no shared-memory atomics: float atomicAdd on shared memory is a CAS loop).  The tile then issues one
+        // float64 atomicAdd per (face, channel).
         extern __shared__ float s_dyn[];
         __shared__ unsigned char s_pos_all[GG_RASTER_WARPS][GG_TILE_W * GG_TILE_H];
         __shared__ int s_cnt_all[GG_RASTER_WARPS][GG_CHUNK];
         const int C = dense.C;
-        float *s_acc = s_dyn + warp * (GG_CHUNK * C);
+        float *s_acc = s_dyn + warp * (GG_CHUNK * 32);
         unsigned char *s_pos = s_pos_all[warp];
         int *s_cnt = s_cnt_all[warp];
         const T *__restrict__ pred = (const T *)dense.preds.p[view];
@@ -675,61 +676,72 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
             }
             *reinterpret_cast<uint2 *>(&s_pos[ty * GG_TILE_W + tx0]) = make_uint2(lo, hi);
         }
-        for (int i = lane; i < GG_CHUNK * C; i += 32) s_acc[i] = 0.f;
+        const int nk = min(len, GG_CHUNK);
+        for (int i = lane; i < nk * 32; i += 32) s_acc[i] = 0.f;
         s_cnt[lane] = 0;
         __syncwarp();
-        const int g = 32 / C;  // pixels per step (C <= 32 on this path)
-        const int grp = lane / C, ch = lane - grp * C;
-        if (grp < g) {
-            float acc = 0.f;
-            int cnt = 0;
-            unsigned cur = 255u;
-            for (int t0 = grp; t0 < GG_TILE_W * GG_TILE_H; t0 += 4 * g) {
-                float v[4];
-                unsigned ps[4];
+        {  // pixel counts per list position: integer shared-memory atomics are native, one per run of equal winners
+            int run = 0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {  // issue the loads of four steps before consuming them
-                    const int t = t0 + u * g;
-                    ps[u] = 255u;
-                    v[u] = 0.f;
-                    if (t < GG_TILE_W * GG_TILE_H) {
-                        const int r = tile_y0 + (t >> 5), cc = tile_x0 + (t & 31);
-                        if (r < H && cc < W) {
-                            ps[u] = s_pos[t];
-                            if (ps[u] < (unsigned)GG_CHUNK) v[u] = dense_load<T>(pred, (int64_t)r * W + cc, C, ch, dense.index_kind);
-                        }
+            for (int i = 0; i < 8; ++i) {
+                const bool in_img = row_ok && (col + i < W);
+                if (in_img && bp[i] >= 0 && bp[i] < GG_CHUNK) {
+                    run += 1;
+                    const bool last = (i == 7) || (bp[i + 1 < 8 ? i + 1 : 7] != bp[i]) || !(col + i + 1 < W);
+                    if (last) {
+                        atomicAdd(&s_cnt[bp[i]], run);
+                        run = 0;
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (ps[u] != cur) {
-                        if (cur < (unsigned)GG_CHUNK) {
-                            atomicAdd(&s_acc[cur * C + ch], acc);
-                            if (ch == 0) atomicAdd(&s_cnt[cur], cnt);
-                        }
-                        acc = 0.f;
-                        cnt = 0;
-                        cur = ps[u];
-                    }
-                    if (ps[u] < (unsigned)GG_CHUNK) {
-                        acc += v[u];
-                        cnt += 1;
-                    }
-                }
-            }
-            if (cur < (unsigned)GG_CHUNK) {
-                atomicAdd(&s_acc[cur * C + ch], acc);
-                if (ch == 0) atomicAdd(&s_cnt[cur], cnt);
             }
         }
+        const int g = 32 / C;                 // pixels per step (C <= 32 on this path)
+        const int gC = g * C;                 // floats per step
+        const int grp = lane / C, ch = lane - grp * C;
+        const int cols = min(GG_TILE_W, W - tile_x0), rows = min(GG_TILE_H, H - tile_y0);
+        const int steps = (cols + g - 1) / g;
+        if (lane < gC && nk > 0) {
+            float acc = 0.f;
+            unsigned cur = 255u;
+            for (int r = 0; r < rows; ++r) {
+                const int64_t pix0 = (int64_t)(tile_y0 + r) * W + tile_x0;
+                const unsigned char *prow = s_pos + r * GG_TILE_W;
+                for (int j0 = 0; j0 < steps; j0 += 4) {
+                    float v[4];
+                    unsigned ps[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {  // issue the loads of four steps before consuming them
+                        const int x = (j0 + u) * g + grp;
+                        ps[u] = 255u;
+                        v[u] = 0.f;
+                        if (x < cols) {
+                            ps[u] = prow[x];
+                            v[u] = dense_load<T>(pred, pix0 + x, C, ch, dense.index_kind);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (ps[u] != cur) {
+                            if (cur < (unsigned)GG_CHUNK) s_acc[cur * 32 + lane] += acc;
+                            acc = 0.f;
+                            cur = ps[u];
+                        }
+                        acc += v[u];
+                    }
+                }
+            }
+            if (cur < (unsigned)GG_CHUNK) s_acc[cur * 32 + lane] += acc;
+        }
         __syncwarp();
-        const int nk = min(len, GG_CHUNK);
         for (int idx = lane; idx < nk * C; idx += 32) {
             const int k = idx / C, cch = idx - k * C;
-            if (s_cnt[k] > 0) {
+            const int n_px = s_cnt[k];
+            float total = 0.f;
+            for (int q = 0; q < g; ++q) total += s_acc[k * 32 + q * C + cch];
+            if (n_px > 0) {
                 const int64_t face = len <= GG_CHUNK ? s_faces[k].face : vs.bins[beg + k].face;
-                atomicAdd(&dense.sum[face * C + cch], (double)s_acc[idx]);
-                if (cch == 0) atomicAdd(&dense.count[face], s_cnt[k]);
+                atomicAdd(&dense.sum[face * C + cch], (double)total);
+                if (cch == 0) atomicAdd(&dense.count[face], n_px);
             }
         }
         // list positions beyond the shared-memory table (tiles with more than GG_CHUNK faces): direct atomics
@@ -818,7 +830,7 @@ int gg_launch_project(gg_context *ctx, const gg_camera *cams, int n, int32_t *dX
 template <typename T>
 static int launch_dense(gg_context *ctx, const GGCamBatch &cb, dim3 rgrid, int n_tiles, int32_t *d_pix2face,
                         const GGDenseArgs &da, cudaStream_t st) {
-    const size_t dyn = (size_t)GG_RASTER_WARPS * GG_CHUNK * da.C * sizeof(float);
+    const size_t dyn = (size_t)GG_RASTER_WARPS * GG_CHUNK * 32 * sizeof(float);
     GG_LAUNCH(ctx, GG_ST_RASTER, st,
               (k_raster_tiles<GG_RM_DENSE, T><<<rgrid, GG_RASTER_THREADS, dyn, st>>>(cb, ctx->views, n_tiles, d_pix2face,
                                                                                     nullptr, 0, da)));
