@@ -703,30 +703,41 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
         if (lane < gC && nk > 0) {
             float acc = 0.f;
             unsigned cur = 255u;
+            const bool index_kind = dense.index_kind != 0;
+            const int stride = index_kind ? g : gC;              // elements per step
+            const int first = index_kind ? grp : lane;           // this lane's element in step 0
+            const int last = (index_kind ? cols : cols * C) - 1;  // last element of the tile row
             for (int r = 0; r < rows; ++r) {
                 const int64_t pix0 = (int64_t)(tile_y0 + r) * W + tile_x0;
+                const T *__restrict__ rp = pred + (index_kind ? pix0 : pix0 * C);
                 const unsigned char *prow = s_pos + r * GG_TILE_W;
                 for (int j0 = 0; j0 < steps; j0 += 4) {
-                    float v[4];
+                    T raw[4];
                     unsigned ps[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {  // issue the loads of four steps before consuming them
+                    for (int u = 0; u < 4; ++u)  // four independent, unconditional loads (index clamped to the row)
+                        raw[u] = rp[min((j0 + u) * stride + first, last)];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
                         const int x = (j0 + u) * g + grp;
-                        ps[u] = 255u;
-                        v[u] = 0.f;
-                        if (x < cols) {
-                            ps[u] = prow[x];
-                            v[u] = dense_load<T>(pred, pix0 + x, C, ch, dense.index_kind);
-                        }
+                        const unsigned pp = prow[min(x, GG_TILE_W - 1)];
+                        ps[u] = x < cols ? pp : 255u;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
+                        float v;
+                        if (index_kind) {
+                            v = ((int)raw[u] == ch) ? 1.f : 0.f;
+                        } else {
+                            v = (float)raw[u];
+                            v = v == v ? v : 0.f;  // NaN = null -> contributes nothing
+                        }
                         if (ps[u] != cur) {
                             if (cur < (unsigned)GG_CHUNK) s_acc[cur * 32 + lane] += acc;
                             acc = 0.f;
                             cur = ps[u];
                         }
-                        acc += v[u];
+                        acc += v;
                     }
                 }
             }
