@@ -706,7 +706,6 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
             const bool index_kind = dense.index_kind != 0;
             const int stride = index_kind ? g : gC;     // elements per step
             const int first = index_kind ? grp : lane;  // this lane's element in step 0
-            const int steps_full = (cols / g) & ~3;     // steps in which every lane has a pixel, multiple of 4
             auto to_score = [&](T raw) -> float {
                 if (index_kind) return ((int)raw == ch) ? 1.f : 0.f;
                 const float v = (float)raw;
@@ -720,30 +719,44 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                 }
                 acc += v;
             };
+            const int last = (index_kind ? cols : cols * C) - 1;  // last element of the tile row
             for (int r = 0; r < rows; ++r) {
                 const int64_t pix0 = (int64_t)(tile_y0 + r) * W + tile_x0;
-                const T *__restrict__ lp = pred + (index_kind ? pix0 : pix0 * C) + first;
-                const unsigned char *q = s_pos + r * GG_TILE_W + grp;
-                int j = 0;
-                for (; j < steps_full; j += 4) {  // no bounds checks: four independent loads, then the four lookups
-                    const T r0 = lp[0], r1 = lp[stride], r2 = lp[2 * stride], r3 = lp[3 * stride];
-                    const unsigned p0 = q[0], p1 = q[g], p2 = q[2 * g], p3 = q[3 * g];
-                    lp += 4 * stride;
-                    q += 4 * g;
-                    const float v0 = to_score(r0), v1 = to_score(r1), v2 = to_score(r2), v3 = to_score(r3);
-                    if (p0 == cur && p1 == cur && p2 == cur && p3 == cur) {
-                        acc += (v0 + v1) + (v2 + v3);
-                    } else {
-                        consume(p0, v0);
-                        consume(p1, v1);
-                        consume(p2, v2);
-                        consume(p3, v3);
+                const T *__restrict__ rp = pred + (index_kind ? pix0 : pix0 * C);
+                const unsigned char *prow = s_pos + r * GG_TILE_W;
+                for (int j0 = 0; j0 < steps; j0 += 8) {
+                    // eight independent, unconditional loads per lane (element index clamped to the tile row) keep
+                    // enough bytes in flight to cover the HBM latency; the values of steps past the row are ignored
+                    T raw[8];
+                    unsigned ps[8];
+                    int off = j0 * stride + first;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        raw[u] = rp[min(off, last)];
+                        off += stride;
                     }
-                }
-                for (; j < steps; ++j) {  // tail: lanes whose pixel falls outside the tile row sit out
-                    if (j * g + grp < cols) consume(q[0], to_score(lp[0]));
-                    lp += stride;
-                    q += g;
+                    int x = j0 * g + grp;
+                    bool same = true;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const unsigned pp = prow[min(x, GG_TILE_W - 1)];
+                        ps[u] = x < cols ? pp : cur;  // out-of-row steps look like "no change" and add 0
+                        same = same && (ps[u] == cur);
+                        x += g;
+                    }
+                    x = j0 * g + grp;
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        v[u] = (x < cols) ? to_score(raw[u]) : 0.f;
+                        x += g;
+                    }
+                    if (same) {
+                        acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) consume(ps[u], v[u]);
+                    }
                 }
             }
             if (cur < (unsigned)GG_CHUNK) s_acc[cur * 32 + lane] += acc;
