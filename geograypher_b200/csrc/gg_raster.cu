@@ -491,7 +491,7 @@ __device__ __forceinline__ float dense_load(const T *__restrict__ pred, int64_t 
     return v == v ? v : 0.f;  // NaN = null -> contributes nothing
 }
 
-template <int MODE, typename T>
+template <int MODE, typename T, int CT>
 __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_raster_tiles(const __grid_constant__ GGCamBatch cams,
                                                                        const __grid_constant__ GGViewBatch views,
                                                                        int n_tiles, int32_t *__restrict__ pix2face,
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
         extern __shared__ float s_dyn[];
         __shared__ unsigned char s_pos_all[GG_RASTER_WARPS][GG_TILE_W * GG_TILE_H];
         __shared__ int s_cnt_all[GG_RASTER_WARPS][GG_CHUNK];
-        const int C = dense.C;
+        const int C = CT > 0 ? CT : dense.C;  // CT > 0: channel count known at compile time (fully unrolled rows)
         float *s_acc = s_dyn + warp * (GG_CHUNK * 32);
         unsigned char *s_pos = s_pos_all[warp];
         int *s_cnt = s_cnt_all[warp];
@@ -720,43 +720,47 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                 acc += v;
             };
             const int last = (index_kind ? cols : cols * C) - 1;  // last element of the tile row
+            if (CT > 0 && cols == GG_TILE_W) {
+                // Compile-time channel count and a full-width tile: the whole row (kSteps loads per lane) is issued
+                // from one base pointer with immediate offsets before anything is consumed.
+                constexpr int kG = CT > 0 ? 32 / CT : 1, kGC = kG * (CT > 0 ? CT : 1);
+                constexpr int kSteps = (GG_TILE_W + kG - 1) / kG;
+                for (int r = 0; r < rows; ++r) {
+                    const int64_t pix0 = (int64_t)(tile_y0 + r) * W + tile_x0;
+                    const T *__restrict__ lp = pred + (index_kind ? pix0 + grp : pix0 * CT + lane);
+                    const unsigned char *q = s_pos + r * GG_TILE_W + grp;
+                    const int kStride = index_kind ? kG : kGC;
+                    T raw[kSteps];
+#pragma unroll
+                    for (int u = 0; u < kSteps; ++u) {
+                        const bool in_row = (u + 1) * kG <= GG_TILE_W || u * kG + grp < GG_TILE_W;
+                        raw[u] = in_row ? lp[u * kStride] : (T)0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < kSteps; ++u) {
+                        const bool in_row = (u + 1) * kG <= GG_TILE_W || u * kG + grp < GG_TILE_W;
+                        if (in_row) consume(q[u * kG], to_score(raw[u]));
+                    }
+                }
+            } else
             for (int r = 0; r < rows; ++r) {
                 const int64_t pix0 = (int64_t)(tile_y0 + r) * W + tile_x0;
                 const T *__restrict__ rp = pred + (index_kind ? pix0 : pix0 * C);
                 const unsigned char *prow = s_pos + r * GG_TILE_W;
-                for (int j0 = 0; j0 < steps; j0 += 8) {
-                    // eight independent, unconditional loads per lane (element index clamped to the tile row) keep
-                    // enough bytes in flight to cover the HBM latency; the values of steps past the row are ignored
-                    T raw[8];
-                    unsigned ps[8];
-                    int off = j0 * stride + first;
+                for (int j0 = 0; j0 < steps; j0 += 4) {
+                    T raw[4];
+                    unsigned ps[4];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        raw[u] = rp[min(off, last)];
-                        off += stride;
-                    }
-                    int x = j0 * g + grp;
-                    bool same = true;
+                    for (int u = 0; u < 4; ++u)  // four independent, unconditional loads (index clamped to the row)
+                        raw[u] = rp[min((j0 + u) * stride + first, last)];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < 4; ++u) {
+                        const int x = (j0 + u) * g + grp;
                         const unsigned pp = prow[min(x, GG_TILE_W - 1)];
-                        ps[u] = x < cols ? pp : cur;  // out-of-row steps look like "no change" and add 0
-                        same = same && (ps[u] == cur);
-                        x += g;
+                        ps[u] = x < cols ? pp : 255u;
                     }
-                    x = j0 * g + grp;
-                    float v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        v[u] = (x < cols) ? to_score(raw[u]) : 0.f;
-                        x += g;
-                    }
-                    if (same) {
-                        acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) consume(ps[u], v[u]);
-                    }
+                    for (int u = 0; u < 4; ++u) consume(ps[u], ps[u] == 255u ? 0.f : to_score(raw[u]));
                 }
             }
             if (cur < (unsigned)GG_CHUNK) s_acc[cur * 32 + lane] += acc;
@@ -860,9 +864,25 @@ template <typename T>
 static int launch_dense(gg_context *ctx, const GGCamBatch &cb, dim3 rgrid, int n_tiles, int32_t *d_pix2face,
                         const GGDenseArgs &da, cudaStream_t st) {
     const size_t dyn = (size_t)GG_RASTER_WARPS * GG_CHUNK * 32 * sizeof(float);
-    GG_LAUNCH(ctx, GG_ST_RASTER, st,
-              (k_raster_tiles<GG_RM_DENSE, T><<<rgrid, GG_RASTER_THREADS, dyn, st>>>(cb, ctx->views, n_tiles, d_pix2face,
-                                                                                    nullptr, 0, da)));
+#define GG_DENSE_CASE(CT)                                                                                             \
+    case CT:                                                                                                          \
+        GG_LAUNCH(ctx, GG_ST_RASTER, st,                                                                              \
+                  (k_raster_tiles<GG_RM_DENSE, T, CT><<<rgrid, GG_RASTER_THREADS, dyn, st>>>(cb, ctx->views, n_tiles,   \
+                                                                                            d_pix2face, nullptr, 0, da))); \
+        break;
+    switch (da.index_kind ? 0 : da.C) {  // compile-time channel counts for the common cases, generic otherwise
+        GG_DENSE_CASE(3)
+        GG_DENSE_CASE(4)
+        GG_DENSE_CASE(5)
+        GG_DENSE_CASE(8)
+        GG_DENSE_CASE(10)
+        GG_DENSE_CASE(16)
+        default:
+            GG_LAUNCH(ctx, GG_ST_RASTER, st,
+                      (k_raster_tiles<GG_RM_DENSE, T, 0><<<rgrid, GG_RASTER_THREADS, dyn, st>>>(cb, ctx->views, n_tiles,
+                                                                                               d_pix2face, nullptr, 0, da)));
+    }
+#undef GG_DENSE_CASE
     return GG_OK;
 }
 
@@ -924,11 +944,11 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
     }
     if (want_winners)
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  (k_raster_tiles<GG_RM_WINNERS, float><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
+                  (k_raster_tiles<GG_RM_WINNERS, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
                       cb, ctx->views, n_tiles, d_pix2face, d_depth, compat_bg ? (int)ctx->F : 0, da)));
     else
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  (k_raster_tiles<GG_RM_PLAIN, float><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, n_tiles,
+                  (k_raster_tiles<GG_RM_PLAIN, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, n_tiles,
                                                                                           d_pix2face, d_depth, 0, da)));
     return GG_OK;
 }
