@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-views", type=int, default=6, help="views in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--single-mode", action="store_true", help="time only --mode (skip the other aggregation mode)")
     return ap.parse_args()
 
 
@@ -247,7 +248,7 @@ def run_ours(args):
     W, H = cfg.image_size
     C, F, P = cfg.n_classes, len(faces), W * H
     B = args.views_per_step
-    mode = {"last_pixel": _lib.MODE_LAST_PIXEL, "pixel_sum": _lib.MODE_PIXEL_SUM}[args.mode]
+    mode = _lib.MODE_LAST_PIXEL
 
     my_cams = shard(len(c2ws), rank, world)
     ctx = _lib.Context(local_rank)
@@ -270,56 +271,77 @@ def run_ours(args):
             dist.all_reduce(d_count)
         return ctx.finalize(d_sum, d_count)
 
-    for i in range(args.warmup):
-        step(i)
-    ctx.sync()
-    stats = ctx.last_batch_stats(B)
-    d_sum.zero_()
-    d_count.zero_()
-    ctx.profile(True)
-    ctx.profile_read(reset=True)
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    avg, argmax = epilogue()
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
-    elapsed_s = float(elapsed_ms.item()) / 1e3
-    clocks = sampler.stop() if rank == 0 else None
-    ctx.sync()  # surfaces a scratch overflow of the last batch
-    prof = ctx.profile_read(reset=True)
-    ctx.profile(False)
-
-    views = args.steps * B * world
-    value = views / elapsed_s
-    observed = int((d_count > 0).sum().item())
-
-    # ---- roofline of the dominant kernel ---------------------------------------------------------------------
-    raster_ms, raster_launches = prof["raster_tiles"]
-    f_v = float(stats[:, 1].mean())
-    bytes_per_view = 12.0 * (f_v / 2.0) + 12.0 * f_v + 4.0 * P  # B12 = 12 V_v + 12 F_v + 4 P
     peak, peak_src = measured_peak_gbs()
-    achieved = bytes_per_view * B / (raster_ms / max(raster_launches, 1) * 1e-3) / 1e9 if raster_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_raster_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_per_view * B, "avg_launch_ms": raster_ms / max(raster_launches, 1),
-                "note": "last_pixel (reference-parity) mode needs only ~80 MB/view of HBM traffic; the rasterizer is "
-                        "ALU/issue-bound, see DESIGN.md"}
-    stage_ms = {k: round(v[0], 3) for k, v in prof.items() if v[1] > 0}
-    launches = int(sum(v[1] for v in prof.values()))
+
+    def timed_run(run_mode):
+        """W warm-up steps, then K timed steps + all-reduce + finalize, bracketed by barrier + synchronize; the
+        time is the max over ranks.  Returns a dict with the numbers of this mode."""
+        nonlocal mode
+        mode = run_mode
+        d_sum.zero_()
+        d_count.zero_()
+        for i in range(args.warmup):
+            step(i)
+        ctx.sync()
+        stats = ctx.last_batch_stats(B)
+        d_sum.zero_()
+        d_count.zero_()
+        ctx.profile(True)
+        ctx.profile_read(reset=True)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        epilogue()
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+        elapsed_s = float(elapsed_ms.item()) / 1e3
+        clocks = sampler.stop() if rank == 0 else None
+        ctx.sync()  # surfaces a scratch overflow of the last batch
+        prof = ctx.profile_read(reset=True)
+        ctx.profile(False)
+        views = args.steps * B * world
+        raster_ms, raster_launches = prof["raster_tiles"]
+        f_v = float(stats[:, 1].mean())
+        # algorithmic bytes per view (SURVEY 8d).  Stage 1+2: 12 V_v + 12 F_v (+ 4 P only when the raster is written,
+        # which the fused paths do not do).  Dense stage 3: s*C*P scores + read-modify-write of the float64 sums and
+        # int32 counts of the touched faces.
+        b12 = 12.0 * (f_v / 2.0) + 12.0 * f_v
+        if run_mode == _lib.MODE_PIXEL_SUM:
+            bytes_per_view = b12 + 4.0 * C * P + (16.0 * C + 8.0) * f_v
+        else:
+            bytes_per_view = b12 + 4.0 * P  # B12 of SURVEY 8d: the figure for pix2face, IDs written once
+        avg_ms = raster_ms / max(raster_launches, 1)
+        achieved = bytes_per_view * B / (avg_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "k_raster_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": bytes_per_view * B, "avg_launch_ms": avg_ms}
+        return {"value": views / elapsed_s, "elapsed_s": elapsed_s, "roofline": roofline, "clocks": clocks,
+                "stage_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1] > 0},
+                "launches": int(sum(v[1] for v in prof.values())), "faces_per_view": f_v,
+                "faces_observed": int((d_count > 0).sum().item())}
+
+    headline_mode = {"last_pixel": _lib.MODE_LAST_PIXEL, "pixel_sum": _lib.MODE_PIXEL_SUM}[args.mode]
+    other_mode = _lib.MODE_PIXEL_SUM if headline_mode == _lib.MODE_LAST_PIXEL else _lib.MODE_LAST_PIXEL
+    other = timed_run(other_mode) if not args.single_mode else None
+    main = timed_run(headline_mode)
+    value, elapsed_s, roofline, clocks = main["value"], main["elapsed_s"], main["roofline"], main["clocks"]
+    stage_ms, launches, f_v, observed = main["stage_ms"], main["launches"], main["faces_per_view"], main["faces_observed"]
+    if headline_mode == _lib.MODE_LAST_PIXEL:
+        roofline["note"] = ("reference-parity (last_pixel) aggregation needs ~0.1 GB of HBM traffic per 20-Mpx view: the "
+                            "rasterizer is instruction-issue bound, not HBM bound (DESIGN.md section 5); the dense "
+                            "pixel_sum mode, which streams every score, is reported under 'pixel_sum'")
 
     # ---- end to end through the public API with host buffers ---------------------------------------------------
     e2e = None
@@ -348,6 +370,13 @@ def run_ours(args):
             "mpix_per_s": value * P / 1e6, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks, "stage_ms": stage_ms,
             "faces_per_view": f_v, "faces_observed": observed,
+            ("pixel_sum" if headline_mode == _lib.MODE_LAST_PIXEL else "last_pixel"): None if other is None else {
+                "value": other["value"], "unit": "views/s", "mpix_per_s": other["value"] * P / 1e6,
+                "ms_per_step": 1e3 * other["elapsed_s"] / args.steps, "roofline": other["roofline"],
+                "stage_ms": other["stage_ms"],
+                "note": "same workload with every pixel adding its scores (GG_MODE_PIXEL_SUM, not the reference's "
+                        "semantics): the fused rasterizer epilogue streams the (H,W,C) float32 scores from HBM"
+                        if headline_mode == _lib.MODE_LAST_PIXEL else "reference-parity mode"},
             "accumulators": "float64 sums + int32 counts; one NCCL all-reduce at the end" if world > 1 else
                             "float64 sums + int32 counts",
         }
