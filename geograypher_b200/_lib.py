@@ -247,7 +247,8 @@ class Context:
 
     def _grow_after_overflow(self, n):
         stats = self.last_batch_stats(n)
-        self.reserve(0, int(stats[:, 2].max() * 1.5) + 4096)
+        # counters keep counting past the capacity, so they tell how much is needed
+        self.reserve(int(stats[:, 1].max() * 1.5) + 4096, int(stats[:, 2].max() * 1.5) + 4096)
 
     # -- stage 3 -------------------------------------------------------------------------------------------
     def aggregate(self, pix2face, pred, pred_kind, C, mode, flags, d_sum, d_count, stream=None):

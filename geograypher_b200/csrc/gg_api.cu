@@ -183,9 +183,12 @@ int gg_last_batch_stats(gg_context *ctx, int n, int64_t *h_out) {
     if (rc != GG_OK) return rc;
     if (n > ctx->last_batch_n) n = ctx->last_batch_n;
     for (int i = 0; i < n; ++i) {
-        int32_t c[4];
+        int32_t c[8];
         GG_CUDA(cudaMemcpy(c, ctx->views.v[i].counters, sizeof(c), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < 4; ++k) h_out[4 * i + k] = c[k];
+        h_out[4 * i + 0] = c[0];
+        h_out[4 * i + 1] = c[6] > c[1] ? c[6] : c[1];  // face records wanted, even beyond the capacity
+        h_out[4 * i + 2] = c[2];
+        h_out[4 * i + 3] = c[3];
     }
     return GG_OK;
 }

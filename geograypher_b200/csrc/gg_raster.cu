@@ -347,7 +347,10 @@ __global__ void __launch_bounds__(256) k_reserve_tiles(int n_tiles, int64_t cap_
     const GGViewScratch &vs = views.v[blockIdx.y];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    if (t == 0 && vs.counters[1] > cap_recs) vs.counters[1] = (int)cap_recs;  // records beyond capacity were dropped
+    if (t == 0) {
+        vs.counters[6] = vs.counters[1];  // records wanted (reported by gg_last_batch_stats)
+        if (vs.counters[1] > cap_recs) vs.counters[1] = (int)cap_recs;  // records beyond capacity were dropped
+    }
     const int v = (t < n_tiles) ? vs.tile_count[t] : 0;
     int x = v;
 #pragma unroll
@@ -801,8 +804,11 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
     const int64_t tiles = (int64_t)((W + GG_TILE_W - 1) / GG_TILE_W) * ((H + GG_TILE_H - 1) / GG_TILE_H);
-    const int64_t cap_recs = ctx->req_recs > 0 ? ctx->req_recs : ctx->F;
-    const int64_t cap_bins = ctx->req_bins > 0 ? ctx->req_bins : (6 * tiles > (1 << 20) ? 6 * tiles : (1 << 20));
+    // defaults: a view rarely sees more than 1/8 of a large mesh, and a tile list is a few faces long; both are
+    // grown on demand (GG_ERR_OVERFLOW -> gg_reserve -> replay)
+    const int64_t auto_recs = ctx->F < (1 << 20) ? ctx->F : ((ctx->F / 8 > (1 << 20)) ? ctx->F / 8 : (1 << 20));
+    const int64_t cap_recs = ctx->req_recs > 0 ? ctx->req_recs : auto_recs;
+    const int64_t cap_bins = ctx->req_bins > 0 ? ctx->req_bins : (16 * tiles > (1 << 20) ? 16 * tiles : (1 << 20));
     if (n_views <= ctx->n_slots && tiles <= ctx->slot_tiles && cap_recs == ctx->cap_recs && cap_bins == ctx->cap_bins)
         return GG_OK;
     if (ctx->d_scratch) {
@@ -898,7 +904,7 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
     const int n_tiles = tiles_x * tiles_y;
     for (int i = 0; i < n; ++i) {
         GG_CUDA(cudaMemsetAsync(ctx->views.v[i].tile_count, 0, (size_t)n_tiles * 4, st));
-        GG_CUDA(cudaMemsetAsync(ctx->views.v[i].counters, 0, 16, st));
+        GG_CUDA(cudaMemsetAsync(ctx->views.v[i].counters, 0, 32, st));
         GG_CUDA(cudaMemsetAsync(ctx->views.v[i].counters + 4, 0xFF, 8, st));
     }
     ctx->last_batch_n = n;
