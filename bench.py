@@ -266,6 +266,7 @@ def run_ours(args):
         ctx.project_aggregate([gg_cams[k] for k in ids], ring, _lib.PRED_F32, C, mode, 0, d_sum, d_count, check=check)
 
     def epilogue():
+        ctx.drain()  # the accumulators are written on the library's internal streams
         if world > 1:
             dist.all_reduce(d_sum)
             dist.all_reduce(d_count)

@@ -28,7 +28,7 @@ EXPORTS = [
     "gg_abi_version", "gg_last_error", "gg_create", "gg_destroy", "gg_sync", "gg_reserve",
     "gg_last_batch_stats", "gg_set_mesh", "gg_project", "gg_rasterize", "gg_aggregate",
     "gg_project_aggregate", "gg_finalize", "gg_render_flat", "gg_stage_count", "gg_stage_name", "gg_profile",
-    "gg_profile_read",
+    "gg_profile_read", "gg_drain", "gg_set_pipeline",
 ]
 
 
@@ -92,6 +92,8 @@ def load():
     lib.gg_render_flat.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp]
     lib.gg_stage_name.argtypes = [i32]
     lib.gg_stage_name.restype = ctypes.c_char_p
+    lib.gg_drain.argtypes = [vp, vp]
+    lib.gg_set_pipeline.argtypes = [vp, i32]
     lib.gg_profile.argtypes = [vp, i32]
     lib.gg_profile_read.argtypes = [vp, vp, vp, i32]
     for name in EXPORTS:
@@ -180,6 +182,13 @@ class Context:
 
     def sync(self, stream=None):
         _check(self.lib.gg_sync(self.handle, _stream_ptr(stream)))
+
+    def drain(self, stream=None):
+        """Make `stream` wait (on the device) for the fused aggregation still in flight on the internal streams."""
+        _check(self.lib.gg_drain(self.handle, _stream_ptr(stream)))
+
+    def set_pipeline(self, enable: bool):
+        _check(self.lib.gg_set_pipeline(self.handle, 1 if enable else 0))
 
     def reserve(self, max_faces_per_view=0, max_bin_entries_per_view=0):
         _check(self.lib.gg_reserve(self.handle, int(max_faces_per_view), int(max_bin_entries_per_view)))

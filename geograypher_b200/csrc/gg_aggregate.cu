@@ -352,10 +352,10 @@ int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, i
     const dim3 g((unsigned)(ctx->sm_count * 2), n);
     const int64_t F = ctx->F;
     switch (pred_kind) {
-        case GG_PRED_F32: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_batch<float><<<g, 256, 0, st>>>(ctx->views, n, F, pb, C, pred_kind, mode, flags, d_sum, d_count)); break;
-        case GG_PRED_F64: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_batch<double><<<g, 256, 0, st>>>(ctx->views, n, F, pb, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_F32: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_batch<float><<<g, 256, 0, st>>>(ctx->vset[ctx->cur], n, F, pb, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_F64: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_batch<double><<<g, 256, 0, st>>>(ctx->vset[ctx->cur], n, F, pb, C, pred_kind, mode, flags, d_sum, d_count)); break;
         case GG_PRED_U8:
-        case GG_PRED_INDEX_U8: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_batch<uint8_t><<<g, 256, 0, st>>>(ctx->views, n, F, pb, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_INDEX_U8: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_resolve_batch<uint8_t><<<g, 256, 0, st>>>(ctx->vset[ctx->cur], n, F, pb, C, pred_kind, mode, flags, d_sum, d_count)); break;
         default: gg_set_error("gg_project_aggregate: bad pred_kind"); return GG_ERR_INVALID;
     }
     return GG_OK;

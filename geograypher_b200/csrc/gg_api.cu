@@ -83,7 +83,14 @@ int gg_create(int device, gg_context **out) {
     cudaDeviceProp prop;
     GG_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
-    memset(&ctx->views, 0, sizeof(ctx->views));
+    memset(ctx->vset, 0, sizeof(ctx->vset));
+    GG_CUDA(cudaStreamCreateWithFlags(&ctx->sA, cudaStreamNonBlocking));
+    GG_CUDA(cudaStreamCreateWithFlags(&ctx->sB, cudaStreamNonBlocking));
+    GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_user, cudaEventDisableTiming));
+    for (int s = 0; s < 2; ++s) {
+        GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_bin[s], cudaEventDisableTiming));
+        GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_ras[s], cudaEventDisableTiming));
+    }
     *out = ctx;
     return GG_OK;
 }
@@ -105,17 +112,27 @@ void gg_destroy(gg_context *ctx) {
         cudaEventDestroy(p.b);
     }
     for (auto e : ctx->prof.pool) cudaEventDestroy(e);
+    if (ctx->sA) cudaStreamDestroy(ctx->sA);
+    if (ctx->sB) cudaStreamDestroy(ctx->sB);
+    if (ctx->ev_user) cudaEventDestroy(ctx->ev_user);
+    for (int s = 0; s < 2; ++s) {
+        if (ctx->ev_bin[s]) cudaEventDestroy(ctx->ev_bin[s]);
+        if (ctx->ev_ras[s]) cudaEventDestroy(ctx->ev_ras[s]);
+    }
     delete ctx;
 }
 
 int gg_sync(gg_context *ctx, void *stream) {
     int rc = check_ctx(ctx, false);
     if (rc != GG_OK) return rc;
+    GG_CUDA(cudaStreamSynchronize(ctx->sA));
+    GG_CUDA(cudaStreamSynchronize(ctx->sB));
+    ctx->ras_pending[0] = ctx->ras_pending[1] = false;
     GG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     GG_CUDA(cudaGetLastError());
     for (int i = 0; i < ctx->last_batch_n; ++i) {
         int32_t c[4];
-        GG_CUDA(cudaMemcpy(c, ctx->views.v[i].counters, sizeof(c), cudaMemcpyDeviceToHost));
+        GG_CUDA(cudaMemcpy(c, ctx->vset[ctx->cur].v[i].counters, sizeof(c), cudaMemcpyDeviceToHost));
         if (c[3] != 0) {
             char buf[256];
             snprintf(buf, sizeof(buf),
@@ -166,6 +183,21 @@ int gg_profile_read(gg_context *ctx, double *h_ms, int64_t *h_launches, int rese
     return GG_OK;
 }
 
+int gg_drain(gg_context *ctx, void *stream) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    return gg_pipeline_drain(ctx, (cudaStream_t)stream);
+}
+
+int gg_set_pipeline(gg_context *ctx, int enable) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    GG_CUDA(cudaDeviceSynchronize());
+    ctx->ras_pending[0] = ctx->ras_pending[1] = false;
+    ctx->pipeline = enable != 0;
+    return GG_OK;
+}
+
 int gg_reserve(gg_context *ctx, int64_t max_faces_per_view, int64_t max_bin_entries_per_view) {
     int rc = check_ctx(ctx, false);
     if (rc != GG_OK) return rc;
@@ -184,7 +216,7 @@ int gg_last_batch_stats(gg_context *ctx, int n, int64_t *h_out) {
     if (n > ctx->last_batch_n) n = ctx->last_batch_n;
     for (int i = 0; i < n; ++i) {
         int32_t c[8];
-        GG_CUDA(cudaMemcpy(c, ctx->views.v[i].counters, sizeof(c), cudaMemcpyDeviceToHost));
+        GG_CUDA(cudaMemcpy(c, ctx->vset[ctx->cur].v[i].counters, sizeof(c), cudaMemcpyDeviceToHost));
         h_out[4 * i + 0] = c[0];
         h_out[4 * i + 1] = c[6] > c[1] ? c[6] : c[1];  // face records wanted, even beyond the capacity
         h_out[4 * i + 2] = c[2];
@@ -252,6 +284,8 @@ int gg_project(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_X, in
         gg_set_error("gg_project: bad arguments");
         return GG_ERR_INVALID;
     }
+    rc = gg_pipeline_drain(ctx, (cudaStream_t)stream);
+    if (rc != GG_OK) return rc;
     return gg_launch_project(ctx, h_cams, n, d_X, d_Y, d_invz, d_valid, (cudaStream_t)stream);
 }
 
@@ -264,7 +298,9 @@ int gg_rasterize(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_pix
         gg_set_error("gg_rasterize: d_pix2face is null");
         return GG_ERR_INVALID;
     }
-    return gg_launch_rasterize(ctx, h_cams, n, d_pix2face, d_depth, 0, 0, (cudaStream_t)stream);
+    rc = gg_pipeline_drain(ctx, (cudaStream_t)stream);
+    if (rc != GG_OK) return rc;
+    return gg_launch_rasterize(ctx, h_cams, n, d_pix2face, d_depth, 0, 0, (cudaStream_t)stream, (cudaStream_t)stream);
 }
 
 int gg_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred, int pred_kind, int C,
@@ -275,6 +311,8 @@ int gg_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const
         gg_set_error("gg_aggregate: bad arguments");
         return GG_ERR_INVALID;
     }
+    rc = gg_pipeline_drain(ctx, (cudaStream_t)stream);
+    if (rc != GG_OK) return rc;
     return gg_launch_aggregate(ctx, d_pix2face, H, W, d_pred, pred_kind, C, mode, flags, d_sum, d_count,
                                (cudaStream_t)stream);
 }
@@ -297,18 +335,43 @@ int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const 
         gg_set_error("gg_project_aggregate: raster larger than 2^31 pixels");
         return GG_ERR_INVALID;
     }
-    if (mode == GG_MODE_LAST_PIXEL || mode == GG_MODE_VOTE) {
-        // Fused: the rasterizer leaves every face record's last pixel in scratch; the rasters never touch HBM
-        // unless the caller asked for them.  Views are resolved one after the other so that every face's float64
-        // sum is accumulated in view order (bit-identical to the reference's loop, meshes.py:2056-2062).
-        rc = gg_launch_rasterize(ctx, h_cams, n, d_pix2face, nullptr, 1, flags & GG_FLAG_COMPAT_NEG, st);
+    const bool fused = (mode == GG_MODE_LAST_PIXEL || mode == GG_MODE_VOTE) || (mode == GG_MODE_PIXEL_SUM && C <= 32);
+    if (fused) {
+        // Fused: the rasters never touch HBM unless the caller asked for them.  Last-pixel / vote: the rasterizer
+        // leaves every face's last pixel in scratch and k_resolve_batch applies the views in order (bit-identical
+        // to the reference's loop, meshes.py:2056-2062).  Pixel-sum: the rasterizer's dense epilogue streams the
+        // scores.  Software pipeline: this batch is binned on stream A while the previous batch is still being
+        // rasterized on stream B; the two alternate between two sets of scratch slots.  The accumulators are
+        // complete once gg_finalize / gg_sync (or any other entry point) has been called on the caller's stream.
+        cudaStream_t sb = st, sr = st;
+        if (ctx->pipeline) {
+            sb = ctx->sA;
+            sr = ctx->sB;
+            ctx->cur = ctx->parity;
+            ctx->parity ^= 1;
+            GG_CUDA(cudaEventRecord(ctx->ev_user, st));
+            GG_CUDA(cudaStreamWaitEvent(sb, ctx->ev_user, 0));  // after whatever the caller enqueued before
+            GG_CUDA(cudaStreamWaitEvent(sr, ctx->ev_user, 0));
+            if (ctx->ras_pending[ctx->cur]) GG_CUDA(cudaStreamWaitEvent(sb, ctx->ev_ras[ctx->cur], 0));  // slot set free?
+        } else {
+            rc = gg_pipeline_drain(ctx, st);
+            if (rc != GG_OK) return rc;
+        }
+        if (mode == GG_MODE_PIXEL_SUM) {
+            rc = gg_launch_rasterize(ctx, h_cams, n, d_pix2face, nullptr, 0, 0, sb, sr, h_pred, pred_kind, C, d_sum, d_count);
+        } else {
+            rc = gg_launch_rasterize(ctx, h_cams, n, d_pix2face, nullptr, 1, flags & GG_FLAG_COMPAT_NEG, sb, sr);
+            if (rc == GG_OK) rc = gg_launch_resolve_batch(ctx, n, h_pred, pred_kind, C, mode, flags, d_sum, d_count, sr);
+        }
         if (rc != GG_OK) return rc;
-        return gg_launch_resolve_batch(ctx, n, h_pred, pred_kind, C, mode, flags, d_sum, d_count, st);
+        if (ctx->pipeline) {
+            GG_CUDA(cudaEventRecord(ctx->ev_ras[ctx->cur], sr));
+            ctx->ras_pending[ctx->cur] = true;
+        }
+        return GG_OK;
     }
-    if (mode == GG_MODE_PIXEL_SUM && C <= 32) {
-        // Fused dense mode: the rasterizer's epilogue streams the score images and adds every pixel to its face.
-        return gg_launch_rasterize(ctx, h_cams, n, d_pix2face, nullptr, 0, 0, st, h_pred, pred_kind, C, d_sum, d_count);
-    }
+    rc = gg_pipeline_drain(ctx, st);
+    if (rc != GG_OK) return rc;
     int32_t *raster = d_pix2face;
     if (!raster) {
         const int64_t need = P * n;
@@ -323,7 +386,7 @@ int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const 
         }
         raster = ctx->d_raster;
     }
-    rc = gg_launch_rasterize(ctx, h_cams, n, raster, nullptr, 0, 0, st);
+    rc = gg_launch_rasterize(ctx, h_cams, n, raster, nullptr, 0, 0, st, st);
     if (rc != GG_OK) return rc;
     for (int i = 0; i < n; ++i) {
         rc = gg_launch_aggregate(ctx, raster + P * i, H, W, h_pred[i], pred_kind, C, mode, flags, d_sum, d_count, st);
@@ -340,6 +403,8 @@ int gg_finalize(gg_context *ctx, double *d_sum, const int32_t *d_count, int64_t 
         gg_set_error("gg_finalize: bad arguments");
         return GG_ERR_INVALID;
     }
+    rc = gg_pipeline_drain(ctx, (cudaStream_t)stream);
+    if (rc != GG_OK) return rc;
     return gg_launch_finalize(ctx, d_sum, d_count, F, C, d_avg, d_argmax, (cudaStream_t)stream);
 }
 
@@ -351,6 +416,8 @@ int gg_render_flat(gg_context *ctx, const int32_t *d_pix2face, int64_t n_pixels,
         gg_set_error("gg_render_flat: bad arguments");
         return GG_ERR_INVALID;
     }
+    rc = gg_pipeline_drain(ctx, (cudaStream_t)stream);
+    if (rc != GG_OK) return rc;
     return gg_launch_render_flat(ctx, d_pix2face, n_pixels, d_face_tex, D, d_out, out_dtype, (cudaStream_t)stream);
 }
 

@@ -117,7 +117,14 @@ struct gg_context {
     int64_t slot_tiles = 0;
     char *d_scratch = nullptr;
     size_t scratch_bytes = 0;
-    GGViewBatch views;
+    GGViewBatch vset[2];          // two sets of batch slots: batch k+1 is binned while batch k is rasterized
+    int cur = 0;                  // set used by the work being enqueued / most recently enqueued
+    // software pipeline of the fused aggregation (gg_project_aggregate): binning on sA, raster + resolve on sB
+    cudaStream_t sA = nullptr, sB = nullptr;
+    cudaEvent_t ev_user = nullptr, ev_bin[2] = {nullptr, nullptr}, ev_ras[2] = {nullptr, nullptr};
+    bool ras_pending[2] = {false, false};
+    int parity = 0;
+    bool pipeline = true;
     int32_t *d_winner = nullptr;  // [F] last-pixel winner per face (dense, unfused aggregation)
     int64_t winner_cap = 0;
     int32_t *d_wdense = nullptr;  // [n_slots * F] per-view per-face winners of the fused aggregation
@@ -158,13 +165,18 @@ int gg_cuda_fail(cudaError_t e, const char *what);
 
 // gg_raster.cu
 int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H);
+// make `st` wait for everything the internal pipeline streams still have in flight
+int gg_pipeline_drain(gg_context *ctx, cudaStream_t st);
 int gg_launch_mesh_blocks(gg_context *ctx, cudaStream_t st);
 int gg_launch_project(gg_context *ctx, const gg_camera *cams, int n, int32_t *dX, int32_t *dY, float *dinvz,
                       uint8_t *dvalid, cudaStream_t st);
 // h_pred != nullptr selects the fused dense per-pixel-sum epilogue (GG_MODE_PIXEL_SUM, C <= 32)
+// st_bin == st_ras: everything on one stream (set 0).  Otherwise binning goes to st_bin, the rasterizer to st_ras,
+// linked by ev_bin[ctx->cur].
 int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *d_pix2face, float *d_depth,
-                        int want_winners, int compat_bg, cudaStream_t st, const void *const *h_pred = nullptr,
-                        int pred_kind = 0, int C = 0, double *d_sum = nullptr, int32_t *d_count = nullptr);
+                        int want_winners, int compat_bg, cudaStream_t st_bin, cudaStream_t st_ras,
+                        const void *const *h_pred = nullptr, int pred_kind = 0, int C = 0, double *d_sum = nullptr,
+                        int32_t *d_count = nullptr);
 // gg_aggregate.cu: consume the per-face winners of the last rasterization batch (all views, in view order)
 int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, int pred_kind, int C, int mode, int flags,
                             double *d_sum, int32_t *d_count, cudaStream_t st);

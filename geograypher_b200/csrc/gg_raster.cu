@@ -171,6 +171,13 @@ __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ vert
     }
 }
 
+// One launch resets the per-view counters and tile counts of a whole batch.
+__global__ void __launch_bounds__(256) k_reset_views(int n_tiles, const __grid_constant__ GGViewBatch views) {
+    const GGViewScratch &vs = views.v[blockIdx.y];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) vs.tile_count[t] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < 8) vs.counters[threadIdx.x] = (threadIdx.x == 4 || threadIdx.x == 5) ? -1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Per-view frustum culling of face blocks (conservative; never changes the result).
 // ------------------------------------------------------------------------------------------------------
@@ -816,7 +823,7 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
         GG_CUDA(cudaFree(ctx->d_scratch));
         ctx->d_scratch = nullptr;
     }
-    const int slots = n_views > ctx->n_slots ? n_views : ctx->n_slots;
+    const int slots = n_views > ctx->n_slots ? n_views : ctx->n_slots;  // per set; two sets are allocated
     const int64_t slot_tiles = tiles > ctx->slot_tiles ? tiles : ctx->slot_tiles;
     const size_t b_vis = align_up((size_t)ctx->n_blocks * 4, 256);
     const size_t b_rec = align_up((size_t)cap_recs * sizeof(GGFaceRec), 256);
@@ -825,11 +832,11 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
     const size_t b_bin = align_up((size_t)cap_bins * sizeof(GGTileFace), 256);
     const size_t b_ctr = 256;
     const size_t per_slot = b_vis + b_rec + b_cnt + b_off + b_bin + b_ctr;
-    GG_CUDA(cudaMalloc(&ctx->d_scratch, per_slot * slots));
-    ctx->scratch_bytes = per_slot * slots;
-    for (int s = 0; s < slots; ++s) {
+    GG_CUDA(cudaMalloc(&ctx->d_scratch, per_slot * slots * 2));
+    ctx->scratch_bytes = per_slot * slots * 2;
+    for (int s = 0; s < 2 * slots; ++s) {
         char *p = ctx->d_scratch + per_slot * s;
-        GGViewScratch &v = ctx->views.v[s];
+        GGViewScratch &v = ctx->vset[s / slots].v[s % slots];
         v.vis_blocks = (int32_t *)p;
         p += b_vis;
         v.recs = (GGFaceRec *)p;
@@ -873,7 +880,7 @@ static int launch_dense(gg_context *ctx, const GGCamBatch &cb, dim3 rgrid, int n
 #define GG_DENSE_CASE(CT)                                                                                             \
     case CT:                                                                                                          \
         GG_LAUNCH(ctx, GG_ST_RASTER, st,                                                                              \
-                  (k_raster_tiles<GG_RM_DENSE, T, CT><<<rgrid, GG_RASTER_THREADS, dyn, st>>>(cb, ctx->views, n_tiles,   \
+                  (k_raster_tiles<GG_RM_DENSE, T, CT><<<rgrid, GG_RASTER_THREADS, dyn, st>>>(cb, ctx->vset[ctx->cur], n_tiles,   \
                                                                                             d_pix2face, nullptr, 0, da))); \
         break;
     switch (da.index_kind ? 0 : da.C) {  // compile-time channel counts for the common cases, generic otherwise
@@ -885,28 +892,35 @@ static int launch_dense(gg_context *ctx, const GGCamBatch &cb, dim3 rgrid, int n
         GG_DENSE_CASE(16)
         default:
             GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                      (k_raster_tiles<GG_RM_DENSE, T, 0><<<rgrid, GG_RASTER_THREADS, dyn, st>>>(cb, ctx->views, n_tiles,
+                      (k_raster_tiles<GG_RM_DENSE, T, 0><<<rgrid, GG_RASTER_THREADS, dyn, st>>>(cb, ctx->vset[ctx->cur], n_tiles,
                                                                                                d_pix2face, nullptr, 0, da)));
     }
 #undef GG_DENSE_CASE
     return GG_OK;
 }
 
+int gg_pipeline_drain(gg_context *ctx, cudaStream_t st) {
+    for (int s = 0; s < 2; ++s) {
+        if (ctx->ras_pending[s]) {
+            GG_CUDA(cudaStreamWaitEvent(st, ctx->ev_ras[s], 0));
+            ctx->ras_pending[s] = false;
+        }
+    }
+    return GG_OK;
+}
+
 int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *d_pix2face, float *d_depth,
-                        int want_winners, int compat_bg, cudaStream_t st, const void *const *h_pred, int pred_kind,
-                        int C, double *d_sum, int32_t *d_count) {
+                        int want_winners, int compat_bg, cudaStream_t st_bin, cudaStream_t st_ras,
+                        const void *const *h_pred, int pred_kind, int C, double *d_sum, int32_t *d_count) {
     const int W = cams[0].W, H = cams[0].H;
     int rc = gg_ensure_scratch(ctx, n, W, H);
     if (rc != GG_OK) return rc;
+    const bool piped = st_bin != st_ras;
+    if (!piped) ctx->cur = 0;
     GGCamBatch cb;
     for (int i = 0; i < n; ++i) cb.cam[i] = cams[i];
     const int tiles_x = (W + GG_TILE_W - 1) / GG_TILE_W, tiles_y = (H + GG_TILE_H - 1) / GG_TILE_H;
     const int n_tiles = tiles_x * tiles_y;
-    for (int i = 0; i < n; ++i) {
-        GG_CUDA(cudaMemsetAsync(ctx->views.v[i].tile_count, 0, (size_t)n_tiles * 4, st));
-        GG_CUDA(cudaMemsetAsync(ctx->views.v[i].counters, 0, 32, st));
-        GG_CUDA(cudaMemsetAsync(ctx->views.v[i].counters + 4, 0xFF, 8, st));
-    }
     ctx->last_batch_n = n;
     if (want_winners) {
         if (ctx->wdense_cap < (int64_t)n * ctx->F) {
@@ -915,22 +929,32 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
                 GG_CUDA(cudaFree(ctx->d_wdense));
                 ctx->d_wdense = nullptr;
             }
-            GG_CUDA(cudaMalloc(&ctx->d_wdense, (size_t)n * ctx->F * 4));
+            GG_CUDA(cudaMalloc(&ctx->d_wdense, (size_t)2 * n * ctx->F * 4));
             ctx->wdense_cap = (int64_t)n * ctx->F;
         }
-        for (int i = 0; i < n; ++i) ctx->views.v[i].winner = ctx->d_wdense + (int64_t)i * ctx->F;
-        GG_CUDA(cudaMemsetAsync(ctx->d_wdense, 0xFF, (size_t)n * ctx->F * 4, st));
+        for (int i = 0; i < n; ++i)
+            ctx->vset[ctx->cur].v[i].winner = ctx->d_wdense + ((int64_t)ctx->cur * (ctx->wdense_cap / ctx->F) + i) * ctx->F;
     }
+    cudaStream_t st = st_bin;
+    GG_LAUNCH(ctx, GG_ST_MISC, st,
+              k_reset_views<<<dim3((n_tiles + 1023) / 1024, n), 256, 0, st>>>(n_tiles, ctx->vset[ctx->cur]));
     const int nb = (int)ctx->n_blocks;
     GG_LAUNCH(ctx, GG_ST_CULL, st,
-              k_cull_blocks<<<dim3((nb + 255) / 256, n), 256, 0, st>>>(ctx->d_block_lo, ctx->d_block_hi, nb, cb, ctx->views));
+              k_cull_blocks<<<dim3((nb + 255) / 256, n), 256, 0, st>>>(ctx->d_block_lo, ctx->d_block_hi, nb, cb, ctx->vset[ctx->cur]));
     const int gsetup = nb < ctx->sm_count * 8 ? nb : ctx->sm_count * 8;
     GG_LAUNCH(ctx, GG_ST_SETUP, st,
               k_setup_faces<<<dim3(gsetup, n), GG_BLOCK_FACES, 0, st>>>(ctx->d_verts, ctx->d_faces, ctx->F, ctx->cap_recs,
-                                                                        cb, ctx->views));
+                                                                        cb, ctx->vset[ctx->cur]));
     GG_LAUNCH(ctx, GG_ST_SCAN, st,
-              k_reserve_tiles<<<dim3((n_tiles + 255) / 256, n), 256, 0, st>>>(n_tiles, ctx->cap_recs, ctx->views));
-    GG_LAUNCH(ctx, GG_ST_FILL, st, k_fill_bins<<<dim3(ctx->sm_count * 4, n), 256, 0, st>>>(ctx->cap_bins, cb, ctx->views));
+              k_reserve_tiles<<<dim3((n_tiles + 255) / 256, n), 256, 0, st>>>(n_tiles, ctx->cap_recs, ctx->vset[ctx->cur]));
+    GG_LAUNCH(ctx, GG_ST_FILL, st, k_fill_bins<<<dim3(ctx->sm_count * 4, n), 256, 0, st>>>(ctx->cap_bins, cb, ctx->vset[ctx->cur]));
+    if (piped) {
+        GG_CUDA(cudaEventRecord(ctx->ev_bin[ctx->cur], st_bin));
+        GG_CUDA(cudaStreamWaitEvent(st_ras, ctx->ev_bin[ctx->cur], 0));
+    }
+    st = st_ras;
+    if (want_winners)
+        GG_CUDA(cudaMemsetAsync(ctx->vset[ctx->cur].v[0].winner, 0xFF, (size_t)n * ctx->F * 4, st));
     const dim3 rgrid((n_tiles + GG_RASTER_WARPS - 1) / GG_RASTER_WARPS, n);
     GGDenseArgs da;
     memset(&da, 0, sizeof(da));
@@ -951,10 +975,10 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
     if (want_winners)
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
                   (k_raster_tiles<GG_RM_WINNERS, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
-                      cb, ctx->views, n_tiles, d_pix2face, d_depth, compat_bg ? (int)ctx->F : 0, da)));
+                      cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, d_depth, compat_bg ? (int)ctx->F : 0, da)));
     else
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  (k_raster_tiles<GG_RM_PLAIN, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->views, n_tiles,
+                  (k_raster_tiles<GG_RM_PLAIN, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->vset[ctx->cur], n_tiles,
                                                                                           d_pix2face, d_depth, 0, da)));
     return GG_OK;
 }

@@ -77,6 +77,7 @@ def aggregate_projected_images_distributed(mesh, cameras, aggregate_img_scale: f
         dev = torch.device("cuda", mesh.device)
         d_sum = torch.zeros((mesh.faces.shape[0], C), dtype=torch.float64, device=dev)
         d_count = torch.zeros((mesh.faces.shape[0],), dtype=torch.int32, device=dev)
+    mesh._get_context().drain()  # accumulators are written on the library's internal streams
     allreduce_accumulators(d_sum, d_count, group)
     avg, argmax = mesh._get_context().finalize(d_sum, d_count, want_avg=True, want_argmax=return_argmax)
     info = {"projection_counts": d_count.cpu().numpy().astype(float), "summed_projections": d_sum.cpu().numpy()}

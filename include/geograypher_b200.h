@@ -85,6 +85,12 @@ int gg_create(int device, gg_context **out);
 void gg_destroy(gg_context *ctx);
 /* Synchronise `stream` and report a deferred failure of the work enqueued so far (GG_ERR_OVERFLOW, CUDA). */
 int gg_sync(gg_context *ctx, void *stream);
+/* gg_project_aggregate runs its fused modes as a two-stage software pipeline on two internal streams (binning of
+   batch k+1 overlaps the rasterization of batch k).  The accumulators it writes are complete, with respect to
+   `stream`, after gg_drain (no host synchronisation), gg_finalize or gg_sync; every other entry point drains
+   implicitly.  gg_set_pipeline(ctx, 0) turns the overlap off (everything is then enqueued on the caller's stream). */
+int gg_drain(gg_context *ctx, void *stream);
+int gg_set_pipeline(gg_context *ctx, int enable);
 /* Scratch sizing: max face records per view (0 = number of faces) and max (tile, face) pairs per view. */
 int gg_reserve(gg_context *ctx, int64_t max_faces_per_view, int64_t max_bin_entries_per_view);
 /* Counters of the most recent rasterization batch, valid after gg_sync: per view [n_visible_blocks,
