@@ -84,8 +84,12 @@ int gg_create(int device, gg_context **out) {
     GG_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     memset(ctx->vset, 0, sizeof(ctx->vset));
-    GG_CUDA(cudaStreamCreateWithFlags(&ctx->sA, cudaStreamNonBlocking));
-    GG_CUDA(cudaStreamCreateWithFlags(&ctx->sB, cudaStreamNonBlocking));
+    // the short, latency-bound binning kernels get the higher priority so that they slip in between the CTAs of the
+    // rasterizer that is still running for the previous batch
+    int prio_lo = 0, prio_hi = 0;
+    GG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    GG_CUDA(cudaStreamCreateWithPriority(&ctx->sA, cudaStreamNonBlocking, prio_hi));
+    GG_CUDA(cudaStreamCreateWithPriority(&ctx->sB, cudaStreamNonBlocking, prio_lo));
     GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_user, cudaEventDisableTiming));
     for (int s = 0; s < 2; ++s) {
         GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_bin[s], cudaEventDisableTiming));
