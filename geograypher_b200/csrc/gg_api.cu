@@ -90,10 +90,12 @@ int gg_create(int device, gg_context **out) {
     GG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     GG_CUDA(cudaStreamCreateWithPriority(&ctx->sA, cudaStreamNonBlocking, prio_hi));
     GG_CUDA(cudaStreamCreateWithPriority(&ctx->sB, cudaStreamNonBlocking, prio_lo));
+    GG_CUDA(cudaStreamCreateWithPriority(&ctx->sC, cudaStreamNonBlocking, prio_hi));
     GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_user, cudaEventDisableTiming));
     for (int s = 0; s < 2; ++s) {
         GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_bin[s], cudaEventDisableTiming));
         GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_ras[s], cudaEventDisableTiming));
+        GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_mid[s], cudaEventDisableTiming));
     }
     *out = ctx;
     return GG_OK;
@@ -118,10 +120,12 @@ void gg_destroy(gg_context *ctx) {
     for (auto e : ctx->prof.pool) cudaEventDestroy(e);
     if (ctx->sA) cudaStreamDestroy(ctx->sA);
     if (ctx->sB) cudaStreamDestroy(ctx->sB);
+    if (ctx->sC) cudaStreamDestroy(ctx->sC);
     if (ctx->ev_user) cudaEventDestroy(ctx->ev_user);
     for (int s = 0; s < 2; ++s) {
         if (ctx->ev_bin[s]) cudaEventDestroy(ctx->ev_bin[s]);
         if (ctx->ev_ras[s]) cudaEventDestroy(ctx->ev_ras[s]);
+        if (ctx->ev_mid[s]) cudaEventDestroy(ctx->ev_mid[s]);
     }
     delete ctx;
 }
@@ -131,6 +135,7 @@ int gg_sync(gg_context *ctx, void *stream) {
     if (rc != GG_OK) return rc;
     GG_CUDA(cudaStreamSynchronize(ctx->sA));
     GG_CUDA(cudaStreamSynchronize(ctx->sB));
+    GG_CUDA(cudaStreamSynchronize(ctx->sC));
     ctx->ras_pending[0] = ctx->ras_pending[1] = false;
     GG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     GG_CUDA(cudaGetLastError());
@@ -365,7 +370,13 @@ int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const 
             rc = gg_launch_rasterize(ctx, h_cams, n, d_pix2face, nullptr, 0, 0, sb, sr, h_pred, pred_kind, C, d_sum, d_count);
         } else {
             rc = gg_launch_rasterize(ctx, h_cams, n, d_pix2face, nullptr, 1, flags & GG_FLAG_COMPAT_NEG, sb, sr);
-            if (rc == GG_OK) rc = gg_launch_resolve_batch(ctx, n, h_pred, pred_kind, C, mode, flags, d_sum, d_count, sr);
+            if (rc != GG_OK) return rc;
+            if (ctx->pipeline) {  // the (latency-bound) resolve gets its own stream: the next rasterizer need not wait
+                GG_CUDA(cudaEventRecord(ctx->ev_mid[ctx->cur], sr));
+                sr = ctx->sC;
+                GG_CUDA(cudaStreamWaitEvent(sr, ctx->ev_mid[ctx->cur], 0));
+            }
+            rc = gg_launch_resolve_batch(ctx, n, h_pred, pred_kind, C, mode, flags, d_sum, d_count, sr);
         }
         if (rc != GG_OK) return rc;
         if (ctx->pipeline) {

@@ -120,7 +120,8 @@ struct gg_context {
     GGViewBatch vset[2];          // two sets of batch slots: batch k+1 is binned while batch k is rasterized
     int cur = 0;                  // set used by the work being enqueued / most recently enqueued
     // software pipeline of the fused aggregation (gg_project_aggregate): binning on sA, raster + resolve on sB
-    cudaStream_t sA = nullptr, sB = nullptr;
+    cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr;  // binning / rasterizer / resolve
+    cudaEvent_t ev_mid[2] = {nullptr, nullptr};             // rasterizer of a set done (resolve may start)
     cudaEvent_t ev_user = nullptr, ev_bin[2] = {nullptr, nullptr}, ev_ras[2] = {nullptr, nullptr};
     bool ras_pending[2] = {false, false};
     int parity = 0;
