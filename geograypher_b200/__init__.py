@@ -1,6 +1,7 @@
 """geograypher_b200: B200-native multiview projection (pix2face / aggregate / render_flat) behind
 open-forest-observatory/geograypher's TexturedPhotogrammetryMesh and PhotogrammetryCamera(Set) API."""
 from geograypher_b200.cameras import (
+    MetashapeCameraSet,
     PhotogrammetryCamera,
     PhotogrammetryCameraSet,
     SegmentorPhotogrammetryCameraSet,

@@ -28,7 +28,7 @@ EXPORTS = [
     "gg_abi_version", "gg_last_error", "gg_create", "gg_destroy", "gg_sync", "gg_reserve",
     "gg_last_batch_stats", "gg_set_mesh", "gg_project", "gg_rasterize", "gg_aggregate",
     "gg_project_aggregate", "gg_finalize", "gg_render_flat", "gg_stage_count", "gg_stage_name", "gg_profile",
-    "gg_profile_read", "gg_drain", "gg_set_pipeline",
+    "gg_profile_read", "gg_drain", "gg_set_pipeline", "gg_build_warp_map", "gg_gather_i32",
 ]
 
 
@@ -44,6 +44,14 @@ class GGCamera(ctypes.Structure):
         ("H", ctypes.c_int32),
         ("znear", ctypes.c_float),
     ]
+
+
+class GGDistortion(ctypes.Structure):
+    """gg_distortion of the header."""
+
+    _fields_ = [("f", ctypes.c_double), ("cx", ctypes.c_double), ("cy", ctypes.c_double), ("W", ctypes.c_int32),
+                ("H", ctypes.c_int32)] + [(k, ctypes.c_double) for k in ("k1", "k2", "k3", "k4", "p1", "p2", "b1", "b2")] + [
+                    ("image_scale", ctypes.c_double)]
 
 
 class GeograypherB200Error(RuntimeError):
@@ -94,6 +102,8 @@ def load():
     lib.gg_stage_name.restype = ctypes.c_char_p
     lib.gg_drain.argtypes = [vp, vp]
     lib.gg_set_pipeline.argtypes = [vp, i32]
+    lib.gg_build_warp_map.argtypes = [i32, ctypes.POINTER(GGDistortion), i32, i32, i32, vp, vp, vp]
+    lib.gg_gather_i32.argtypes = [i32, vp, vp, i64, ctypes.c_int32, vp, vp]
     lib.gg_profile.argtypes = [vp, i32]
     lib.gg_profile_read.argtypes = [vp, vp, vp, i32]
     for name in EXPORTS:
@@ -133,6 +143,38 @@ def make_camera(world_to_cam, f, cx, cy, image_width, image_height, render_img_s
     cam.H = h
     cam.znear = np.float32(znear)
     return cam
+
+
+def make_distortion(f, cx, cy, image_width, image_height, image_scale=1.0, k1=0.0, k2=0.0, k3=0.0, k4=0.0, p1=0.0,
+                    p2=0.0, b1=0.0, b2=0.0) -> GGDistortion:
+    return GGDistortion(f=f, cx=cx, cy=cy, W=int(image_width), H=int(image_height), k1=k1, k2=k2, k3=k3, k4=k4, p1=p1,
+                        p2=p2, b1=b1, b2=b2, image_scale=image_scale)
+
+
+def build_warp_map(dist: GGDistortion, h: int, w: int, warped_to_ideal: bool, device: int = 0, want_coords=False):
+    """(h, w) int32 CUDA tensor of nearest source indices (-1 = outside); optionally also the (h, w, 2) float32
+    continuous (row, col) source coordinates."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise GeograypherB200Error(-5, "no CUDA device: geograypher_b200 has no CPU fallback")
+    dev = torch.device("cuda", device)
+    src = torch.empty((h, w), dtype=torch.int32, device=dev)
+    rc = torch.empty((h, w, 2), dtype=torch.float32, device=dev) if want_coords else None
+    _check(load().gg_build_warp_map(device, ctypes.byref(dist), h, w, 1 if warped_to_ideal else 0, src.data_ptr(),
+                                    rc.data_ptr() if rc is not None else None, _stream_ptr(None)))
+    return (src, rc) if want_coords else src
+
+
+def gather_i32(d_in, d_src_index, fill: int):
+    """Nearest-neighbour warp of an int32 raster through a source-index map (both CUDA tensors)."""
+    import torch
+
+    assert d_in.dtype == torch.int32 and d_src_index.dtype == torch.int32 and d_in.is_cuda
+    out = torch.empty(d_src_index.shape, dtype=torch.int32, device=d_in.device)
+    _check(load().gg_gather_i32(d_in.device.index or 0, d_in.contiguous().data_ptr(), d_src_index.data_ptr(),
+                                d_src_index.numel(), int(fill), out.data_ptr(), _stream_ptr(None)))
+    return out
 
 
 def _stream_ptr(stream):

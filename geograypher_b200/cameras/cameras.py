@@ -260,6 +260,11 @@ class PhotogrammetryCameraSet:
         return self._local_to_epsg_4978_transform
 
     # ---- lens distortion hooks (reference cameras.py:968-1156) ------------------------------------------
+    def distortion_key(self, parameters: Dict[str, float], image_scale: float = 1.0) -> str:
+        """Repeatable cache key of a distortion-parameter dict, 8 decimals (reference cameras.py:968-993)."""
+        keys = sorted(parameters.keys())
+        return "|".join([f"{k}:{parameters[k]:.8f}" for k in keys] + [f"image_scale:{image_scale:.8f}"])
+
     def ideal_to_warped(self, camera, xpix, ypix):
         """Only calibrated (Metashape) camera sets define a distortion model (reference cameras.py:1088-1090)."""
         raise NotImplementedError("Distortion is only defined for camera sets with a lens model")

@@ -398,20 +398,30 @@ class TexturedPhotogrammetryMesh:
 
         single = isinstance(cameras, PhotogrammetryCamera) or not hasattr(cameras, "cameras")
         p2f = self.pix2face_device(cameras, mesh=mesh, render_img_scale=render_img_scale)
-        p2f = p2f.to(dtype=__import__("torch").int64).cpu().numpy()
         if apply_distortion:
-            cam_list = self._camera_list(cameras)
-            p2f = np.stack(
-                [
-                    distortion_set.warp_dewarp_image(
-                        camera=cam, input_image=p2f[i], warped_to_ideal=False, fill_value=-1,
-                        interpolation_order=0, image_scale=render_img_scale,
-                    )
-                    for i, cam in enumerate(cam_list)
-                ],
-                axis=0,
-            )
+            p2f = self._warp_device(p2f, self._camera_list(cameras), distortion_set, render_img_scale)
+        p2f = p2f.to(dtype=__import__("torch").int64).cpu().numpy()
         return p2f[0] if single else p2f
+
+    @staticmethod
+    def _warp_device(p2f, cam_list, distortion_set, scale):
+        """Warp (n, h, w) int32 device rasters into the distorted image geometry (reference meshes.py:1842-1854:
+        warp_dewarp_image(warped_to_ideal=False, fill_value=-1, interpolation_order=0)).  Camera sets with a GPU lens
+        model (MetashapeCameraSet.warp_dewarp_device) never leave the device; any other set goes through its own
+        warp_dewarp_image on the host, which raises NotImplementedError when there is no lens model
+        (reference cameras.py:1088-1090)."""
+        import torch
+
+        if hasattr(distortion_set, "warp_dewarp_device"):
+            return torch.stack([
+                distortion_set.warp_dewarp_device(cam, p2f[i], warped_to_ideal=False, fill_value=-1, image_scale=scale)
+                for i, cam in enumerate(cam_list)])
+        host = p2f.to(torch.int64).cpu().numpy()
+        out = np.stack([
+            distortion_set.warp_dewarp_image(camera=cam, input_image=host[i], warped_to_ideal=False, fill_value=-1,
+                                             interpolation_order=0, image_scale=scale)
+            for i, cam in enumerate(cam_list)], axis=0)
+        return torch.from_numpy(out.astype(np.int32)).to(p2f.device)
 
     # ------------------------------------------------------------------------------------------------
     # render_flat
@@ -456,16 +466,15 @@ class TexturedPhotogrammetryMesh:
                     yield (img, cam_list[k]) if return_camera else img
                     k += 1
             return
-        # distortion requested: warp the rasters on the host side of the boundary, then gather
+        # distortion requested: rasterize, warp the face-ID raster into the distorted geometry, then gather
         import torch
 
         mesh = self.get_mesh_in_cameras_coords(cameras)
         face_texture = self.get_texture(request_vertex_texture=False, try_verts_faces_conversion=True)
         tex = torch.from_numpy(np.ascontiguousarray(face_texture, dtype=np.float64)).to(torch.device("cuda", self.device))
         for k, cam in enumerate(cam_list):
-            p2f = self.pix2face(cam, mesh=mesh, render_img_scale=render_img_scale, **pix2face_kwargs)
-            d_p2f = torch.from_numpy(p2f.astype(np.int32)).to(tex.device)
-            img = mesh.context.render_flat(d_p2f, tex).cpu().numpy()
+            d_p2f = self._pix2face_for_aggregation(cam, mesh, render_img_scale, pix2face_kwargs)
+            img = mesh.context.render_flat(d_p2f[0].contiguous(), tex).cpu().numpy()
             yield (img, cam) if return_camera else img
 
     # ------------------------------------------------------------------------------------------------
@@ -514,54 +523,10 @@ class TexturedPhotogrammetryMesh:
 
         apply_distortion = pix2face_kwargs.get("apply_distortion", True)
         distortion_set = pix2face_kwargs.get("distortion_set", None)
+        p2f = self.pix2face_device(cameras, mesh=mesh, render_img_scale=scale)
         if distortion_set is None or not apply_distortion:
-            return self.pix2face_device(cameras, mesh=mesh, render_img_scale=scale)
-        p2f = self.pix2face(cameras, mesh=mesh, render_img_scale=scale, **pix2face_kwargs)
-        p2f = p2f[None] if p2f.ndim == 2 else p2f
-        return torch.from_numpy(p2f.astype(np.int32)).to(torch.device("cuda", self.device))
-
-    @staticmethod
-    def _to_device_or_mapped(arr, dev, zero_copy=True):
-        """Device tensor for a host prediction image.  The fused last-pixel / vote aggregation reads ONE pixel per
-        visible face, so an image that already sits in page-locked host memory is not copied at all: CUDA's unified
-        addressing lets the kernel fetch those few rows over PCIe straight from the host buffer.  Pageable arrays
-        are uploaded."""
-        import torch
-
-        t = torch.from_numpy(arr)
-        if zero_copy and t.is_pinned():
-            return _HostMapped(t)
-        return t.to(dev, non_blocking=True)
-
-    def _to_host(self, *tensors):
-        """Device tensors -> fresh NumPy arrays owned by the caller.  The transfer goes through page-locked staging
-        buffers that the mesh keeps (full PCIe rate), followed by a multi-threaded host copy into new arrays."""
-        import torch
-
-        outs = []
-        stage = self.__dict__.setdefault("_pinned_stage", {})
-        for i, t in enumerate(tensors):
-            key = (i, t.dtype, tuple(t.shape))
-            if key not in stage:
-                for old in [k for k in stage if k[0] == i]:
-                    del stage[old]
-                stage[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            stage[key].copy_(t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        for i, t in enumerate(tensors):
-            outs.append(torch.empty(t.shape, dtype=t.dtype).copy_(stage[(i, t.dtype, tuple(t.shape))]).numpy())
-        return outs
-
-    def _fetch_prediction(self, cameras, k, scale, image_getter, index_getter):
-        """(array, pred_kind, C) of view k: a caller-supplied getter, else the segmentor's class-index image when
-        it offers one (expanded on the GPU), else whatever get_image_by_index returns."""
-        if image_getter is not None:
-            return self._classify_image(image_getter(k))
-        if index_getter is not None:
-            inds = index_getter(k, scale)
-            if inds is not None:
-                return np.ascontiguousarray(inds), _lib.PRED_INDEX_U8, cameras.n_image_channels()
-        return self._classify_image(cameras.get_image_by_index(k, scale))
+            return p2f
+        return self._warp_device(p2f, self._camera_list(cameras), distortion_set, scale)
 
     def _accumulate_views(self, cameras, aggregate_img_scale, mode, n_channels=None, pix2face_kwargs=None,
                           image_getter=None, single_view_total=None):

@@ -156,6 +156,28 @@ int gg_finalize(gg_context *ctx, double *d_sum, const int32_t *d_count, int64_t 
 int gg_render_flat(gg_context *ctx, const int32_t *d_pix2face, int64_t n_pixels, const double *d_face_tex,
                    int D, void *d_out, int out_dtype, void *stream);
 
+/* ---- lens distortion: Metashape frame-camera model of MetashapeCameraSet.ideal_to_warped
+        (cameras/derived_cameras.py:163-208).  f, cx, cy, W, H are the FULL-resolution intrinsics; image_scale the
+        render scale of the rasters being warped (cameras.py:1027-1053). ---------------------------------------- */
+typedef struct {
+    double f, cx, cy;
+    int32_t W, H;
+    double k1, k2, k3, k4, p1, p2, b1, b2;
+    double image_scale;
+} gg_distortion;
+
+/* For every pixel of an h x w output image: linear index of the nearest source pixel, -1 if the source falls outside
+   the image (replaces make_distortion_map + inverse_map_interpolation, cameras.py:995-1062, utils/indexing.py:87-150).
+   warped_to_ideal = 0: the output is the distorted image and samples an ideal (pinhole) raster -- the pix2face case,
+   solved exactly with Newton iterations; 1: the output is the ideal image and samples the distorted one.
+   d_src_rc (optional, 2*h*w float32): the continuous (row, col) source coordinates. */
+int gg_build_warp_map(int device, const gg_distortion *h_dist, int h, int w, int warped_to_ideal,
+                      int32_t *d_src_index, float *d_src_rc, void *stream);
+/* out[p] = src_index[p] >= 0 ? in[src_index[p]] : fill -- the nearest-neighbour warp of a face-ID raster
+   (utils/image.py:72-126 with interpolation_order = 0), integer-safe. */
+int gg_gather_i32(int device, const int32_t *d_in, const int32_t *d_src_index, int64_t n_out, int32_t fill,
+                  int32_t *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

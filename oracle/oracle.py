@@ -306,3 +306,99 @@ def find_argmax_nonzero_value(array, keepdims=False, axis=1):
 def pix2face_set(verts32, faces, cams, nthreads=0):
     """(n, H, W) int64 -- meshes.py:1735-1749 (per-camera recursion + np.stack)."""
     return np.stack([rasterize(verts32, faces, c, nthreads=nthreads) for c in cams], axis=0)
+
+
+# --------------------------------------------------------------------------------------------------
+# Lens distortion (SURVEY 8f-1): literal restatements of the reference, for the warp parity tests
+# --------------------------------------------------------------------------------------------------
+def metashape_ideal_to_warped(xpix, ypix, f, cx, cy, image_width, image_height, k1=0.0, k2=0.0, k3=0.0, k4=0.0,
+                              p1=0.0, p2=0.0, b1=0.0, b2=0.0):
+    """MetashapeCameraSet.ideal_to_warped, cameras/derived_cameras.py:163-208."""
+    x = (xpix - image_width / 2.0) / f
+    y = (ypix - image_height / 2.0) / f
+    r = np.sqrt(x**2 + y**2)
+    xd = x * (1 + k1 * r**2 + k2 * r**4 + k3 * r**6 + k4 * r**8) + (p1 * (r**2 + 2 * x**2) + 2 * p2 * x * y)
+    yd = y * (1 + k1 * r**2 + k2 * r**4 + k3 * r**6 + k4 * r**8) + (p2 * (r**2 + 2 * y**2) + 2 * p1 * x * y)
+    return image_width / 2.0 + cx + xd * f + xd * b1 + yd * b2, image_height / 2.0 + cy + yd * f
+
+
+def ideal_to_warped_map(params, image_scale=1.0):
+    """make_distortion_map's forward map, cameras/cameras.py:1027-1053: (2, h, w) [rows, cols] of the position in
+    the warped image that every ideal pixel maps to."""
+    im_h, im_w = params["image_height"], params["image_width"]
+    if np.isclose(image_scale, 1.0):
+        h_range, w_range = np.arange(im_h), np.arange(im_w)
+    else:
+        kw = {"start": 1 / (2 * image_scale), "step": 1 / image_scale}
+        h_range = np.arange(stop=im_h, **kw)[: int(im_h * image_scale)]
+        w_range = np.arange(stop=im_w, **kw)[: int(im_w * image_scale)]
+    rows, cols = np.meshgrid(h_range, w_range, indexing="ij")
+    wc, wr = metashape_ideal_to_warped(cols, rows, **params)
+    if not np.isclose(image_scale, 1.0):
+        wc, wr = wc * image_scale, wr * image_scale
+    return np.stack([wr, wc], axis=0)
+
+
+def inverse_map_griddata(ijmap, downsample=1, fill=-1):
+    """inverse_map_interpolation, utils/indexing.py:87-150 (scipy griddata, linear)."""
+    from scipy.interpolate import griddata
+
+    H, W = ijmap.shape[1:]
+    igrid, jgrid = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    grid = np.stack([igrid.ravel(), jgrid.ravel()], axis=1)
+    ds = slice(None, None, downsample)
+    sample_y = np.stack([igrid[ds, ds].ravel(), jgrid[ds, ds].ravel()], axis=1)
+    sample_x = np.stack([ijmap[0][ds, ds].ravel(), ijmap[1][ds, ds].ravel()], axis=1)
+    inv_i = griddata(sample_x, sample_y[:, 0], grid, method="linear", fill_value=fill)
+    inv_j = griddata(sample_x, sample_y[:, 1], grid, method="linear", fill_value=fill)
+    return np.stack([inv_i.reshape(H, W), inv_j.reshape(H, W)], axis=0)
+
+
+def nearest_source_index(src_rows, src_cols, h, w):
+    """Nearest source pixel of continuous (row, col) coordinates, -1 outside the image: what skimage.transform.warp
+    (order=0, mode='constant') does through scipy.ndimage.map_coordinates (utils/image.py:108-117)."""
+    rr, cc = np.floor(src_rows + 0.5), np.floor(src_cols + 0.5)
+    ok = np.isfinite(rr) & np.isfinite(cc) & (rr >= 0) & (rr < h) & (cc >= 0) & (cc < w)
+    idx = np.full(src_rows.shape, -1, dtype=np.int64)
+    idx[ok] = (rr[ok] * w + cc[ok]).astype(np.int64)
+    return idx
+
+
+def warp_ids(ids, src_index, fill=-1):
+    """Integer-safe nearest warp: out[p] = ids.flat[src_index[p]] or fill."""
+    out = np.full(src_index.shape, fill, dtype=ids.dtype)
+    ok = src_index >= 0
+    out[ok] = ids.ravel()[src_index[ok]]
+    return out
+
+
+def exact_inverse_coordinates(params, image_scale=1.0, iters=40):
+    """Exact ideal <- warped source coordinates (rows, cols) by Newton iterations on the forward model in float64:
+    the 'corrected reference' the GPU warp is held to (the reference interpolates a down-sampled forward map)."""
+    im_h, im_w = params["image_height"], params["image_width"]
+    h, w = int(im_h * image_scale), int(im_w * image_scale)
+    one = np.isclose(image_scale, 1.0)
+    ti, tj = np.meshgrid(np.arange(h, dtype=float), np.arange(w, dtype=float), indexing="ij")
+    tx, ty = (tj, ti) if one else (tj / image_scale, ti / image_scale)
+    x, y = tx.copy(), ty.copy()
+    ok = np.zeros(x.shape, dtype=bool)
+    e = 1e-4
+    with np.errstate(all="ignore"):
+        for _ in range(iters):
+            fx, fy = metashape_ideal_to_warped(x, y, **params)
+            rx, ry = fx - tx, fy - ty
+            ok = (np.abs(rx) < 1e-9) & (np.abs(ry) < 1e-9)
+            fxx, fyx = metashape_ideal_to_warped(x + e, y, **params)
+            fxy, fyy = metashape_ideal_to_warped(x, y + e, **params)
+            a, b, c, d = (fxx - fx) / e, (fxy - fx) / e, (fyx - fy) / e, (fyy - fy) / e
+            det = a * d - b * c
+            dx, dy = (d * rx - b * ry) / det, (-c * rx + a * ry) / det
+            lim = 0.25 * (im_w / 2.0 + im_h / 2.0)
+            n = np.maximum(np.abs(dx), np.abs(dy))
+            scale = np.where(n > lim, lim / n, 1.0)
+            x = np.where(ok, x, x - dx * scale)
+            y = np.where(ok, y, y - dy * scale)
+    rows, cols = (y, x) if one else (y * image_scale - 0.5, x * image_scale - 0.5)
+    rows = np.where(ok, rows, np.nan)
+    cols = np.where(ok, cols, np.nan)
+    return rows, cols

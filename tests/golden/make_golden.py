@@ -196,5 +196,62 @@ def main():
         print(fn, (OUT / fn).stat().st_size, "bytes")
 
 
+def main_metashape():
+    """MetashapeCameraSet parsing + lens model + distortion maps from the reference's own code."""
+    import tempfile
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    import metashape_fixture as mf
+    import pyproj  # the stub: make Transformer.from_crs(...).transform(...) return three arrays
+
+    from geograypher.cameras.derived_cameras import MetashapeCameraSet
+
+    poses = mf.poses(5)
+    pyproj.Transformer.from_crs.return_value.transform.side_effect = lambda xx, yy, zz: (xx * 0, yy * 0, zz * 0)
+    with tempfile.TemporaryDirectory() as tmp:
+        xml = mf.camera_xml(poses, unaligned=(3,), other_component=(4,), extra_uncalibrated_sensor=True)
+        path = Path(tmp, "cameras.xml")
+        path.write_text(xml)
+        cams = MetashapeCameraSet(camera_file=path, image_folder="/mnt/images", original_image_folder="/data/survey/images")
+    cam = cams.cameras[0]
+    rng = np.random.default_rng(3)
+    xp, yp = rng.uniform(0, cam.image_width, 200), rng.uniform(0, cam.image_height, 200)
+    xw, yw = cams.ideal_to_warped(cam, xp, yp)
+
+    # a small strongly distorted sensor, like the reference's test (f = 100, k1 = -0.05), scale 1 and 0.5
+    small = cams.cameras[1]
+    small.f, small.cx, small.cy = 100.0, 1.25, -0.75
+    small.image_width, small.image_height, small.image_size = 161, 129, (129, 161)
+    small.distortion_params = dict(k1=-0.05, k2=0.004, k3=0.0, k4=0.0, p1=0.001, p2=-0.0005, b1=0.02, b2=-0.01)
+    maps = {}
+    for scale in (1.0, 0.5):
+        cams.make_distortion_map(small, inversion_downsample=1, image_scale=scale)
+        key = cams.distortion_key(small.distortion_params, scale)
+        maps[f"i2w_{scale}"] = cams._maps_ideal_to_warped[key]
+        maps[f"w2i_{scale}"] = cams._maps_warped_to_ideal[key]
+    cams._maps_ideal_to_warped.clear(); cams._maps_warped_to_ideal.clear()
+    cams.make_distortion_map(small, inversion_downsample=8, image_scale=1.0)
+    maps["w2i_ds8_1.0"] = cams._maps_warped_to_ideal[cams.distortion_key(small.distortion_params, 1.0)]
+
+    np.savez_compressed(
+        OUT / "golden_metashape.npz",
+        xml=np.array(xml), n_cameras=np.array(len(cams)),
+        c2w=np.stack([c.cam_to_world_transform for c in cams.cameras]),
+        filenames=np.array([str(c.image_filename) for c in cams.cameras]),
+        local_to_epsg_4978=cams.get_local_to_epsg_4978_transform(),
+        f=np.array(cam.f), cx=np.array(cam.cx), cy=np.array(cam.cy),
+        size=np.array([cam.image_width, cam.image_height]),
+        dist_keys=np.array(sorted(cam.distortion_params)), dist_vals=np.array([cam.distortion_params[k] for k in sorted(cam.distortion_params)]),
+        xp=xp, yp=yp, xw=xw, yw=yw,
+        small_params=np.array([small.f, small.cx, small.cy, small.image_width, small.image_height] +
+                              [small.distortion_params[k] for k in ("k1", "k2", "k3", "k4", "p1", "p2", "b1", "b2")]),
+        key=np.array(cams.distortion_key(small.distortion_params, 0.5)),
+        **{k.replace(".", "_"): v.astype(np.float32) for k, v in maps.items()},
+    )
+    print("golden_metashape.npz", (OUT / "golden_metashape.npz").stat().st_size, "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--metashape-only" not in sys.argv:
+        main()
+    main_metashape()
