@@ -528,6 +528,50 @@ class TexturedPhotogrammetryMesh:
             return p2f
         return self._warp_device(p2f, self._camera_list(cameras), distortion_set, scale)
 
+
+    @staticmethod
+    def _to_device_or_mapped(arr, dev, zero_copy=True):
+        """Device tensor for a host prediction image.  The fused last-pixel / vote aggregation reads ONE pixel per
+        visible face, so an image that already sits in page-locked host memory is not copied at all: CUDA's unified
+        addressing lets the kernel fetch those few rows over PCIe straight from the host buffer.  Pageable arrays
+        are uploaded."""
+        import torch
+
+        t = torch.from_numpy(arr)
+        if zero_copy and t.is_pinned():
+            return _HostMapped(t)
+        return t.to(dev, non_blocking=True)
+
+    def _to_host(self, *tensors):
+        """Device tensors -> fresh NumPy arrays owned by the caller.  The transfer goes through page-locked staging
+        buffers that the mesh keeps (full PCIe rate), followed by a multi-threaded host copy into new arrays."""
+        import torch
+
+        outs = []
+        stage = self.__dict__.setdefault("_pinned_stage", {})
+        for i, t in enumerate(tensors):
+            key = (i, t.dtype, tuple(t.shape))
+            if key not in stage:
+                for old in [k for k in stage if k[0] == i]:
+                    del stage[old]
+                stage[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            stage[key].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        for i, t in enumerate(tensors):
+            outs.append(torch.empty(t.shape, dtype=t.dtype).copy_(stage[(i, t.dtype, tuple(t.shape))]).numpy())
+        return outs
+
+    def _fetch_prediction(self, cameras, k, scale, image_getter, index_getter):
+        """(array, pred_kind, C) of view k: a caller-supplied getter, else the segmentor's class-index image when
+        it offers one (expanded on the GPU), else whatever get_image_by_index returns."""
+        if image_getter is not None:
+            return self._classify_image(image_getter(k))
+        if index_getter is not None:
+            inds = index_getter(k, scale)
+            if inds is not None:
+                return np.ascontiguousarray(inds), _lib.PRED_INDEX_U8, cameras.n_image_channels()
+        return self._classify_image(cameras.get_image_by_index(k, scale))
+
     def _accumulate_views(self, cameras, aggregate_img_scale, mode, n_channels=None, pix2face_kwargs=None,
                           image_getter=None, single_view_total=None):
         """Shared driver of the aggregation variants: streams every view's prediction image to the GPU and runs
