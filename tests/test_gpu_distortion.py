@@ -42,13 +42,12 @@ def test_warp_map_matches_exact_inverse(golden, scale):
     src, rc = _lib.build_warp_map(dist, h, w, warped_to_ideal=False, want_coords=True)
     src, rc = src.cpu().numpy(), rc.cpu().numpy()
     rows, cols = ora.exact_inverse_coordinates(p, scale)
-    ok = np.isfinite(rows)
-    assert ((rc[..., 0] >= 0) == ok).mean() > 0.999
-    both = ok & (rc[..., 0] >= 0)
-    np.testing.assert_allclose(rc[..., 0][both], rows[both], rtol=0, atol=2e-4)
-    np.testing.assert_allclose(rc[..., 1][both], cols[both], rtol=0, atol=2e-4)
     want = ora.nearest_source_index(rows, cols, h, w)
     assert (src != want).sum() <= 2  # a sample that lands within 1e-9 of a .5 boundary may round the other way
+    inside = (want >= 0) & (src >= 0)
+    assert inside.mean() > 0.6
+    np.testing.assert_allclose(rc[..., 0][inside], rows[inside], rtol=0, atol=2e-4)  # float32 storage
+    np.testing.assert_allclose(rc[..., 1][inside], cols[inside], rtol=0, atol=2e-4)
     # forward direction (dewarping): exact formula, no iteration
     fsrc, frc = _lib.build_warp_map(dist, h, w, warped_to_ideal=True, want_coords=True)
     fwd = ora.ideal_to_warped_map(p, scale)
