@@ -29,6 +29,7 @@ EXPORTS = [
     "gg_last_batch_stats", "gg_set_mesh", "gg_project", "gg_rasterize", "gg_aggregate",
     "gg_project_aggregate", "gg_finalize", "gg_render_flat", "gg_stage_count", "gg_stage_name", "gg_profile",
     "gg_profile_read", "gg_drain", "gg_set_pipeline", "gg_build_warp_map", "gg_gather_i32",
+    "gg_label_polygons",
 ]
 
 
@@ -104,6 +105,7 @@ def load():
     lib.gg_set_pipeline.argtypes = [vp, i32]
     lib.gg_build_warp_map.argtypes = [i32, ctypes.POINTER(GGDistortion), i32, i32, i32, vp, vp, vp]
     lib.gg_gather_i32.argtypes = [i32, vp, vp, i64, ctypes.c_int32, vp, vp]
+    lib.gg_label_polygons.argtypes = [i32, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, vp, vp]
     lib.gg_profile.argtypes = [vp, i32]
     lib.gg_profile_read.argtypes = [vp, vp, vp, i32]
     for name in EXPORTS:
@@ -175,6 +177,42 @@ def gather_i32(d_in, d_src_index, fill: int):
     _check(load().gg_gather_i32(d_in.device.index or 0, d_in.contiguous().data_ptr(), d_src_index.data_ptr(),
                                 d_src_index.numel(), int(fill), out.data_ptr(), _stream_ptr(None)))
     return out
+
+
+def label_polygons_weights(xyz, xy, faces, labels, face_weight, rings, n_classes, device=0):
+    """(n_polys, n_classes) float64 NumPy array of summed face weights.  ``rings``: list (one entry per polygon) of
+    lists of (K, 2) float arrays (exterior rings and holes alike).  Host arrays in, host array out."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise GeograypherB200Error(-5, "no CUDA device: geograypher_b200 has no CPU fallback")
+    dev = torch.device("cuda", device)
+    flat, ring_off, poly_off, bbox = [], [0], [0], []
+    for poly in rings:
+        pts = []
+        for ring in poly:
+            ring = np.asarray(ring, dtype=np.float64).reshape(-1, 2)
+            if len(ring) > 1 and np.array_equal(ring[0], ring[-1]):
+                ring = ring[:-1]  # closed rings repeat their first vertex
+            flat.append(ring)
+            pts.append(ring)
+            ring_off.append(ring_off[-1] + len(ring))
+        poly_off.append(len(ring_off) - 1)
+        allp = np.concatenate(pts) if pts else np.zeros((0, 2))
+        bbox.append([allp[:, 0].min(), allp[:, 1].min(), allp[:, 0].max(), allp[:, 1].max()] if len(allp) else [1, 1, 0, 0])
+    n_polys = len(rings)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    d_xyz, d_xy = t(xyz, np.float64), t(xy, np.float64)
+    d_faces, d_labels = t(faces, np.int32), t(labels, np.float64)
+    d_fw = t(face_weight, np.float64) if face_weight is not None else None
+    d_pxy = t(np.concatenate(flat) if flat else np.zeros((1, 2)), np.float64)
+    d_ro, d_po, d_bb = t(ring_off, np.int32), t(poly_off, np.int32), t(bbox, np.float64)
+    d_w = torch.zeros((n_polys, n_classes), dtype=torch.float64, device=dev)
+    _check(load().gg_label_polygons(device, d_xyz.data_ptr(), d_xy.data_ptr(), d_faces.data_ptr(), d_labels.data_ptr(),
+                                    d_fw.data_ptr() if d_fw is not None else None, int(len(faces)), d_pxy.data_ptr(),
+                                    d_ro.data_ptr(), d_po.data_ptr(), d_bb.data_ptr(), n_polys, int(n_classes),
+                                    d_w.data_ptr(), _stream_ptr(None)))
+    return d_w.cpu().numpy()
 
 
 def _stream_ptr(stream):

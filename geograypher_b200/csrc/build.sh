@@ -7,8 +7,8 @@ OUT=../libgeograypher_b200.so
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -O2
        --fmad=true -Xptxas -v -ccbin /usr/bin/g++)
 mkdir -p build
-for f in gg_api gg_raster gg_aggregate gg_warp; do
+for f in gg_api gg_raster gg_aggregate gg_warp gg_polygons; do
   "$NVCC" "${FLAGS[@]}" -c $f.cu -o build/$f.o 2> build/$f.ptxas.log || { cat build/$f.ptxas.log; exit 1; }
 done
-"$NVCC" -shared -o "$OUT" build/gg_api.o build/gg_raster.o build/gg_aggregate.o build/gg_warp.o -lcudart -ccbin /usr/bin/g++
+"$NVCC" -shared -o "$OUT" build/gg_api.o build/gg_raster.o build/gg_aggregate.o build/gg_warp.o build/gg_polygons.o -lcudart -ccbin /usr/bin/g++
 echo "built $OUT"

@@ -653,11 +653,65 @@ class TexturedPhotogrammetryMesh:
     # ------------------------------------------------------------------------------------------------
     # label_polygons
     # ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _polygon_rings(polygons):
+        """Normalise the accepted polygon containers to a list (per polygon) of lists of (K, 2) rings: arrays, dicts
+        {"exterior", "holes"}, shapely-like (Multi)Polygons, or anything with a ``.geometry`` column of those."""
+        geoms = getattr(polygons, "geometry", polygons)
+        out = []
+        for g in geoms:
+            if hasattr(g, "geoms"):  # MultiPolygon: rings of all parts, even-odd rule
+                parts = list(g.geoms)
+            else:
+                parts = [g]
+            rings = []
+            for part in parts:
+                if hasattr(part, "exterior"):
+                    rings.append(np.asarray(part.exterior.coords)[:, :2])
+                    rings.extend(np.asarray(i.coords)[:, :2] for i in part.interiors)
+                elif isinstance(part, dict):
+                    rings.append(np.asarray(part["exterior"], dtype=float))
+                    rings.extend(np.asarray(h, dtype=float) for h in part.get("holes", []))
+                else:
+                    rings.append(np.asarray(part, dtype=float))
+            out.append(rings)
+        return out
+
     def label_polygons(self, face_labels, polygons, face_weighting=None, sjoin_overlay=True,
-                       return_class_labels=True, unknown_class_label="unknown", buffer_dist_meters=2.0):
-        """Reference meshes.py:1141-1306.  The polygon overlay is geopandas / shapely work downstream of the
-        projection path; it is not part of this build yet."""
-        raise NotImplementedError(
-            "label_polygons is a 'next' row of the hot-path scope (geopandas overlay downstream of aggregation); "
-            "use geograypher's implementation on the face labels returned by aggregate_projected_images"
-        )
+                       return_class_labels=True, unknown_class_label="unknown", buffer_dist_meters=2.0,
+                       vertex_xy=None):
+        """Assign a class to every polygon from per-face labels (reference meshes.py:1141-1306, sjoin path).
+
+        Every face with a finite label whose 2-D triangle lies within a polygon votes for its class with weight
+        ``area3D * face_weighting``; the polygon gets the class with the largest total (lowest class ID on ties),
+        NaN / ``unknown_class_label`` when no face voted.  The polygon tests and the weighted vote run on the GPU
+        (``gg_label_polygons``).
+
+        ``polygons``: sequence of (K, 2) exterior rings, dicts ``{"exterior", "holes"}``, shapely-like polygons, or a
+        GeoDataFrame-like object -- in the SAME planar coordinates as ``vertex_xy``.  ``vertex_xy`` (*new*, (V, 2)):
+        planar coordinates of the mesh vertices; defaults to the x, y of the stored vertices, which is right for meshes
+        kept in a local metric frame (the reference reprojects the mesh to the polygons' CRS with pyproj, which is
+        outside this build).  ``sjoin_overlay=False`` (exact overlay of partially covered faces) is not provided.
+        """
+        if not sjoin_overlay:
+            raise NotImplementedError("only the sjoin (faces entirely within a polygon) overlay is provided")
+        del buffer_dist_meters
+        face_labels = np.squeeze(np.asarray(face_labels, dtype=float))
+        if face_labels.ndim != 1:
+            raise ValueError(f"Faces labels must be one-dimensional, but is {face_labels.ndim}")
+        if face_weighting is not None:
+            face_weighting = np.squeeze(np.asarray(face_weighting, dtype=float))
+            if face_weighting.ndim != 1:
+                raise ValueError(f"Faces labels must be one-dimensional, but is {face_weighting.ndim}")
+        rings = self._polygon_rings(polygons)
+        xy = self.points[:, :2] if vertex_xy is None else np.asarray(vertex_xy, dtype=float)
+        finite = face_labels[np.isfinite(face_labels)]
+        n_classes = int(finite.max()) + 1 if len(finite) else 1
+        weights = _lib.label_polygons_weights(self.points, xy, self.faces, face_labels, face_weighting, rings,
+                                              n_classes, self.device)
+        best = weights.max(axis=1)
+        predicted = np.where(best > 0, weights.argmax(axis=1).astype(float), np.nan).tolist()
+        IDs_to_labels = self.get_IDs_to_labels()
+        if return_class_labels and IDs_to_labels is not None:
+            predicted = [(IDs_to_labels[int(p)] if np.isfinite(p) else unknown_class_label) for p in predicted]
+        return predicted

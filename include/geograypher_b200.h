@@ -178,6 +178,18 @@ int gg_build_warp_map(int device, const gg_distortion *h_dist, int h, int w, int
 int gg_gather_i32(int device, const int32_t *d_in, const int32_t *d_src_index, int64_t n_out, int32_t fill,
                   int32_t *d_out, void *stream);
 
+/* ---- label_polygons (meshes.py:1141-1306 with sjoin_overlay=True): every face with a finite label whose
+        2-D triangle lies within polygon p adds  area3D(face) * face_weight  to d_weights[p][class].
+        d_xyz: V x 3 float64 (3-D area), d_xy: V x 2 float64 (planar coordinates shared with the polygons),
+        d_labels: F float64 (NaN = unlabelled), d_face_weight: F float64 or NULL.  Polygons are sets of rings
+        (exteriors and holes alike, even-odd rule): vertices d_poly_xy, ring r spans [ring_offsets[r], ring_offsets[r+1]),
+        polygon p owns rings [poly_ring_offsets[p], poly_ring_offsets[p+1]), d_poly_bbox: n_polys x 4 (xmin ymin xmax ymax).
+        d_weights (n_polys x n_classes float64) is accumulated into. -------------------------------------------------- */
+int gg_label_polygons(int device, const double *d_xyz, const double *d_xy, const int32_t *d_faces,
+                      const double *d_labels, const double *d_face_weight, int64_t F, const double *d_poly_xy,
+                      const int32_t *d_ring_offsets, const int32_t *d_poly_ring_offsets, const double *d_poly_bbox,
+                      int n_polys, int n_classes, double *d_weights, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -402,3 +402,76 @@ def exact_inverse_coordinates(params, image_scale=1.0, iters=40):
     rows = np.where(ok, rows, np.nan)
     cols = np.where(ok, cols, np.nan)
     return rows, cols
+
+
+# --------------------------------------------------------------------------------------------------
+# label_polygons, shapely-free restatement of the sjoin path (meshes.py:1141-1306)
+# --------------------------------------------------------------------------------------------------
+def _point_in_rings(px, py, rings):
+    inside = np.zeros(px.shape, dtype=bool)
+    for ring in rings:
+        ring = np.asarray(ring, dtype=float)
+        if len(ring) > 1 and np.array_equal(ring[0], ring[-1]):
+            ring = ring[:-1]
+        x0, y0 = ring[:, 0], ring[:, 1]
+        x1, y1 = np.roll(x0, -1), np.roll(y0, -1)
+        for a, b, c, d in zip(x0, y0, x1, y1):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                hit = ((b > py) != (d > py)) & (px < (c - a) * (py - b) / (d - b) + a)
+            inside ^= hit
+    return inside
+
+
+def _segments_cross(ax, ay, bx, by, cx, cy, dx, dy):
+    def orient(px, py, qx, qy, rx, ry):
+        return (qx - px) * (ry - py) - (qy - py) * (rx - px)
+
+    o1, o2 = orient(ax, ay, bx, by, cx, cy), orient(ax, ay, bx, by, dx, dy)
+    o3, o4 = orient(cx, cy, dx, dy, ax, ay), orient(cx, cy, dx, dy, bx, by)
+    return ((o1 > 0) != (o2 > 0)) & ((o3 > 0) != (o4 > 0)) & (o1 != 0) & (o2 != 0) & (o3 != 0) & (o4 != 0)
+
+
+def label_polygons(points, faces, face_labels, polygons_rings, face_weighting=None, xy=None):
+    """Per polygon: class with the largest sum of area3D * weight over the labelled faces whose 2-D triangle lies
+    within the polygon (all vertices inside by the even-odd rule, no edge crossing, no ring inside the triangle);
+    NaN when nothing voted.  Returns (labels list, weights (n_polys, n_classes))."""
+    points = np.asarray(points, dtype=float)
+    xy = points[:, :2] if xy is None else np.asarray(xy, dtype=float)
+    face_labels = np.asarray(face_labels, dtype=float)
+    finite = np.isfinite(face_labels)
+    n_classes = int(face_labels[finite].max()) + 1 if finite.any() else 1
+    tri = xy[faces]  # (F, 3, 2)
+    a3 = points[faces]
+    area3d = 0.5 * np.linalg.norm(np.cross(a3[:, 1] - a3[:, 0], a3[:, 2] - a3[:, 0]), axis=1)
+    w = area3d * (1.0 if face_weighting is None else np.asarray(face_weighting, dtype=float))
+    weights = np.zeros((len(polygons_rings), n_classes))
+    for p, rings in enumerate(polygons_rings):
+        allp = np.concatenate([np.asarray(r, dtype=float) for r in rings])
+        lo, hi = allp.min(0), allp.max(0)
+        cand = finite & (tri[..., 0].min(1) >= lo[0]) & (tri[..., 1].min(1) >= lo[1]) & (tri[..., 0].max(1) <= hi[0]) & (
+            tri[..., 1].max(1) <= hi[1])
+        idx = np.nonzero(cand)[0]
+        if len(idx) == 0:
+            continue
+        t = tri[idx]
+        ok = np.ones(len(idx), dtype=bool)
+        for v in range(3):
+            ok &= _point_in_rings(t[:, v, 0], t[:, v, 1], rings)
+        for ring in rings:
+            ring = np.asarray(ring, dtype=float)
+            if len(ring) > 1 and np.array_equal(ring[0], ring[-1]):
+                ring = ring[:-1]
+            nxt = np.roll(ring, -1, axis=0)
+            for (ex0, ey0), (ex1, ey1) in zip(ring, nxt):
+                for v in range(3):
+                    u = (v + 1) % 3
+                    ok &= ~_segments_cross(t[:, v, 0], t[:, v, 1], t[:, u, 0], t[:, u, 1], ex0, ey0, ex1, ey1)
+            qx, qy = ring[0]
+            s = [(t[:, (v + 1) % 3, 0] - t[:, v, 0]) * (qy - t[:, v, 1]) - (t[:, (v + 1) % 3, 1] - t[:, v, 1]) * (qx - t[:, v, 0])
+                 for v in range(3)]
+            ok &= ~(((s[0] > 0) & (s[1] > 0) & (s[2] > 0)) | ((s[0] < 0) & (s[1] < 0) & (s[2] < 0)))
+        sel = idx[ok]
+        np.add.at(weights[p], face_labels[sel].astype(int), w[sel])
+    best = weights.max(axis=1)
+    labels = np.where(best > 0, weights.argmax(axis=1).astype(float), np.nan)
+    return labels.tolist(), weights

@@ -108,7 +108,11 @@ def test_mesh_host_side():
     with pytest.raises(NotImplementedError):
         gg.TexturedPhotogrammetryMesh((verts, faces), downsample_target=0.5)
     with pytest.raises(NotImplementedError):
-        m.label_polygons(None, None)
+        m.label_polygons(np.zeros(len(faces)), [], sjoin_overlay=False)
+    with pytest.raises(ValueError):  # reference meshes.py:1181-1185
+        m.label_polygons(np.zeros((len(faces), 2)), [])
+    rings = m._polygon_rings([np.array([[0, 0], [1, 0], [1, 1]]), {"exterior": [[0, 0], [4, 0], [4, 4]], "holes": [[[1, 1], [2, 1], [2, 2]]]}])
+    assert [len(r) for r in rings] == [1, 2]
     assert len(m.get_mesh_hash()) == 64
 
 
