@@ -653,6 +653,95 @@ class TexturedPhotogrammetryMesh:
     # ------------------------------------------------------------------------------------------------
     # label_polygons
     # ------------------------------------------------------------------------------------------------
+    # ------------------------------------------------------------------------------------------------
+    # save_renders
+    # ------------------------------------------------------------------------------------------------
+    def save_IDs_to_labels(self, savepath):
+        """Write the ID -> class-name mapping next to the renders (reference meshes.py:2225-2246)."""
+        import json
+
+        Path(savepath).parent.mkdir(parents=True, exist_ok=True)
+        IDs_to_labels = self.get_IDs_to_labels() or {}
+        with open(savepath, "w") as f:
+            json.dump({str(int(k)): (v if isinstance(v, str) else float(v)) for k, v in IDs_to_labels.items()}, f,
+                      ensure_ascii=False, indent=4)
+
+    def save_renders(self, camera_set, render_image_scale=1.0, output_folder="renders", make_composites: bool = False,
+                     save_native_resolution: bool = False, cast_to_uint8: bool = True, save_as_npy: bool = False,
+                     uint8_value_for_null_texture=NULL_TEXTURE_INT_VALUE, n_writer_threads: int = 8, **render_kwargs):
+        """Render the face texture from every camera and write one file per image (reference meshes.py:2248-2397).
+
+        With ``cast_to_uint8`` the cast rule of the reference (< 0, > 255 or non-finite -> the null value, then
+        truncation, meshes.py:2323-2334) is applied on the GPU and only one byte per pixel and channel crosses PCIe;
+        files are written by a small thread pool so that the disk does not stall the GPU.  Outputs keep the image's
+        path relative to ``camera_set.image_folder`` (meshes.py:2349-2366) and are ``.npy`` arrays (``save_as_npy``) or
+        deflate-compressed TIFFs (needs Pillow).  Composites with the photographs and up-sampling to the native
+        resolution are visualisation features outside this build.
+        """
+        if make_composites or (save_native_resolution and render_image_scale != 1):
+            raise NotImplementedError("composites / native-resolution up-sampling are visualisation steps outside this build")
+        if uint8_value_for_null_texture != 0 and cast_to_uint8:
+            raise NotImplementedError("only NULL_TEXTURE_INT_VALUE = 0 is supported for the fused uint8 cast")
+        from concurrent.futures import ThreadPoolExecutor
+
+        output_folder = Path(output_folder)
+        output_folder.mkdir(parents=True, exist_ok=True)
+        self.logger.info(f"Saving renders to {output_folder}")
+        self.save_IDs_to_labels(Path(output_folder, "IDs_to_labels.json"))
+        cam_list = self._camera_list(camera_set)
+
+        def write(path, array):
+            path.parent.mkdir(parents=True, exist_ok=True)
+            array = np.squeeze(array)
+            if save_as_npy:
+                np.save(str(path.with_suffix(".npy")), array)
+                return
+            try:
+                from PIL import Image
+            except ImportError as e:
+                raise ImportError("writing TIFFs needs Pillow; use save_as_npy=True") from e
+            if not cast_to_uint8:  # uint16 when it fits, else uint32 (reference meshes.py:2381-2388)
+                array = array.astype(np.uint16 if np.nanmax(array) <= np.iinfo(np.uint16).max else np.uint32)
+            if array.ndim == 3:
+                array = array[..., :3]
+            Image.fromarray(array).save(str(path.with_suffix(".tif")), compression="tiff_adobe_deflate")
+
+        apply_distortion = render_kwargs.pop("apply_distortion", True)
+        if apply_distortion and not hasattr(camera_set, "warp_dewarp_device"):
+            apply_distortion = False if render_kwargs.get("distortion_set") is None else apply_distortion
+        gen = (self._render_flat_distorted_device(camera_set, render_image_scale, cast_to_uint8)
+               if apply_distortion and hasattr(camera_set, "warp_dewarp_device")
+               else self.render_flat_device(camera_set, None, render_image_scale, "uint8" if cast_to_uint8 else "float64"))
+        k = 0
+        with ThreadPoolExecutor(max_workers=max(1, n_writer_threads)) as pool:
+            futures = []
+            for batch in gen:
+                host = batch.cpu().numpy()
+                for img in host:
+                    cam = cam_list[k]
+                    try:
+                        rel = Path(cam.get_image_filename()).relative_to(camera_set.image_folder)
+                    except (ValueError, TypeError):
+                        raise ValueError(
+                            f"Tried to find the relative path of the camera path ({cam.get_image_filename()}) inside of "
+                            f"the camera set image folder ({camera_set.image_folder}), but failed.")
+                    futures.append(pool.submit(write, Path(output_folder, rel), img))
+                    k += 1
+            for f in futures:
+                f.result()
+
+    def _render_flat_distorted_device(self, cameras, scale, cast_to_uint8):
+        """render_flat through the lens model, on the device: rasterize, warp the face-ID raster, gather."""
+        import torch
+
+        mesh = self.get_mesh_in_cameras_coords(cameras)
+        tex = torch.from_numpy(np.ascontiguousarray(self.get_texture(request_vertex_texture=False), dtype=np.float64)).to(
+            torch.device("cuda", self.device))
+        code = _lib.OUT_U8 if cast_to_uint8 else _lib.OUT_F64
+        for cam in self._camera_list(cameras):
+            p2f = self._pix2face_for_aggregation(cam, mesh, scale, {"distortion_set": cameras, "apply_distortion": True})
+            yield mesh.context.render_flat(p2f.contiguous(), tex, out_dtype=code)
+
     @staticmethod
     def _polygon_rings(polygons):
         """Normalise the accepted polygon containers to a list (per polygon) of lists of (K, 2) rings: arrays, dicts

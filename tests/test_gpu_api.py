@@ -144,3 +144,28 @@ def test_reference_structural_pins(render_img_scale):
         ideal, ora.rasterize(verts.astype(np.float32) - 0, faces,
                              ora.make_camera(cam.cam_to_world_transform, 100, 0, 0, sensor, sensor, render_img_scale,
                                              origin=np.zeros(3))))
+
+
+def test_save_renders(scene, golden_render, tmp_path):
+    """save_renders writes one uint8 file per image, with the reference's cast rule, under the image's relative path."""
+    g, cams0 = scene
+    r = golden_render
+    f, cx, cy, W, H = g["intrinsics"]
+    cams = gg.PhotogrammetryCameraSet(
+        cameras=[gg.PhotogrammetryCamera(f"/data/imgs/flight{i % 2}/{i:04d}.JPG", T, f, cx, cy, int(W), int(H))
+                 for i, T in enumerate(g["c2ws"])])
+    mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), log_level="WARNING")
+    mesh.set_texture(r["tex1"], is_vertex_texture=False)
+    mesh.save_renders(cams, output_folder=tmp_path / "out", save_as_npy=True, apply_distortion=False)
+    assert (tmp_path / "out" / "IDs_to_labels.json").exists()
+    for k in range(len(cams)):
+        arr = np.load(tmp_path / "out" / f"flight{k % 2}" / f"{k:04d}.npy")
+        assert arr.dtype == np.uint8
+        np.testing.assert_array_equal(arr, ora.cast_render_to_uint8(r["render1"][k]))
+    try:
+        from PIL import Image
+    except ImportError:
+        return
+    mesh.save_renders(cams, output_folder=tmp_path / "tif", apply_distortion=False)
+    img = np.asarray(Image.open(tmp_path / "tif" / "flight1" / "0001.tif"))
+    np.testing.assert_array_equal(img, ora.cast_render_to_uint8(r["render1"][1]))
