@@ -29,7 +29,7 @@ EXPORTS = [
     "gg_last_batch_stats", "gg_set_mesh", "gg_project", "gg_rasterize", "gg_aggregate",
     "gg_project_aggregate", "gg_finalize", "gg_render_flat", "gg_stage_count", "gg_stage_name", "gg_profile",
     "gg_profile_read", "gg_drain", "gg_set_pipeline", "gg_build_warp_map", "gg_gather_i32",
-    "gg_label_polygons",
+    "gg_label_polygons", "gg_get_capacity",
 ]
 
 
@@ -92,6 +92,7 @@ def load():
     lib.gg_sync.argtypes = [vp, vp]
     lib.gg_reserve.argtypes = [vp, i64, i64]
     lib.gg_last_batch_stats.argtypes = [vp, i32, vp]
+    lib.gg_get_capacity.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
     lib.gg_set_mesh.argtypes = [vp, vp, i64, vp, i64, vp]
     lib.gg_project.argtypes = [vp, camp, i32, vp, vp, vp, vp, vp]
     lib.gg_rasterize.argtypes = [vp, camp, i32, vp, vp, vp]
@@ -336,8 +337,13 @@ class Context:
 
     def _grow_after_overflow(self, n):
         stats = self.last_batch_stats(n)
-        # counters keep counting past the capacity, so they tell how much is needed
-        self.reserve(int(stats[:, 1].max() * 1.5) + 4096, int(stats[:, 2].max() * 1.5) + 4096)
+        recs, bins = ctypes.c_int64(), ctypes.c_int64()
+        _check(self.lib.gg_get_capacity(self.handle, ctypes.byref(recs), ctypes.byref(bins)))
+        # counters keep counting past the capacity, so they tell how much the last batch needed; an earlier batch may
+        # have been the one that overflowed, hence at least a doubling
+        need_recs = max(int(stats[:, 1].max() * 1.5) + 4096, 2 * recs.value if stats[:, 1].max() >= recs.value else recs.value)
+        need_bins = max(int(stats[:, 2].max() * 1.5) + 4096, 2 * bins.value)
+        self.reserve(need_recs, need_bins)
 
     # -- stage 3 -------------------------------------------------------------------------------------------
     def aggregate(self, pix2face, pred, pred_kind, C, mode, flags, d_sum, d_count, stream=None):

@@ -84,6 +84,8 @@ int gg_create(int device, gg_context **out) {
     GG_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     memset(ctx->vset, 0, sizeof(ctx->vset));
+    GG_CUDA(cudaMalloc(&ctx->d_sticky, sizeof(int32_t)));
+    GG_CUDA(cudaMemset(ctx->d_sticky, 0, sizeof(int32_t)));
     // the short, latency-bound binning kernels get the higher priority so that they slip in between the CTAs of the
     // rasterizer that is still running for the previous batch
     int prio_lo = 0, prio_hi = 0;
@@ -112,6 +114,7 @@ void gg_destroy(gg_context *ctx) {
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_winner);
     cudaFree(ctx->d_wdense);
+    cudaFree(ctx->d_sticky);
     cudaFree(ctx->d_raster);
     for (auto &p : ctx->prof.pending) {
         cudaEventDestroy(p.a);
@@ -139,18 +142,18 @@ int gg_sync(gg_context *ctx, void *stream) {
     ctx->ras_pending[0] = ctx->ras_pending[1] = false;
     GG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     GG_CUDA(cudaGetLastError());
-    for (int i = 0; i < ctx->last_batch_n; ++i) {
-        int32_t c[4];
-        GG_CUDA(cudaMemcpy(c, ctx->vset[ctx->cur].v[i].counters, sizeof(c), cudaMemcpyDeviceToHost));
-        if (c[3] != 0) {
-            char buf[256];
-            snprintf(buf, sizeof(buf),
-                     "scratch overflow in view %d of the last batch (records %d / cap %lld, bin entries %d / cap %lld): "
-                     "call gg_reserve with larger capacities and retry",
-                     i, c[1], (long long)ctx->cap_recs, c[2], (long long)ctx->cap_bins);
-            gg_set_error(buf);
-            return GG_ERR_OVERFLOW;
-        }
+    int32_t sticky = 0;
+    GG_CUDA(cudaMemcpy(&sticky, ctx->d_sticky, sizeof(sticky), cudaMemcpyDeviceToHost));
+    if (sticky != 0) {
+        GG_CUDA(cudaMemset(ctx->d_sticky, 0, sizeof(int32_t)));
+        char buf[320];
+        snprintf(buf, sizeof(buf),
+                 "scratch overflow since the last gg_sync (%s%s; capacity: %lld face records, %lld tile entries per "
+                 "view): the affected batches were skipped; call gg_reserve with larger capacities and redo them",
+                 (sticky & 1) ? "face records " : "", (sticky & 2) ? "tile entries" : "", (long long)ctx->cap_recs,
+                 (long long)ctx->cap_bins);
+        gg_set_error(buf);
+        return GG_ERR_OVERFLOW;
     }
     return GG_OK;
 }
@@ -216,6 +219,14 @@ int gg_reserve(gg_context *ctx, int64_t max_faces_per_view, int64_t max_bin_entr
     }
     ctx->req_recs = max_faces_per_view;
     ctx->req_bins = max_bin_entries_per_view;
+    return GG_OK;
+}
+
+int gg_get_capacity(gg_context *ctx, int64_t *h_faces_per_view, int64_t *h_bin_entries_per_view) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    if (h_faces_per_view) *h_faces_per_view = ctx->cap_recs;
+    if (h_bin_entries_per_view) *h_bin_entries_per_view = ctx->cap_bins;
     return GG_OK;
 }
 

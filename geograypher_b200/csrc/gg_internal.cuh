@@ -132,6 +132,7 @@ struct gg_context {
     int64_t wdense_cap = 0;
     int32_t *d_raster = nullptr;  // internal n x H x W raster when the caller does not want pix2face back
     int64_t raster_cap = 0;
+    int32_t *d_sticky = nullptr;  // OR of the overflow flags of every batch since the last gg_sync
     int last_batch_n = 0;
     int sm_count = 148;
 };

@@ -247,7 +247,7 @@ __device__ __forceinline__ bool tile_may_touch(const GGFaceRec &r, int tx, int t
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__restrict__ verts,
                                                                const int4 *__restrict__ faces, int64_t F,
-                                                               int64_t cap_recs,
+                                                               int64_t cap_recs, int32_t *__restrict__ sticky,
                                                                const __grid_constant__ GGCamBatch cams,
                                                                const __grid_constant__ GGViewBatch views) {
     const int view = blockIdx.y;
@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__
                 if (r.face == (int32_t)(F - 1)) vs.counters[5] = idx;
             } else {
                 atomicOr(&vs.counters[3], 1);
+                atomicOr(sticky, 1);
             }
         }
     }
@@ -413,12 +414,16 @@ __device__ __forceinline__ GGTileFace setup_tile_face(const GGFaceRec &r, int re
     return tf;
 }
 
-__global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, const __grid_constant__ GGCamBatch cams,
+__global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, int32_t *__restrict__ sticky,
+                                                   const __grid_constant__ GGCamBatch cams,
                                                    const __grid_constant__ GGViewBatch views) {
     const int view = blockIdx.y;
     const GGViewScratch &vs = views.v[view];
     if ((int64_t)vs.counters[2] > cap_bins) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&vs.counters[3], 2);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicOr(&vs.counters[3], 2);
+            atomicOr(sticky, 2);
+        }
         return;
     }
     if (vs.counters[3] != 0) return;
@@ -944,10 +949,10 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
     const int gsetup = nb < ctx->sm_count * 8 ? nb : ctx->sm_count * 8;
     GG_LAUNCH(ctx, GG_ST_SETUP, st,
               k_setup_faces<<<dim3(gsetup, n), GG_BLOCK_FACES, 0, st>>>(ctx->d_verts, ctx->d_faces, ctx->F, ctx->cap_recs,
-                                                                        cb, ctx->vset[ctx->cur]));
+                                                                        ctx->d_sticky, cb, ctx->vset[ctx->cur]));
     GG_LAUNCH(ctx, GG_ST_SCAN, st,
               k_reserve_tiles<<<dim3((n_tiles + 255) / 256, n), 256, 0, st>>>(n_tiles, ctx->cap_recs, ctx->vset[ctx->cur]));
-    GG_LAUNCH(ctx, GG_ST_FILL, st, k_fill_bins<<<dim3(ctx->sm_count * 4, n), 256, 0, st>>>(ctx->cap_bins, cb, ctx->vset[ctx->cur]));
+    GG_LAUNCH(ctx, GG_ST_FILL, st, k_fill_bins<<<dim3(ctx->sm_count * 4, n), 256, 0, st>>>(ctx->cap_bins, ctx->d_sticky, cb, ctx->vset[ctx->cur]));
     if (piped) {
         GG_CUDA(cudaEventRecord(ctx->ev_bin[ctx->cur], st_bin));
         GG_CUDA(cudaStreamWaitEvent(st_ras, ctx->ev_bin[ctx->cur], 0));

@@ -587,34 +587,54 @@ class TexturedPhotogrammetryMesh:
         n = len(cam_list)
         single = (n == 1) if single_view_total is None else single_view_total
         flags = self._flags(_lib.FLAG_KEEP_NAN if (single and mode == _lib.MODE_LAST_PIXEL) else 0)
-        d_sum = d_count = None
         C = n_channels
         B = 1 if apply_distortion else self.views_per_batch
         index_getter = getattr(cameras, "get_class_index_image_by_index", None) if mode == _lib.MODE_LAST_PIXEL else None
-        for s in range(0, n, B):
-            batch = cam_list[s : s + B]
-            preds, kind = [], None
-            for k in range(s, s + len(batch)):
-                arr, this_kind, this_C = self._fetch_prediction(cameras, k, aggregate_img_scale, image_getter,
-                                                                index_getter)
-                if mode == _lib.MODE_VOTE:
-                    this_C = n_channels
-                if C is None:
-                    C = this_C
-                if d_sum is None:
-                    d_sum = torch.zeros((F, C), dtype=torch.float64, device=dev)
-                    d_count = torch.zeros((F,), dtype=torch.int32, device=dev)
-                if kind is None:
-                    kind = this_kind
-                elif kind != this_kind:
-                    raise ValueError("all prediction images of a batch must share one dtype / layout")
-                preds.append(self._to_device_or_mapped(arr, dev, zero_copy=not apply_distortion))
-            if apply_distortion:
-                p2f = self._pix2face_for_aggregation(batch[0], mesh, aggregate_img_scale, pix2face_kwargs)
-                mesh.context.aggregate(p2f[0], preds[0], kind, C, mode, flags, d_sum, d_count)
-            else:
-                gg = self._gg_cameras(batch, mesh, aggregate_img_scale)
-                mesh.context.project_aggregate(gg, preds, kind, C, mode, flags, d_sum, d_count)
+        ctx = mesh.context
+        window = 4  # batches in flight between two synchronisations (bounds the memory held by queued predictions)
+        for attempt in range(4):
+            d_sum = d_count = None
+            in_flight = []
+            try:
+                for bi, s in enumerate(range(0, n, B)):
+                    batch = cam_list[s : s + B]
+                    preds, kind = [], None
+                    for k in range(s, s + len(batch)):
+                        arr, this_kind, this_C = self._fetch_prediction(cameras, k, aggregate_img_scale, image_getter,
+                                                                        index_getter)
+                        if mode == _lib.MODE_VOTE:
+                            this_C = n_channels
+                        if C is None:
+                            C = this_C
+                        if d_sum is None:
+                            d_sum = torch.zeros((F, C), dtype=torch.float64, device=dev)
+                            d_count = torch.zeros((F,), dtype=torch.int32, device=dev)
+                        if kind is None:
+                            kind = this_kind
+                        elif kind != this_kind:
+                            raise ValueError("all prediction images of a batch must share one dtype / layout")
+                        preds.append(self._to_device_or_mapped(arr, dev, zero_copy=not apply_distortion))
+                    if apply_distortion:
+                        p2f = self._pix2face_for_aggregation(batch[0], mesh, aggregate_img_scale, pix2face_kwargs)
+                        ctx.aggregate(p2f[0], preds[0], kind, C, mode, flags, d_sum, d_count)
+                        continue
+                    gg = self._gg_cameras(batch, mesh, aggregate_img_scale)
+                    # The calls are asynchronous: batch k+1 is binned while batch k is rasterized and batch k-1 resolved
+                    # on the library's internal streams.  Queued predictions are kept alive until the next sync.
+                    ctx.project_aggregate(gg, preds, kind, C, mode, flags, d_sum, d_count, check=False)
+                    in_flight.append(preds)
+                    if (bi + 1) % window == 0:
+                        ctx.sync()
+                        in_flight.clear()
+                ctx.sync()  # raises GG_ERR_OVERFLOW if any batch since the last sync outgrew the scratch
+                break
+            except _lib.GeograypherB200Error as e:
+                # An overflowing batch is skipped as a whole, so the accumulators are consistent but incomplete: grow
+                # the scratch and redo the aggregation.
+                if e.code != _lib.ERR_OVERFLOW or attempt == 3:
+                    raise
+                ctx._grow_after_overflow(min(B, n))
+                C = n_channels
         return d_sum, d_count, C
 
     def aggregate_projected_images(self, cameras, batch_size: int = 1, aggregate_img_scale: float = 1,

@@ -83,7 +83,8 @@ int gg_abi_version(void);
 const char *gg_last_error(void);
 int gg_create(int device, gg_context **out);
 void gg_destroy(gg_context *ctx);
-/* Synchronise `stream` and report a deferred failure of the work enqueued so far (GG_ERR_OVERFLOW, CUDA). */
+/* Synchronise `stream` and the internal streams, and report a deferred failure of the work enqueued since the last
+   gg_sync (GG_ERR_OVERFLOW: the batches that overflowed the scratch were skipped as a whole; CUDA errors). */
 int gg_sync(gg_context *ctx, void *stream);
 /* gg_project_aggregate runs its fused modes as a two-stage software pipeline on two internal streams (binning of
    batch k+1 overlaps the rasterization of batch k).  The accumulators it writes are complete, with respect to
@@ -93,6 +94,8 @@ int gg_drain(gg_context *ctx, void *stream);
 int gg_set_pipeline(gg_context *ctx, int enable);
 /* Scratch sizing: max face records per view (0 = number of faces) and max (tile, face) pairs per view. */
 int gg_reserve(gg_context *ctx, int64_t max_faces_per_view, int64_t max_bin_entries_per_view);
+/* Current scratch capacities per view (0 before the first rasterization). */
+int gg_get_capacity(gg_context *ctx, int64_t *h_faces_per_view, int64_t *h_bin_entries_per_view);
 /* Counters of the most recent rasterization batch, valid after gg_sync: per view [n_visible_blocks,
    n_face_records, n_bin_entries, overflow_flag].  out must hold 4*n int64. */
 int gg_last_batch_stats(gg_context *ctx, int n, int64_t *h_out);
