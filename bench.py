@@ -127,6 +127,16 @@ def bind_to_gpu_numa_node(index):
         return None
 
 
+def measured_traffic(config, mode_name, views_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from a committed `ncu --set full` capture of
+    this command (profiles/traffic.json), per launch; None when no capture matches."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(p.read_text()).get(f"{config}:{mode_name}:{views_per_launch}")
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -340,13 +350,17 @@ def run_ours(args):
         # int32 counts of the touched faces.
         b12 = 12.0 * (f_v / 2.0) + 12.0 * f_v
         if run_mode == _lib.MODE_PIXEL_SUM:
-            bytes_per_view = b12 + 4.0 * C * P + (16.0 * C + 8.0) * f_v
+            # only pixels that hit the mesh contribute scores: count them from the per-face pixel counts
+            px_added = float(d_count.sum().item()) / (args.steps * B * world)
+            bytes_per_view = b12 + 4.0 * C * px_added + (16.0 * C + 8.0) * f_v
         else:
             bytes_per_view = b12 + 4.0 * P  # B12 of SURVEY 8d: the figure for pix2face, IDs written once
         avg_ms = raster_ms / max(raster_launches, 1)
         achieved = bytes_per_view * B / (avg_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
+        mode_name = "pixel_sum" if run_mode == _lib.MODE_PIXEL_SUM else "last_pixel"
         roofline = {"bound": "hbm", "kernel": "k_raster_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": measured_traffic(args.config, mode_name, B),
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bytes_per_view * B, "avg_launch_ms": avg_ms}
         return {"value": views / elapsed_s, "elapsed_s": elapsed_s, "roofline": roofline, "clocks": clocks,
                 "stage_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1] > 0},
