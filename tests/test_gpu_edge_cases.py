@@ -1,0 +1,165 @@
+"""Edge cases of the path: cameras that see nothing, single-face meshes, ragged raster sizes, channel counts on both
+sides of the fused dense limit, class-index images with ignore values, and the largest tile lists."""
+import numpy as np
+import pytest
+
+import geograypher_b200 as gg
+from geograypher_b200 import synthetic as syn
+from oracle import oracle as ora
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    return torch
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from geograypher_b200 import _lib
+
+    return _lib
+
+
+def _gg(lib, cam):
+    out = lib.GGCamera()
+    for k in range(12):
+        out.m[k] = cam.m[k]
+    out.f, out.px, out.py, out.W, out.H, out.znear = cam.f, cam.px, cam.py, cam.W, cam.H, cam.znear
+    return out
+
+
+def _ctx(torch, lib, v32, faces):
+    ctx = lib.Context(0)
+    ctx.set_mesh(torch.from_numpy(np.ascontiguousarray(v32, dtype=np.float32)).cuda(),
+                 torch.from_numpy(np.ascontiguousarray(faces, dtype=np.int32)).cuda())
+    return ctx
+
+
+def test_camera_that_sees_nothing_and_single_face(torch, lib):
+    verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float64)
+    faces = np.array([[0, 1, 2]], dtype=np.int32)
+    look_away = np.eye(4)          # +Z forward from z = 5: the triangle at z = 0 is behind
+    look_away[2, 3] = 5.0
+    look_at = np.diag([1.0, -1.0, -1.0, 1.0])
+    look_at[:3, 3] = [0.3, 0.3, 5.0]
+    cams = [ora.make_camera(T, 50.0, 0, 0, 37, 29) for T in (look_away, look_at)]
+    ctx = _ctx(torch, lib, verts, faces)
+    p2f = ctx.rasterize([_gg(lib, c) for c in cams]).cpu().numpy()
+    assert (p2f[0] == -1).all()
+    np.testing.assert_array_equal(p2f[1], ora.rasterize(verts.astype(np.float32), faces, cams[1]))
+    assert (p2f[1] == 0).sum() > 10
+    # aggregation over both views: the empty view contributes nothing, also with the -1 -> last-face quirk
+    preds = [torch.full((29, 37, 3), 0.25, device="cuda"), torch.full((29, 37, 3), 0.5, device="cuda")]
+    for flags, want_count in ((0, 1), (lib.FLAG_COMPAT_NEGATIVE_INDEX, 2)):
+        d_sum = torch.zeros((1, 3), dtype=torch.float64, device="cuda")
+        d_count = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        ctx.project_aggregate([_gg(lib, c) for c in cams], preds, lib.PRED_F32, 3, lib.MODE_LAST_PIXEL, flags, d_sum, d_count)
+        ref = ora.aggregate(p2f.astype(np.int64), [p.cpu().numpy() for p in preds], 1, compat_negative_index=bool(flags))
+        assert int(d_count.item()) == want_count == int(ref[1][0])
+        np.testing.assert_array_equal(d_sum.cpu().numpy(), np.nan_to_num(ref[2]))
+
+
+@pytest.mark.parametrize("W,H", [(1, 1), (31, 7), (33, 9), (64, 8), (65, 17), (1023, 5)])
+def test_ragged_raster_sizes(torch, lib, W, H):
+    verts, faces = syn.terrain_mesh(12, 1.0, seed=3, crowns=True)
+    origin = 0.5 * (verts.min(0) + verts.max(0))
+    v32 = (verts - origin).astype(np.float32)
+    T = np.diag([1.0, -1.0, -1.0, 1.0])
+    T[:3, 3] = [6.0, 6.0, 25.0]
+    cam = ora.make_camera(T, 0.9 * max(W, H), 0.5, -0.25, W, H, origin=origin)
+    ctx = _ctx(torch, lib, v32, faces)
+    got = ctx.rasterize([_gg(lib, cam)]).cpu().numpy()[0]
+    ref, _, margin = ora.rasterize(v32, faces, cam, want_depth=True, want_margin=True)
+    assert got.shape == (H, W)
+    assert not ((got != ref) & (margin > 1e-5)).any()
+
+
+@pytest.mark.parametrize("C", [1, 2, 7, 32, 33])
+def test_dense_mode_channel_counts(torch, lib, C):
+    """Fused dense epilogue for C <= 32 (compile-time and runtime channel counts), unfused fallback above."""
+    v32, faces, cams = _scene()
+    H, W = cams[0].H, cams[0].W
+    ctx = _ctx(torch, lib, v32, faces)
+    gg_c = [_gg(lib, c) for c in cams]
+    p2f = ctx.rasterize(gg_c).cpu().numpy()
+    rng = np.random.default_rng(C)
+    host = [rng.random((H, W, C)).astype(np.float32) for _ in cams]
+    F = len(faces)
+    d_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda")
+    d_count = torch.zeros((F,), dtype=torch.int32, device="cuda")
+    ctx.project_aggregate(gg_c, [torch.from_numpy(h).cuda() for h in host], lib.PRED_F32, C, lib.MODE_PIXEL_SUM, 0, d_sum, d_count)
+    ref = np.zeros((F, C))
+    cnt = np.zeros(F, dtype=np.int64)
+    for k in range(len(cams)):
+        ids = p2f[k].ravel()
+        keep = ids >= 0
+        np.add.at(ref, ids[keep], host[k].reshape(-1, C)[keep].astype(np.float64))
+        np.add.at(cnt, ids[keep], 1)
+    np.testing.assert_array_equal(d_count.cpu().numpy(), cnt)
+    np.testing.assert_allclose(d_sum.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+
+
+def _scene():
+    verts, faces, c2ws, cfg = syn.make_survey("tiny")
+    origin = 0.5 * (verts.min(0) + verts.max(0))
+    W, H = cfg.image_size
+    return (verts - origin).astype(np.float32), faces, [ora.make_camera(T, cfg.f, cfg.cx, cfg.cy, W, H, origin=origin) for T in c2ws[:3]]
+
+
+def test_long_tile_lists(torch, lib):
+    """Faces much smaller than a pixel: hundreds of faces per 32x8 tile (lists longer than one shared-memory chunk),
+    for the rasters, the fused last-pixel aggregation and the fused dense mode."""
+    verts, faces = syn.terrain_mesh(160, 0.05, seed=9, crowns=False)
+    verts[:, 2] *= 0.02
+    origin = 0.5 * (verts.min(0) + verts.max(0))
+    v32 = (verts - origin).astype(np.float32)
+    T = np.diag([1.0, -1.0, -1.0, 1.0])
+    T[:3, 3] = [4.0, 4.0, 20.0]
+    W, H, C = 96, 40, 4
+    cam = ora.make_camera(T, 200.0, 0, 0, W, H, origin=origin)   # 8 m of mesh on 80 px: ~2 faces per pixel row
+    ctx = _ctx(torch, lib, v32, faces)
+    got = ctx.rasterize([_gg(lib, cam)])
+    stats = ctx.last_batch_stats(1)
+    assert stats[0, 2] / ((W // 32) * (H // 8)) > 64  # long lists indeed
+    ref, _, margin = ora.rasterize(v32, faces, cam, want_depth=True, want_margin=True)
+    g = got.cpu().numpy()[0]
+    assert not ((g != ref) & (margin > 1e-5)).any()
+    F = len(faces)
+    soft = syn.softmax_predictions(0, H, W, C, grid=(5, 7))
+    d_pred = torch.from_numpy(soft).cuda()
+    # last pixel, fused vs unfused
+    a_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda"); a_cnt = torch.zeros((F,), dtype=torch.int32, device="cuda")
+    b_sum = torch.zeros_like(a_sum); b_cnt = torch.zeros_like(a_cnt)
+    ctx.project_aggregate([_gg(lib, cam)], [d_pred], lib.PRED_F32, C, lib.MODE_LAST_PIXEL, 0, a_sum, a_cnt)
+    ctx.aggregate(got[0], d_pred, lib.PRED_F32, C, lib.MODE_LAST_PIXEL, 0, b_sum, b_cnt)
+    torch.cuda.synchronize()
+    assert torch.equal(a_sum, b_sum) and torch.equal(a_cnt, b_cnt)
+    # dense, fused vs numpy
+    d_sum = torch.zeros_like(a_sum); d_cnt = torch.zeros_like(a_cnt)
+    ctx.project_aggregate([_gg(lib, cam)], [d_pred], lib.PRED_F32, C, lib.MODE_PIXEL_SUM, 0, d_sum, d_cnt)
+    ids = g.ravel(); keep = ids >= 0
+    want = np.zeros((F, C)); np.add.at(want, ids[keep], soft.reshape(-1, C)[keep].astype(np.float64))
+    np.testing.assert_allclose(d_sum.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+
+
+def test_api_single_camera_and_index_images(torch):
+    """API level: one camera (keeps per-channel NaNs like the reference), class-index segmentor with ignore values."""
+    verts, faces, c2ws, cfg = syn.make_survey("tiny")
+    W, H = cfg.image_size
+    intr = {0: dict(f=cfg.f, cx=cfg.cx, cy=cfg.cy, image_width=W, image_height=H, distortion_params={})}
+    cams = gg.PhotogrammetryCameraSet(cam_to_world_transforms=c2ws, intrinsic_params_per_sensor_type=intr)
+    idx = [syn.class_index_image(i, H, W, cfg.n_classes, block=8, ignore_frac=0.1) for i in range(len(cams))]
+    seg = gg.SegmentorPhotogrammetryCameraSet(cams, gg.ArraySegmentor(idx, num_classes=cfg.n_classes, one_hot=True))
+    mesh = gg.TexturedPhotogrammetryMesh((verts, faces), compat_negative_index=True, log_level="WARNING")
+    p2f = mesh.pix2face(cams, apply_distortion=False)
+    avg, info = mesh.aggregate_projected_images(seg)
+    ref = ora.aggregate(p2f, [ora.inds_to_one_hot(i, cfg.n_classes) for i in idx], len(faces))
+    np.testing.assert_array_equal(avg, ref[0])
+    one = mesh.aggregate_projected_images(seg.get_subset_cameras([2]))
+    ref1 = ora.aggregate(p2f[2:3], [ora.inds_to_one_hot(idx[2], cfg.n_classes)], len(faces))
+    np.testing.assert_array_equal(one[0], ref1[0])
+    np.testing.assert_array_equal(one[1]["projection_counts"], ref1[1])
