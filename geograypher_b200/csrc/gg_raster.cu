@@ -32,28 +32,39 @@ struct Proj {
     bool ok;
 };
 
-__device__ __forceinline__ Proj project_vertex(float x, float y, float z, const gg_camera &c) {
-    Proj p;
+struct Cam3 {  // camera-space point
+    float x, y, z;
+};
+
+// C1, first half: camera-space coordinates
+__device__ __forceinline__ Cam3 cam_space(float x, float y, float z, const gg_camera &c) {
+    Cam3 p;
     float t;
     t = __fmul_rn(c.m[0], x);
     t = __fadd_rn(t, __fmul_rn(c.m[1], y));
     t = __fadd_rn(t, __fmul_rn(c.m[2], z));
-    const float xc = __fadd_rn(t, c.m[3]);
+    p.x = __fadd_rn(t, c.m[3]);
     t = __fmul_rn(c.m[4], x);
     t = __fadd_rn(t, __fmul_rn(c.m[5], y));
     t = __fadd_rn(t, __fmul_rn(c.m[6], z));
-    const float yc = __fadd_rn(t, c.m[7]);
+    p.y = __fadd_rn(t, c.m[7]);
     t = __fmul_rn(c.m[8], x);
     t = __fadd_rn(t, __fmul_rn(c.m[9], y));
     t = __fadd_rn(t, __fmul_rn(c.m[10], z));
-    const float zc = __fadd_rn(t, c.m[11]);
-    p.ok = (zc >= c.znear) && isfinite(xc) && isfinite(yc) && isfinite(zc);
+    p.z = __fadd_rn(t, c.m[11]);
+    return p;
+}
+
+// C1, second half + C2: perspective division and snapping of a camera-space point in front of the near plane
+__device__ __forceinline__ Proj to_screen(const Cam3 &q, const gg_camera &c) {
+    Proj p;
+    p.ok = (q.z >= c.znear) && isfinite(q.x) && isfinite(q.y) && isfinite(q.z);
     p.X = 0;
     p.Y = 0;
     p.invz = 0.f;
     if (p.ok) {
-        const float sx = __fadd_rn(__fdiv_rn(__fmul_rn(c.f, xc), zc), c.px);
-        const float sy = __fadd_rn(__fdiv_rn(__fmul_rn(c.f, yc), zc), c.py);
+        const float sx = __fadd_rn(__fdiv_rn(__fmul_rn(c.f, q.x), q.z), c.px);
+        const float sy = __fadd_rn(__fdiv_rn(__fmul_rn(c.f, q.y), q.z), c.py);
         float fx = rintf(__fmul_rn(sx, (float)GG_SUBPIX));
         float fy = rintf(__fmul_rn(sy, (float)GG_SUBPIX));
         if (!isfinite(fx) || !isfinite(fy)) {
@@ -63,10 +74,24 @@ __device__ __forceinline__ Proj project_vertex(float x, float y, float z, const 
             fy = fminf(fmaxf(fy, -GG_COORD_CLAMP), GG_COORD_CLAMP);
             p.X = __float2int_rn(fx);
             p.Y = __float2int_rn(fy);
-            p.invz = __fdiv_rn(1.0f, zc);
+            p.invz = __fdiv_rn(1.0f, q.z);
         }
     }
     return p;
+}
+
+__device__ __forceinline__ Proj project_vertex(float x, float y, float z, const gg_camera &c) {
+    return to_screen(cam_space(x, y, z, c), c);
+}
+
+// C5: intersection of the edge from P (in front of the near plane) to Q (behind it) with the plane z = znear
+__device__ __forceinline__ Cam3 clip_edge(const Cam3 &P, const Cam3 &Q, float znear) {
+    const float t = __fdiv_rn(__fsub_rn(P.z, znear), __fsub_rn(P.z, Q.z));
+    Cam3 r;
+    r.x = __fadd_rn(P.x, __fmul_rn(t, __fsub_rn(Q.x, P.x)));
+    r.y = __fadd_rn(P.y, __fmul_rn(t, __fsub_rn(Q.y, P.y)));
+    r.z = znear;
+    return r;
 }
 
 __device__ __forceinline__ int warp_append(int *counter, bool keep) {
@@ -242,6 +267,65 @@ __device__ __forceinline__ bool tile_may_touch(const GGFaceRec &r, int tx, int t
     return true;
 }
 
+// Screen-space record of one (sub-)triangle given in camera space; false when it cannot cover a pixel centre.
+__device__ __forceinline__ bool build_record(const Cam3 &qa, const Cam3 &qb, const Cam3 &qc, int face_id,
+                                             const gg_camera &c, GGFaceRec &r) {
+    const Proj p0 = to_screen(qa, c);
+    Proj p1 = to_screen(qb, c);
+    Proj p2 = to_screen(qc, c);
+    if (!(p0.ok && p1.ok && p2.ok)) return false;
+    const long long area2 = (long long)(p1.X - p0.X) * (long long)(p2.Y - p0.Y) -
+                            (long long)(p2.X - p0.X) * (long long)(p1.Y - p0.Y);
+    if (area2 == 0) return false;
+    if (area2 < 0) {  // make the interior the positive side
+        const Proj t = p1;
+        p1 = p2;
+        p2 = t;
+    }
+    const int xmin = min(p0.X, min(p1.X, p2.X)), xmax = max(p0.X, max(p1.X, p2.X));
+    const int ymin = min(p0.Y, min(p1.Y, p2.Y)), ymax = max(p0.Y, max(p1.Y, p2.Y));
+    // pixel centres 256*j+128 inside [xmin, xmax]; arithmetic shift == floor division
+    int jmin = (xmin + (GG_SUBPIX - GG_HALF - 1)) >> GG_SUBPIX_LOG2;
+    int jmax = (xmax - GG_HALF) >> GG_SUBPIX_LOG2;
+    int imin = (ymin + (GG_SUBPIX - GG_HALF - 1)) >> GG_SUBPIX_LOG2;
+    int imax = (ymax - GG_HALF) >> GG_SUBPIX_LOG2;
+    jmin = max(jmin, 0);
+    imin = max(imin, 0);
+    jmax = min(jmax, c.W - 1);
+    imax = min(imax, c.H - 1);
+    if (jmin > jmax || imin > imax) return false;
+    const long long X[3] = {p0.X, p1.X, p2.X}, Y[3] = {p0.Y, p1.Y, p2.Y};
+    long long Ak[3], Bk[3], E0[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int k1 = (k + 1) % 3;
+        Ak[k] = -(Y[k1] - Y[k]);
+        Bk[k] = (X[k1] - X[k]);
+        E0[k] = Bk[k] * (GG_HALF - Y[k]) + Ak[k] * (GG_HALF - X[k]);  // at pixel (0,0) centre
+        // contract C3 (top-left rule): E == 0 is inside only on left / top edges
+        const bool inclusive = (Ak[k] > 0) || (Ak[k] == 0 && Bk[k] > 0);
+        r.A[k] = (int)Ak[k];
+        r.B[k] = (int)Bk[k];
+        r.C[k] = E0[k] - (inclusive ? 0 : 1);
+    }
+    const long long a2 = area2 < 0 ? -area2 : area2;
+    const double inv_area = 1.0 / (double)a2;
+    const double w0 = p0.invz, w1 = p1.invz, w2 = p2.invz;
+    // barycentric weights: E1 -> v0, E2 -> v1, E0 -> v2
+    r.w00 = ((double)E0[1] * w0 + (double)E0[2] * w1 + (double)E0[0] * w2) * inv_area;
+    r.gx = (double)GG_SUBPIX * ((double)Ak[1] * w0 + (double)Ak[2] * w1 + (double)Ak[0] * w2) * inv_area;
+    r.gy = (double)GG_SUBPIX * ((double)Bk[1] * w0 + (double)Bk[2] * w1 + (double)Bk[0] * w2) * inv_area;
+    r.w0 = p0.invz;
+    r.w1 = p1.invz;
+    r.w2 = p2.invz;
+    r.face = face_id;
+    r.jmin = (uint16_t)jmin;
+    r.jmax = (uint16_t)jmax;
+    r.imin = (uint16_t)imin;
+    r.imax = (uint16_t)imax;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Face setup: one thread per face of a visible block.
 // ------------------------------------------------------------------------------------------------------
@@ -257,89 +341,74 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__
     const int tiles_x = (c.W + GG_TILE_W - 1) / GG_TILE_W;
     for (int vb = blockIdx.x; vb < n_vis; vb += gridDim.x) {
         const int64_t fi = (int64_t)vs.vis_blocks[vb] * GG_BLOCK_FACES + threadIdx.x;
-        bool keep = false;
-        GGFaceRec r;
+        // up to two triangles per face: faces crossing the near plane are clipped in camera space (contract C5)
+        Cam3 tri[2][3];
+        int n_tri = 0, face_id = -1;
         if (fi < F) {
             const int4 f = faces[fi];
+            face_id = f.w;
             const float4 a = verts[f.x], b = verts[f.y], d = verts[f.z];
-            const Proj p0 = project_vertex(a.x, a.y, a.z, c);
-            Proj p1 = project_vertex(b.x, b.y, b.z, c);
-            Proj p2 = project_vertex(d.x, d.y, d.z, c);
-            if (p0.ok && p1.ok && p2.ok) {
-                long long area2 = (long long)(p1.X - p0.X) * (long long)(p2.Y - p0.Y) -
-                                  (long long)(p2.X - p0.X) * (long long)(p1.Y - p0.Y);
-                if (area2 != 0) {
-                    if (area2 < 0) {
-                        const Proj t = p1;
-                        p1 = p2;
-                        p2 = t;
-                    }
-                    const int xmin = min(p0.X, min(p1.X, p2.X)), xmax = max(p0.X, max(p1.X, p2.X));
-                    const int ymin = min(p0.Y, min(p1.Y, p2.Y)), ymax = max(p0.Y, max(p1.Y, p2.Y));
-                    // pixel centres 256*j+128 inside [xmin, xmax]; arithmetic shift == floor division
-                    int jmin = (xmin + (GG_SUBPIX - GG_HALF - 1)) >> GG_SUBPIX_LOG2;
-                    int jmax = (xmax - GG_HALF) >> GG_SUBPIX_LOG2;
-                    int imin = (ymin + (GG_SUBPIX - GG_HALF - 1)) >> GG_SUBPIX_LOG2;
-                    int imax = (ymax - GG_HALF) >> GG_SUBPIX_LOG2;
-                    jmin = max(jmin, 0);
-                    imin = max(imin, 0);
-                    jmax = min(jmax, c.W - 1);
-                    imax = min(imax, c.H - 1);
-                    if (jmin <= jmax && imin <= imax) {
-                        keep = true;
-                        const long long X[3] = {p0.X, p1.X, p2.X}, Y[3] = {p0.Y, p1.Y, p2.Y};
-                        long long Ak[3], Bk[3], E0[3];
+            const Cam3 p[3] = {cam_space(a.x, a.y, a.z, c), cam_space(b.x, b.y, b.z, c), cam_space(d.x, d.y, d.z, c)};
+            bool finite = true;
+            int nfront = 0;
+            bool front[3];
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            const int k1 = (k + 1) % 3;
-                            Ak[k] = -(Y[k1] - Y[k]);
-                            Bk[k] = (X[k1] - X[k]);
-                            E0[k] = Bk[k] * (GG_HALF - Y[k]) + Ak[k] * (GG_HALF - X[k]);  // at pixel (0,0) centre
-                            // contract C3 (top-left rule): E == 0 is inside only on left / top edges
-                            const bool inclusive = (Ak[k] > 0) || (Ak[k] == 0 && Bk[k] > 0);
-                            r.A[k] = (int)Ak[k];
-                            r.B[k] = (int)Bk[k];
-                            r.C[k] = E0[k] - (inclusive ? 0 : 1);
-                        }
-                        const long long a2 = area2 < 0 ? -area2 : area2;
-                        const double inv_area = 1.0 / (double)a2;
-                        const double w0 = p0.invz, w1 = p1.invz, w2 = p2.invz;
-                        // barycentric weights: E1 -> v0, E2 -> v1, E0 -> v2
-                        r.w00 = ((double)E0[1] * w0 + (double)E0[2] * w1 + (double)E0[0] * w2) * inv_area;
-                        r.gx = (double)GG_SUBPIX * ((double)Ak[1] * w0 + (double)Ak[2] * w1 + (double)Ak[0] * w2) * inv_area;
-                        r.gy = (double)GG_SUBPIX * ((double)Bk[1] * w0 + (double)Bk[2] * w1 + (double)Bk[0] * w2) * inv_area;
-                        r.w0 = p0.invz;
-                        r.w1 = p1.invz;
-                        r.w2 = p2.invz;
-                        r.face = f.w;
-                        r.jmin = (uint16_t)jmin;
-                        r.jmax = (uint16_t)jmax;
-                        r.imin = (uint16_t)imin;
-                        r.imax = (uint16_t)imax;
-                    }
-                }
+            for (int k = 0; k < 3; ++k) {
+                finite = finite && isfinite(p[k].x) && isfinite(p[k].y) && isfinite(p[k].z);
+                front[k] = p[k].z >= c.znear;
+                nfront += front[k] ? 1 : 0;
+            }
+            if (finite && nfront == 3) {
+                tri[0][0] = p[0];
+                tri[0][1] = p[1];
+                tri[0][2] = p[2];
+                n_tri = 1;
+            } else if (finite && nfront == 1) {  // rotate so that the vertex in front comes first: (A, B, C)
+                const int ia = front[0] ? 0 : (front[1] ? 1 : 2);
+                const Cam3 A = p[ia], B = p[(ia + 1) % 3], C = p[(ia + 2) % 3];
+                tri[0][0] = A;
+                tri[0][1] = clip_edge(A, B, c.znear);
+                tri[0][2] = clip_edge(A, C, c.znear);
+                n_tri = 1;
+            } else if (finite && nfront == 2) {  // rotate so that the vertex behind comes last: (A, B, C)
+                const int ic = !front[0] ? 0 : (!front[1] ? 1 : 2);
+                const Cam3 A = p[(ic + 1) % 3], B = p[(ic + 2) % 3], C = p[ic];
+                const Cam3 rbc = clip_edge(B, C, c.znear), rac = clip_edge(A, C, c.znear);
+                tri[0][0] = A;
+                tri[0][1] = B;
+                tri[0][2] = rbc;
+                tri[1][0] = A;
+                tri[1][1] = rbc;
+                tri[1][2] = rac;
+                n_tri = 2;
             }
         }
-        const int idx = warp_append(&vs.counters[1], keep);
-        if (keep) {
-            if (idx < cap_recs) {
-                const int tx0 = r.jmin / GG_TILE_W, tx1 = r.jmax / GG_TILE_W;
-                const int ty0 = r.imin / GG_TILE_H, ty1 = r.imax / GG_TILE_H;
-                const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
-                unsigned long long tmask = 0;
-                const bool small = ntx * nty <= 64;
-                for (int ty = ty0; ty <= ty1; ++ty)
-                    for (int tx = tx0; tx <= tx1; ++tx) {
-                        if (!tile_may_touch(r, tx, ty)) continue;
-                        atomicAdd(&vs.tile_count[ty * tiles_x + tx], 1);
-                        if (small) tmask |= 1ull << ((ty - ty0) * ntx + (tx - tx0));
-                    }
-                r.tmask = small ? tmask : ~0ull;
-                store_vec16(&vs.recs[idx], r);
-                if (r.face == (int32_t)(F - 1)) vs.counters[5] = idx;
-            } else {
-                atomicOr(&vs.counters[3], 1);
-                atomicOr(sticky, 1);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {  // every lane takes part in both rounds (warp-aggregated append)
+            bool keep = false;
+            GGFaceRec r;
+            if (t < n_tri) keep = build_record(tri[t][0], tri[t][1], tri[t][2], face_id, c, r);
+            const int idx = warp_append(&vs.counters[1], keep);
+            if (keep) {
+                if (idx < cap_recs) {
+                    const int tx0 = r.jmin / GG_TILE_W, tx1 = r.jmax / GG_TILE_W;
+                    const int ty0 = r.imin / GG_TILE_H, ty1 = r.imax / GG_TILE_H;
+                    const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
+                    unsigned long long tmask = 0;
+                    const bool small = ntx * nty <= 64;
+                    for (int ty = ty0; ty <= ty1; ++ty)
+                        for (int tx = tx0; tx <= tx1; ++tx) {
+                            if (!tile_may_touch(r, tx, ty)) continue;
+                            atomicAdd(&vs.tile_count[ty * tiles_x + tx], 1);
+                            if (small) tmask |= 1ull << ((ty - ty0) * ntx + (tx - tx0));
+                        }
+                    r.tmask = small ? tmask : ~0ull;
+                    store_vec16(&vs.recs[idx], r);
+                    if (r.face == (int32_t)(F - 1)) vs.counters[5] = idx;
+                } else {
+                    atomicOr(&vs.counters[3], 1);
+                    atomicOr(sticky, 1);
+                }
             }
         }
     }

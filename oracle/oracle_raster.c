@@ -24,7 +24,8 @@
  *   C3  coverage = exact integer edge functions, pixel centre (j+0.5, i+0.5), top-left fill rule
  *   C4  depth = 1/z_cam interpolated linearly in screen space (perspective-correct), nearest wins,
  *       exact ties -> lowest face ID
- *   C5  a face with any vertex at z_cam < znear (or non-finite) is dropped
+ *   C5  faces are clipped against the plane z_cam = znear in camera space (float32, fixed operation order); a face
+ *       entirely behind it, or with a non-finite coordinate, is dropped
  * It is pinned against the reference's own known-answer tests for this path
  * (tests/test_derived_meshes.py:23-76, tests/test_derived_cameras.py:339-415) in
  * tests/test_oracle_reference_pins.py.
@@ -52,40 +53,37 @@ typedef struct {
     float znear;  /* contract C5 */
 } ora_camera;
 
-/* Contract C1+C2 for one vertex.  volatile-free: relies on -ffp-contract=off and SSE float math. */
-static inline int project_vertex(const float *v, const ora_camera *c, int32_t *X, int32_t *Y,
-                                 float *invz) {
+/* Contract C1, first half: camera-space coordinates.  Relies on -ffp-contract=off and SSE float math. */
+static inline void cam_space(const float *v, const ora_camera *c, float *out) {
     const float x = v[0], y = v[1], z = v[2];
     const float *m = c->m;
     float t;
     t = m[0] * x;
     t = t + m[1] * y;
     t = t + m[2] * z;
-    const float xc = t + m[3];
+    out[0] = t + m[3];
     t = m[4] * x;
     t = t + m[5] * y;
     t = t + m[6] * z;
-    const float yc = t + m[7];
+    out[1] = t + m[7];
     t = m[8] * x;
     t = t + m[9] * y;
     t = t + m[10] * z;
-    const float zc = t + m[11];
-    if (!(zc >= c->znear) || !isfinite(xc) || !isfinite(yc) || !isfinite(zc)) {
-        *X = 0;
-        *Y = 0;
-        *invz = 0.0f;
-        return 0;
-    }
+    out[2] = t + m[11];
+}
+
+/* Contract C1 second half + C2: perspective division and snapping of a camera-space point with zc >= znear. */
+static inline int to_screen(const float *pc, const ora_camera *c, int32_t *X, int32_t *Y, float *invz) {
+    const float xc = pc[0], yc = pc[1], zc = pc[2];
+    *X = 0;
+    *Y = 0;
+    *invz = 0.0f;
+    if (!(zc >= c->znear) || !isfinite(xc) || !isfinite(yc) || !isfinite(zc)) return 0;
     float sx = (c->f * xc) / zc + c->px;
     float sy = (c->f * yc) / zc + c->py;
     float fx = nearbyintf(sx * (float)ORA_SUBPIX); /* round-half-even */
     float fy = nearbyintf(sy * (float)ORA_SUBPIX);
-    if (!isfinite(fx) || !isfinite(fy)) {
-        *X = 0;
-        *Y = 0;
-        *invz = 0.0f;
-        return 0;
-    }
+    if (!isfinite(fx) || !isfinite(fy)) return 0;
     if (fx > ORA_CLAMP) fx = ORA_CLAMP;
     if (fx < -ORA_CLAMP) fx = -ORA_CLAMP;
     if (fy > ORA_CLAMP) fy = ORA_CLAMP;
@@ -94,6 +92,23 @@ static inline int project_vertex(const float *v, const ora_camera *c, int32_t *X
     *Y = (int32_t)fy;
     *invz = 1.0f / zc;
     return 1;
+}
+
+static inline int project_vertex(const float *v, const ora_camera *c, int32_t *X, int32_t *Y, float *invz) {
+    float pc[3];
+    cam_space(v, c, pc);
+    return to_screen(pc, c, X, Y, invz);
+}
+
+/* Contract C5: intersection of the edge from P (in front, zp >= znear) to Q (behind) with the plane z = znear. */
+static inline void clip_edge(const float *P, const float *Q, float znear, float *R) {
+    const float t = (P[2] - znear) / (P[2] - Q[2]);
+    float d;
+    d = Q[0] - P[0];
+    R[0] = P[0] + t * d;
+    d = Q[1] - P[1];
+    R[1] = P[1] + t * d;
+    R[2] = znear;
 }
 
 /* Stage 1 on its own: project every vertex (used to check the CUDA projection bit for bit). */
@@ -115,23 +130,93 @@ static inline int64_t floordiv(int64_t a, int64_t b) {
  * the interior towards +y, i.e. below it on a y-down screen).  (A,B) = gradient of E. */
 static inline int edge_inclusive(int64_t A, int64_t B) { return (A > 0) || (A == 0 && B > 0); }
 
+/* Rasterize one (sub-)triangle given in camera space (all three points in front of the near plane) into the
+ * row band [r0, r1).  Strictly nearer replaces: with faces visited in increasing ID this is the lowest-ID tie-break. */
+static void raster_tri(const float *pa, const float *pb, const float *pc, int32_t face, const ora_camera *cam, int r0,
+                       int r1, int32_t *pix2face, double *wbest, double *wsecond) {
+    const int W = cam->W;
+    int32_t X[3], Y[3];
+    float IZ[3];
+    if (!to_screen(pa, cam, &X[0], &Y[0], &IZ[0]) || !to_screen(pb, cam, &X[1], &Y[1], &IZ[1]) ||
+        !to_screen(pc, cam, &X[2], &Y[2], &IZ[2]))
+        return;
+    int64_t x0 = X[0], y0 = Y[0], x1 = X[1], y1 = Y[1], x2 = X[2], y2 = Y[2];
+    double w0 = IZ[0], w1 = IZ[1], w2 = IZ[2];
+    /* bounding box in fixed point -> pixel-centre index range */
+    int64_t xmin = x0 < x1 ? x0 : x1;
+    if (x2 < xmin) xmin = x2;
+    int64_t xmax = x0 > x1 ? x0 : x1;
+    if (x2 > xmax) xmax = x2;
+    int64_t ymin = y0 < y1 ? y0 : y1;
+    if (y2 < ymin) ymin = y2;
+    int64_t ymax = y0 > y1 ? y0 : y1;
+    if (y2 > ymax) ymax = y2;
+    /* centres c = 256*j + 128 with xmin <= c <= xmax */
+    int64_t jmin = floordiv(xmin - ORA_HALF + ORA_SUBPIX - 1, ORA_SUBPIX); /* ceil */
+    int64_t jmax = floordiv(xmax - ORA_HALF, ORA_SUBPIX);
+    int64_t imin = floordiv(ymin - ORA_HALF + ORA_SUBPIX - 1, ORA_SUBPIX);
+    int64_t imax = floordiv(ymax - ORA_HALF, ORA_SUBPIX);
+    if (jmin < 0) jmin = 0;
+    if (jmax > W - 1) jmax = W - 1;
+    if (imin < r0) imin = r0;
+    if (imax > r1 - 1) imax = r1 - 1;
+    if (jmin > jmax || imin > imax) return;
+    int64_t area2 = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+    if (area2 == 0) return;
+    if (area2 < 0) { /* make the interior the positive side */
+        int64_t tx = x1, ty = y1;
+        double tw = w1;
+        x1 = x2;
+        y1 = y2;
+        w1 = w2;
+        x2 = tx;
+        y2 = ty;
+        w2 = tw;
+        area2 = -area2;
+    }
+    /* E_k(P) = A_k*Px + B_k*Py + C_k ; edge k runs v_k -> v_{k+1} */
+    const int64_t A0 = -(y1 - y0), B0 = (x1 - x0);
+    const int64_t A1 = -(y2 - y1), B1 = (x2 - x1);
+    const int64_t A2 = -(y0 - y2), B2 = (x0 - x2);
+    const int inc0 = edge_inclusive(A0, B0), inc1 = edge_inclusive(A1, B1), inc2 = edge_inclusive(A2, B2);
+    const double inv_area = 1.0 / (double)area2;
+    for (int64_t i = imin; i <= imax; ++i) {
+        const int64_t Py = ORA_SUBPIX * i + ORA_HALF;
+        for (int64_t j = jmin; j <= jmax; ++j) {
+            const int64_t Px = ORA_SUBPIX * j + ORA_HALF;
+            const int64_t E0 = B0 * (Py - y0) + A0 * (Px - x0);
+            const int64_t E1 = B1 * (Py - y1) + A1 * (Px - x1);
+            const int64_t E2 = B2 * (Py - y2) + A2 * (Px - x2);
+            if (E0 < 0 || E1 < 0 || E2 < 0) continue;
+            if ((E0 == 0 && !inc0) || (E1 == 0 && !inc1) || (E2 == 0 && !inc2)) continue;
+            /* barycentric weights: E1 -> v0, E2 -> v1, E0 -> v2 */
+            const double w = ((double)E1 * w0 + (double)E2 * w1 + (double)E0 * w2) * inv_area;
+            const size_t p = (size_t)i * (size_t)W + (size_t)j;
+            if (w > wbest[p]) {
+                if (wsecond && pix2face[p] != face) wsecond[p] = wbest[p];
+                wbest[p] = w;
+                pix2face[p] = face;
+            } else if (wsecond && pix2face[p] != face && w > wsecond[p]) {
+                wsecond[p] = w;
+            }
+        }
+    }
+}
+
 /*
  * Rasterize one view.
  *   pix2face : H*W int32, -1 = no face                                  (required)
  *   depth_w  : H*W double, best 1/z_cam (0 where no face)               (optional)
  *   margin   : H*W double, (w_best - w_second)/w_best, 1 if no runner-up (optional; contract: a pixel is
  *              "depth-safe" iff margin > eps_depth)
- * Faces are visited in increasing ID inside every row band, so "strictly nearer replaces" realises the
- * lowest-ID tie-break of C4.
+ * Faces are visited in increasing ID inside every row band.
  */
 void ora_rasterize(const float *verts, int64_t V, const int32_t *faces, int64_t F, const ora_camera *cam,
                    int32_t *pix2face, double *depth_w, double *margin, int nthreads) {
     const int W = cam->W, H = cam->H;
-    int32_t *X = (int32_t *)malloc(sizeof(int32_t) * (size_t)V);
-    int32_t *Y = (int32_t *)malloc(sizeof(int32_t) * (size_t)V);
-    float *IZ = (float *)malloc(sizeof(float) * (size_t)V);
-    uint8_t *OK = (uint8_t *)malloc((size_t)V);
-    ora_project(verts, V, cam, X, Y, IZ, OK);
+    float *PC = (float *)malloc(sizeof(float) * 3 * (size_t)V); /* camera-space vertices */
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < V; ++i) cam_space(verts + 3 * i, cam, PC + 3 * i);
 
     const size_t P = (size_t)W * (size_t)H;
     double *wbest = (double *)malloc(sizeof(double) * P);
@@ -150,76 +235,40 @@ void ora_rasterize(const float *verts, int64_t V, const int32_t *faces, int64_t 
     int nbands = nthreads * 4;
     if (nbands > H) nbands = H;
     if (nbands < 1) nbands = 1;
+    const float znear = cam->znear;
 
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
     for (int band = 0; band < nbands; ++band) {
         const int r0 = (int)((int64_t)H * band / nbands);
         const int r1 = (int)((int64_t)H * (band + 1) / nbands);
         for (int64_t fi = 0; fi < F; ++fi) {
-            const int32_t i0 = faces[3 * fi], i1 = faces[3 * fi + 1], i2 = faces[3 * fi + 2];
-            if (i0 < 0 || i1 < 0 || i2 < 0 || i0 >= V || i1 >= V || i2 >= V) continue;
-            if (!(OK[i0] && OK[i1] && OK[i2])) continue; /* C5 */
-            int64_t x0 = X[i0], y0 = Y[i0], x1 = X[i1], y1 = Y[i1], x2 = X[i2], y2 = Y[i2];
-            double w0 = IZ[i0], w1 = IZ[i1], w2 = IZ[i2];
-            /* bounding box in fixed point -> pixel-centre index range */
-            int64_t xmin = x0 < x1 ? x0 : x1;
-            if (x2 < xmin) xmin = x2;
-            int64_t xmax = x0 > x1 ? x0 : x1;
-            if (x2 > xmax) xmax = x2;
-            int64_t ymin = y0 < y1 ? y0 : y1;
-            if (y2 < ymin) ymin = y2;
-            int64_t ymax = y0 > y1 ? y0 : y1;
-            if (y2 > ymax) ymax = y2;
-            /* centres c = 256*j + 128 with xmin <= c <= xmax */
-            int64_t jmin = floordiv(xmin - ORA_HALF + ORA_SUBPIX - 1, ORA_SUBPIX); /* ceil */
-            int64_t jmax = floordiv(xmax - ORA_HALF, ORA_SUBPIX);
-            int64_t imin = floordiv(ymin - ORA_HALF + ORA_SUBPIX - 1, ORA_SUBPIX);
-            int64_t imax = floordiv(ymax - ORA_HALF, ORA_SUBPIX);
-            if (jmin < 0) jmin = 0;
-            if (jmax > W - 1) jmax = W - 1;
-            if (imin < r0) imin = r0;
-            if (imax > r1 - 1) imax = r1 - 1;
-            if (jmin > jmax || imin > imax) continue;
-            int64_t area2 = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
-            if (area2 == 0) continue;
-            if (area2 < 0) { /* make the interior the positive side */
-                int64_t tx = x1, ty = y1;
-                double tw = w1;
-                x1 = x2;
-                y1 = y2;
-                w1 = w2;
-                x2 = tx;
-                y2 = ty;
-                w2 = tw;
-                area2 = -area2;
+            const int32_t idx[3] = {faces[3 * fi], faces[3 * fi + 1], faces[3 * fi + 2]};
+            if (idx[0] < 0 || idx[1] < 0 || idx[2] < 0 || idx[0] >= V || idx[1] >= V || idx[2] >= V) continue;
+            const float *p[3] = {PC + 3 * (size_t)idx[0], PC + 3 * (size_t)idx[1], PC + 3 * (size_t)idx[2]};
+            int front[3], nfront = 0, finite = 1;
+            for (int k = 0; k < 3; ++k) {
+                finite = finite && isfinite(p[k][0]) && isfinite(p[k][1]) && isfinite(p[k][2]);
+                front[k] = p[k][2] >= znear;
+                nfront += front[k];
             }
-            /* E_k(P) = A_k*Px + B_k*Py + C_k ; edge k runs v_k -> v_{k+1} */
-            const int64_t A0 = -(y1 - y0), B0 = (x1 - x0);
-            const int64_t A1 = -(y2 - y1), B1 = (x2 - x1);
-            const int64_t A2 = -(y0 - y2), B2 = (x0 - x2);
-            const int inc0 = edge_inclusive(A0, B0), inc1 = edge_inclusive(A1, B1),
-                      inc2 = edge_inclusive(A2, B2);
-            const double inv_area = 1.0 / (double)area2;
-            for (int64_t i = imin; i <= imax; ++i) {
-                const int64_t Py = ORA_SUBPIX * i + ORA_HALF;
-                for (int64_t j = jmin; j <= jmax; ++j) {
-                    const int64_t Px = ORA_SUBPIX * j + ORA_HALF;
-                    const int64_t E0 = B0 * (Py - y0) + A0 * (Px - x0);
-                    const int64_t E1 = B1 * (Py - y1) + A1 * (Px - x1);
-                    const int64_t E2 = B2 * (Py - y2) + A2 * (Px - x2);
-                    if (E0 < 0 || E1 < 0 || E2 < 0) continue;
-                    if ((E0 == 0 && !inc0) || (E1 == 0 && !inc1) || (E2 == 0 && !inc2)) continue;
-                    /* barycentric weights: E1 -> v0, E2 -> v1, E0 -> v2 */
-                    const double w = ((double)E1 * w0 + (double)E2 * w1 + (double)E0 * w2) * inv_area;
-                    const size_t p = (size_t)i * (size_t)W + (size_t)j;
-                    if (w > wbest[p]) {
-                        if (wsecond) wsecond[p] = wbest[p];
-                        wbest[p] = w;
-                        pix2face[p] = (int32_t)fi;
-                    } else if (wsecond && w > wsecond[p]) {
-                        wsecond[p] = w;
-                    }
-                }
+            if (!finite || nfront == 0) continue;
+            if (nfront == 3) {
+                raster_tri(p[0], p[1], p[2], (int32_t)fi, cam, r0, r1, pix2face, wbest, wsecond);
+            } else if (nfront == 1) { /* C5: rotate so that the vertex in front comes first: (A, B, C) */
+                const int a = front[0] ? 0 : (front[1] ? 1 : 2);
+                const float *A = p[a], *B = p[(a + 1) % 3], *C = p[(a + 2) % 3];
+                float rab[3], rac[3];
+                clip_edge(A, B, znear, rab);
+                clip_edge(A, C, znear, rac);
+                raster_tri(A, rab, rac, (int32_t)fi, cam, r0, r1, pix2face, wbest, wsecond);
+            } else { /* two in front: rotate so that the vertex behind comes last: (A, B, C) */
+                const int c = !front[0] ? 0 : (!front[1] ? 1 : 2);
+                const float *A = p[(c + 1) % 3], *B = p[(c + 2) % 3], *C = p[c];
+                float rbc[3], rac[3];
+                clip_edge(B, C, znear, rbc);
+                clip_edge(A, C, znear, rac);
+                raster_tri(A, B, rbc, (int32_t)fi, cam, r0, r1, pix2face, wbest, wsecond);
+                raster_tri(A, rbc, rac, (int32_t)fi, cam, r0, r1, pix2face, wbest, wsecond);
             }
         }
     }
@@ -230,10 +279,7 @@ void ora_rasterize(const float *verts, int64_t V, const int32_t *faces, int64_t 
     }
     free(wbest);
     if (wsecond) free(wsecond);
-    free(X);
-    free(Y);
-    free(IZ);
-    free(OK);
+    free(PC);
 }
 
 int ora_num_threads(void) {

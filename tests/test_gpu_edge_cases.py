@@ -163,3 +163,33 @@ def test_api_single_camera_and_index_images(torch):
     ref1 = ora.aggregate(p2f[2:3], [ora.inds_to_one_hot(idx[2], cfg.n_classes)], len(faces))
     np.testing.assert_array_equal(one[0], ref1[0])
     np.testing.assert_array_equal(one[1]["projection_counts"], ref1[1])
+
+
+@pytest.mark.parametrize("znear", [1e-3, 0.75, 3.0])
+def test_near_plane_clipping(torch, lib, znear):
+    """Contract C5: faces crossing the plane z_cam = znear are clipped, not dropped.  A camera standing ON the
+    terrain, looking along it: the ground under and beside the camera crosses the near plane."""
+    verts, faces = syn.terrain_mesh(40, 1.0, seed=4, crowns=True)
+    origin = 0.5 * (verts.min(0) + verts.max(0))
+    v32 = (verts - origin).astype(np.float32)
+    eye = np.array([20.3, 6.2, float(verts[:, 2].max()) * 0.3 + 1.5])
+    # camera looking along +Y (world), image up = +Z: columns of c2w are the camera axes in world coordinates
+    c2w = np.eye(4)
+    c2w[:3, 0] = [1, 0, 0]
+    c2w[:3, 1] = [0, 0, -1]
+    c2w[:3, 2] = [0, 1, 0]
+    c2w[:3, 3] = eye
+    W, H = 320, 200
+    cam = ora.make_camera(c2w, 160.0, 0, 0, W, H, origin=origin, znear=znear)
+    ctx = _ctx(torch, lib, v32, faces)
+    got = ctx.rasterize([_gg(lib, cam)]).cpu().numpy()[0]
+    ref, _, margin = ora.rasterize(v32, faces, cam, want_depth=True, want_margin=True)
+    bad = (got != ref) & (margin > 1e-5)
+    assert not bad.any(), int(bad.sum())
+    assert (ref >= 0).mean() > 0.3
+    # clipped faces are really there: faces with a vertex behind the near plane own pixels
+    X, Y, invz, valid = ora.project(v32, cam)
+    crossing = (~valid[faces]).any(axis=1) & valid[faces].any(axis=1)
+    assert crossing.sum() > 0
+    if znear >= 0.75:
+        assert np.isin(ref[ref >= 0], np.nonzero(crossing)[0]).sum() > 50
