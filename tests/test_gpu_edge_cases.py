@@ -172,12 +172,14 @@ def test_near_plane_clipping(torch, lib, znear):
     verts, faces = syn.terrain_mesh(40, 1.0, seed=4, crowns=True)
     origin = 0.5 * (verts.min(0) + verts.max(0))
     v32 = (verts - origin).astype(np.float32)
-    eye = np.array([20.3, 6.2, float(verts[:, 2].max()) * 0.3 + 1.5])
-    # camera looking along +Y (world), image up = +Z: columns of c2w are the camera axes in world coordinates
+    ground = float(verts[(np.abs(verts[:, 0] - 20.3) < 1) & (np.abs(verts[:, 1] - 6.2) < 1), 2].max())
+    eye = np.array([20.3, 6.2, ground + 2.0])
+    # camera looking forward (+Y) and 45 degrees down: the columns of c2w are the camera axes in world coordinates
+    a = np.sqrt(0.5)
     c2w = np.eye(4)
     c2w[:3, 0] = [1, 0, 0]
-    c2w[:3, 1] = [0, 0, -1]
-    c2w[:3, 2] = [0, 1, 0]
+    c2w[:3, 1] = [0, -a, -a]
+    c2w[:3, 2] = [0, a, -a]
     c2w[:3, 3] = eye
     W, H = 320, 200
     cam = ora.make_camera(c2w, 160.0, 0, 0, W, H, origin=origin, znear=znear)
