@@ -323,6 +323,23 @@ int gg_rasterize(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_pix
     return gg_launch_rasterize(ctx, h_cams, n, d_pix2face, d_depth, 0, 0, (cudaStream_t)stream, (cudaStream_t)stream);
 }
 
+int gg_rasterize_render_flat(gg_context *ctx, const gg_camera *h_cams, int n, const double *d_face_tex, int D,
+                             void *d_out, int out_dtype, int32_t *d_pix2face, void *stream) {
+    int rc = check_ctx(ctx, true);
+    if (rc != GG_OK) return rc;
+    rc = check_cams(h_cams, n);
+    if (rc != GG_OK) return rc;
+    if (!d_face_tex || !d_out || D < 1) {
+        gg_set_error("gg_rasterize_render_flat: bad arguments");
+        return GG_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = gg_pipeline_drain(ctx, st);
+    if (rc != GG_OK) return rc;
+    return gg_launch_rasterize(ctx, h_cams, n, d_pix2face, nullptr, 0, 0, st, st, nullptr, 0, 0, nullptr, nullptr, d_face_tex,
+                               D, d_out, out_dtype);
+}
+
 int gg_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred, int pred_kind, int C,
                  int mode, int flags, double *d_sum, int32_t *d_count, void *stream) {
     int rc = check_ctx(ctx, true);

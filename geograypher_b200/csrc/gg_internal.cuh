@@ -178,7 +178,8 @@ int gg_launch_project(gg_context *ctx, const gg_camera *cams, int n, int32_t *dX
 int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *d_pix2face, float *d_depth,
                         int want_winners, int compat_bg, cudaStream_t st_bin, cudaStream_t st_ras,
                         const void *const *h_pred = nullptr, int pred_kind = 0, int C = 0, double *d_sum = nullptr,
-                        int32_t *d_count = nullptr);
+                        int32_t *d_count = nullptr, const double *d_tex = nullptr, int D = 0, void *d_out = nullptr,
+                        int out_dtype = 0);
 // gg_aggregate.cu: consume the per-face winners of the last rasterization batch (all views, in view order)
 int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, int pred_kind, int C, int mode, int flags,
                             double *d_sum, int32_t *d_count, cudaStream_t st);

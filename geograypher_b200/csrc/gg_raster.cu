@@ -559,6 +559,7 @@ __device__ __noinline__ bool exact_cover(const GGFaceRec &r, int j, int i, float
 #define GG_RM_PLAIN 0
 #define GG_RM_WINNERS 1
 #define GG_RM_DENSE 2
+#define GG_RM_GATHER 3  // fused render_flat: out[p, :] = tex[face, :] (T = output element type)
 
 struct GGDenseArgs {
     GGPredBatch preds;
@@ -566,7 +567,28 @@ struct GGDenseArgs {
     int32_t *count;  // [F]
     int C;
     int index_kind;  // 1: (H,W) uint8 class index expanded on the fly
+    // GG_RM_GATHER
+    const double *tex;  // [F][D]
+    void *out;          // [n][H][W][D]
+    int D;
 };
+
+template <typename OUT>
+__device__ __forceinline__ OUT gather_convert(double v);
+template <>
+__device__ __forceinline__ double gather_convert<double>(double v) {
+    return v;
+}
+template <>
+__device__ __forceinline__ float gather_convert<float>(double v) {
+    return (float)v;
+}
+template <>
+__device__ __forceinline__ uint8_t gather_convert<uint8_t>(double v) {
+    // save_renders' rule (meshes.py:2323-2334): < 0, > 255 or non-finite -> 0, then astype(uint8) truncates
+    if (!(v >= 0.0) || v > 255.0 || !isfinite(v)) return 0;
+    return (uint8_t)v;
+}
 
 template <typename T>
 __device__ __forceinline__ float dense_load(const T *__restrict__ pred, int64_t pix, int C, int ch, int index_kind) {
@@ -731,6 +753,35 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
         if (compat_bg) {  // meshes.py:2000: background pixels index the last face
             bgmax = __reduce_max_sync(0xffffffffu, bgmax);
             if (lane == 0 && bgmax >= 0) atomicMax(&vs.winner[compat_bg - 1], bgmax);
+        }
+    }
+
+    if (MODE == GG_RM_GATHER) {
+        // Fused render_flat (meshes.py:1921-1937): every pixel takes the texture row of its face, NaN where no face
+        // was hit; the face-ID raster itself need not be written.
+        const int D = dense.D;
+        T *out = reinterpret_cast<T *>(dense.out);
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        if (row_ok && col < W) {
+            const int64_t o = ((int64_t)view * H + row) * W + col;
+            if (D == 1 && sizeof(T) == 1 && col + 7 < W && ((o & 7) == 0)) {
+                unsigned lo = 0, hi = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned b = (unsigned)gather_convert<uint8_t>(bf[i] >= 0 ? dense.tex[bf[i]] : nan);
+                    if (i < 4) lo |= b << (8 * i);
+                    else hi |= b << (8 * (i - 4));
+                }
+                *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(dense.out) + o) = make_uint2(lo, hi);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (col + i < W) {
+                        for (int d = 0; d < D; ++d)
+                            out[(o + i) * D + d] = gather_convert<T>(bf[i] >= 0 ? dense.tex[(int64_t)bf[i] * D + d] : nan);
+                    }
+                }
+            }
         }
     }
 
@@ -985,7 +1036,8 @@ int gg_pipeline_drain(gg_context *ctx, cudaStream_t st) {
 
 int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *d_pix2face, float *d_depth,
                         int want_winners, int compat_bg, cudaStream_t st_bin, cudaStream_t st_ras,
-                        const void *const *h_pred, int pred_kind, int C, double *d_sum, int32_t *d_count) {
+                        const void *const *h_pred, int pred_kind, int C, double *d_sum, int32_t *d_count,
+                        const double *d_tex, int D, void *d_out, int out_dtype) {
     const int W = cams[0].W, H = cams[0].H;
     int rc = gg_ensure_scratch(ctx, n, W, H);
     if (rc != GG_OK) return rc;
@@ -1045,6 +1097,27 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
             case GG_PRED_INDEX_U8: return launch_dense<uint8_t>(ctx, cb, rgrid, n_tiles, d_pix2face, da, st);
             default: gg_set_error("bad pred_kind"); return GG_ERR_INVALID;
         }
+    }
+    if (d_tex) {  // fused render_flat
+        da.tex = d_tex;
+        da.out = d_out;
+        da.D = D;
+        switch (out_dtype) {
+            case GG_OUT_F64:
+                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, double, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
+                                                     cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da)));
+                break;
+            case GG_OUT_F32:
+                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
+                                                     cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da)));
+                break;
+            case GG_OUT_U8:
+                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, uint8_t, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
+                                                     cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da)));
+                break;
+            default: gg_set_error("bad out_dtype"); return GG_ERR_INVALID;
+        }
+        return GG_OK;
     }
     if (want_winners)
         GG_LAUNCH(ctx, GG_ST_RASTER, st,

@@ -159,6 +159,11 @@ int gg_finalize(gg_context *ctx, double *d_sum, const int32_t *d_count, int64_t 
 int gg_render_flat(gg_context *ctx, const int32_t *d_pix2face, int64_t n_pixels, const double *d_face_tex,
                    int D, void *d_out, int out_dtype, void *stream);
 
+/* ---- stage 1+2+4 fused: rasterize n views and write the rendered face texture directly (render_flat,
+        meshes.py:1858-1942); d_out: n x H x W x D of out_dtype; d_pix2face (n x H x W int32) may be NULL. ---------- */
+int gg_rasterize_render_flat(gg_context *ctx, const gg_camera *h_cams, int n, const double *d_face_tex, int D,
+                             void *d_out, int out_dtype, int32_t *d_pix2face, void *stream);
+
 /* ---- lens distortion: Metashape frame-camera model of MetashapeCameraSet.ideal_to_warped
         (cameras/derived_cameras.py:163-208).  f, cx, cy, W, H are the FULL-resolution intrinsics; image_scale the
         render scale of the rasters being warped (cameras.py:1027-1053). ---------------------------------------- */
