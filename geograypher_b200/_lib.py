@@ -29,7 +29,7 @@ EXPORTS = [
     "gg_last_batch_stats", "gg_set_mesh", "gg_project", "gg_rasterize", "gg_aggregate",
     "gg_project_aggregate", "gg_finalize", "gg_render_flat", "gg_stage_count", "gg_stage_name", "gg_profile",
     "gg_profile_read", "gg_drain", "gg_set_pipeline", "gg_build_warp_map", "gg_gather_i32",
-    "gg_label_polygons", "gg_get_capacity",
+    "gg_label_polygons", "gg_get_capacity", "gg_rasterize_render_flat",
 ]
 
 
@@ -100,6 +100,7 @@ def load():
     lib.gg_project_aggregate.argtypes = [vp, camp, i32, ctypes.POINTER(vp), i32, i32, i32, i32, vp, vp, vp, vp]
     lib.gg_finalize.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
     lib.gg_render_flat.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp]
+    lib.gg_rasterize_render_flat.argtypes = [vp, camp, i32, vp, i32, vp, i32, vp, vp]
     lib.gg_stage_name.argtypes = [i32]
     lib.gg_stage_name.restype = ctypes.c_char_p
     lib.gg_drain.argtypes = [vp, vp]
@@ -381,6 +382,30 @@ class Context:
                                     avg.data_ptr() if avg is not None else None,
                                     argmax.data_ptr() if argmax is not None else None, _stream_ptr(stream)))
         return avg, argmax
+
+    def rasterize_render_flat(self, cams, face_tex64, out_dtype=OUT_F64, out=None, pix2face_out=None, stream=None,
+                              check=True):
+        """Fused pix2face + render_flat gather for up to 32 same-size views: (n, H, W, D) CUDA tensor."""
+        t, n = self.torch, len(cams)
+        H, W, D = cams[0].H, cams[0].W, int(face_tex64.shape[1])
+        dt = {OUT_F64: t.float64, OUT_F32: t.float32, OUT_U8: t.uint8}[out_dtype]
+        if out is None:
+            out = t.empty((n, H, W, D), dtype=dt, device=self._dev())
+        for attempt in range(4):
+            _check(self.lib.gg_rasterize_render_flat(self.handle, self._cam_array(cams), n, face_tex64.data_ptr(), D,
+                                                     out.data_ptr(), out_dtype,
+                                                     pix2face_out.data_ptr() if pix2face_out is not None else None,
+                                                     _stream_ptr(stream)))
+            if not check:
+                break
+            try:
+                self.sync(stream)
+                break
+            except GeograypherB200Error as e:
+                if e.code != ERR_OVERFLOW or attempt == 3:
+                    raise
+                self._grow_after_overflow(n)
+        return out
 
     # -- stage 4 -------------------------------------------------------------------------------------------
     def render_flat(self, pix2face, face_tex64, out_dtype=OUT_F64, out=None, stream=None):

@@ -438,9 +438,8 @@ class TexturedPhotogrammetryMesh:
         code = {"float64": _lib.OUT_F64, "float32": _lib.OUT_F32, "uint8": _lib.OUT_U8}[out_dtype]
         gg = self._gg_cameras(cam_list, mesh, render_img_scale)
         B = self.views_per_batch if batch_size is None else max(1, min(batch_size, _lib.MAX_VIEWS_PER_CALL))
-        for s in range(0, len(gg), B):
-            p2f = mesh.context.rasterize(gg[s : s + B])
-            yield mesh.context.render_flat(p2f, tex, out_dtype=code)
+        for s in range(0, len(gg), B):  # fused: the face-ID rasters are never written
+            yield mesh.context.rasterize_render_flat(gg[s : s + B], tex, out_dtype=code)
 
     def render_flat(self, cameras, batch_size: int = 1, render_img_scale: float = 1, return_camera: bool = False,
                     **pix2face_kwargs):

@@ -34,7 +34,15 @@ if "c4" in sys.argv:
     step(0); ctx.sync()
     ms = timeit(step, 8)
     ctx.sync()
-    print(f"c4 render_flat -> uint8: {ms/B*1e3:.1f} us/view, {B/ms*1e3:.0f} views/s; labelled px frac {(out>0).float().mean().item():.3f}")
+    ref = out.clone()
+    print(f"c4 render_flat -> uint8 (two kernels): {ms/B*1e3:.1f} us/view, {B/ms*1e3:.0f} views/s; labelled px frac {(out>0).float().mean().item():.3f}")
+    def fused(i):
+        ctx.rasterize_render_flat(cams[(i % 4) * B:(i % 4) * B + B], tex, out_dtype=_lib.OUT_U8, out=out, check=False)
+    fused(7); ctx.sync()
+    assert torch.equal(out, ref)
+    ms = timeit(fused, 8)
+    ctx.sync()
+    print(f"c4 render_flat -> uint8 (fused): {ms/B*1e3:.1f} us/view, {B/ms*1e3:.0f} views/s")
 
 if "c5" in sys.argv:
     verts, faces, cfg, ctx, cams = build("c5", 40)
