@@ -2,6 +2,9 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+
 #include "gg_internal.cuh"
 
 static thread_local std::string g_last_error;
@@ -24,7 +27,120 @@ __global__ void k_pack_mesh(const float *__restrict__ v, int64_t V, const int32_
         f4[i] = make_int4(a, b, c, (int)i);
     }
 }
+// ---- spatial ordering of the faces (Morton order of the centroids) -----------------------------------------
+// The frustum culling works on blocks of 128 consecutive faces; sorting the faces along a Z-order curve makes those
+// blocks compact whatever order the mesh file had.  Face IDs travel with the faces (int4.w), so results are unchanged.
+__device__ __forceinline__ unsigned spread_bits10(unsigned v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__global__ void k_vertex_bounds_init(float *lohi) {
+    if (threadIdx.x < 3) {
+        lohi[threadIdx.x] = INFINITY;
+        lohi[3 + threadIdx.x] = -INFINITY;
+    }
+}
+
+__device__ __forceinline__ void atomic_min_float(float *addr, float v) {  // valid for any sign
+    if (v >= 0) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned *>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+    if (v >= 0) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned *>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(256) k_vertex_bounds(const float4 *__restrict__ v4, int64_t V, float *lohi) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = v4[i];
+        if (isfinite(v.x) && isfinite(v.y) && isfinite(v.z)) {
+            mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
+            mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
+            mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (mn[k] < INFINITY) atomic_min_float(&lohi[k], mn[k]);
+            if (mx[k] > -INFINITY) atomic_max_float(&lohi[3 + k], mx[k]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_morton_codes(const float4 *__restrict__ v4, const int4 *__restrict__ f4, int64_t F,
+                                                      const float *__restrict__ lohi, unsigned *__restrict__ codes,
+                                                      int *__restrict__ order) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F) return;
+    const int4 f = f4[i];
+    const float4 a = v4[f.x], b = v4[f.y], c = v4[f.z];
+    const float cen[3] = {(a.x + b.x + c.x) * (1.f / 3.f), (a.y + b.y + c.y) * (1.f / 3.f), (a.z + b.z + c.z) * (1.f / 3.f)};
+    unsigned code = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float ext = lohi[3 + k] - lohi[k];
+        float t = ext > 0.f ? (cen[k] - lohi[k]) / ext : 0.f;
+        t = isfinite(t) ? fminf(fmaxf(t, 0.f), 1.f) : 0.f;
+        code |= spread_bits10((unsigned)(t * 1023.f)) << k;
+    }
+    codes[i] = code;
+    order[i] = (int)i;
+}
+
+__global__ void __launch_bounds__(256) k_permute_faces(const int4 *__restrict__ in, const int *__restrict__ order, int64_t F,
+                                                       int4 *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F) out[i] = in[order[i]];
+}
 }  // namespace
+
+static int sort_faces_spatially(gg_context *ctx, cudaStream_t st) {
+    const int64_t F = ctx->F, V = ctx->V;
+    if (F < 2 * GG_BLOCK_FACES || V == 0) return GG_OK;  // a single cull block: nothing to gain
+    float *d_lohi = nullptr;
+    unsigned *d_codes = nullptr, *d_codes_out = nullptr;
+    int *d_order = nullptr, *d_order_out = nullptr;
+    int4 *d_sorted = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    GG_CUDA(cudaMalloc(&d_lohi, 6 * sizeof(float)));
+    GG_CUDA(cudaMalloc(&d_codes, (size_t)F * 4));
+    GG_CUDA(cudaMalloc(&d_codes_out, (size_t)F * 4));
+    GG_CUDA(cudaMalloc(&d_order, (size_t)F * 4));
+    GG_CUDA(cudaMalloc(&d_order_out, (size_t)F * 4));
+    GG_CUDA(cudaMalloc(&d_sorted, (size_t)F * sizeof(int4)));
+    k_vertex_bounds_init<<<1, 32, 0, st>>>(d_lohi);
+    k_vertex_bounds<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->d_verts, V, d_lohi);
+    k_morton_codes<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(ctx->d_verts, ctx->d_faces, F, d_lohi, d_codes, d_order);
+    GG_CUDA(cudaGetLastError());
+    GG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_codes, d_codes_out, d_order, d_order_out, (int)F, 0, 30, st));
+    GG_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
+    GG_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_codes, d_codes_out, d_order, d_order_out, (int)F, 0, 30, st));
+    k_permute_faces<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(ctx->d_faces, d_order_out, F, d_sorted);
+    GG_CUDA(cudaGetLastError());
+    GG_CUDA(cudaStreamSynchronize(st));
+    cudaFree(ctx->d_faces);
+    ctx->d_faces = d_sorted;
+    cudaFree(d_lohi);
+    cudaFree(d_codes);
+    cudaFree(d_codes_out);
+    cudaFree(d_order);
+    cudaFree(d_order_out);
+    cudaFree(d_tmp);
+    return GG_OK;
+}
 
 static int check_ctx(gg_context *ctx, bool need_mesh) {
     if (!ctx) {
@@ -290,6 +406,8 @@ int gg_set_mesh(gg_context *ctx, const float *d_verts, int64_t V, const int32_t 
     }
     ctx->V = V;
     ctx->F = F;
+    rc = sort_faces_spatially(ctx, st);
+    if (rc != GG_OK) return rc;
     rc = gg_launch_mesh_blocks(ctx, st);
     if (rc != GG_OK) return rc;
     GG_CUDA(cudaStreamSynchronize(st));
