@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 
@@ -200,6 +201,7 @@ int gg_create(int device, gg_context **out) {
     GG_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     memset(ctx->vset, 0, sizeof(ctx->vset));
+    if (const char *e = getenv("GG_DENSE_PREFETCH")) ctx->dense_prefetch = atoi(e) != 0;
     GG_CUDA(cudaMalloc(&ctx->d_sticky, sizeof(int32_t)));
     GG_CUDA(cudaMemset(ctx->d_sticky, 0, sizeof(int32_t)));
     // the short, latency-bound binning kernels get the higher priority so that they slip in between the CTAs of the

@@ -107,6 +107,7 @@ struct gg_context {
     int64_t V = 0, F = 0;
     float4 *d_verts = nullptr;   // [V] xyz + pad
     int4 *d_faces = nullptr;     // [F] i0,i1,i2,face_id
+    int dense_prefetch = 1;      // GG_MODE_PIXEL_SUM: L2 prefetch of the score tiles (GG_DENSE_PREFETCH=0 turns it off)
     float *d_block_lo = nullptr; // [n_blocks*3]
     float *d_block_hi = nullptr; // [n_blocks*3]
     int64_t n_blocks = 0;

@@ -559,6 +559,7 @@ __device__ __noinline__ bool exact_cover(const GGFaceRec &r, int j, int i, float
 #define GG_RM_PLAIN 0
 #define GG_RM_WINNERS 1
 #define GG_RM_DENSE 2
+#define GG_DENSE_ACC_FLOATS (GG_CHUNK * 32 + 64)  // per warp: slots of the list positions + one scratch row
 #define GG_RM_GATHER 3  // fused render_flat: out[p, :] = tex[face, :] (T = output element type)
 
 struct GGDenseArgs {
@@ -567,6 +568,8 @@ struct GGDenseArgs {
     int32_t *count;  // [F]
     int C;
     int index_kind;  // 1: (H,W) uint8 class index expanded on the fly
+    int vec_ok;      // every image base and row start is 16-byte aligned: two channels per load
+    int l2_prefetch; // ... and so is every tile row: bulk L2 prefetch of the tile's scores ahead of the epilogue
     // GG_RM_GATHER
     const double *tex;  // [F][D]
     void *out;          // [n][H][W][D]
@@ -636,6 +639,17 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
     const bool overflow = vs.counters[3] != 0;
     const int beg = vs.tile_offset[tile];
     const int len = overflow ? 0 : vs.tile_count[tile];
+
+    if (MODE == GG_RM_DENSE) {
+        // The epilogue will stream this tile's scores: ask for them now (one bulk L2 prefetch per tile row, issued by
+        // one lane each) so that they travel from HBM while the faces are rasterized.
+        const int C = CT > 0 ? CT : dense.C;
+        if (dense.l2_prefetch && len > 0 && W - tile_x0 >= GG_TILE_W && lane < min(GG_TILE_H, H - tile_y0)) {
+            const T *src = (const T *)dense.preds.p[view] + ((int64_t)(tile_y0 + lane) * W + tile_x0) * C;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(GG_TILE_W * C * sizeof(T)))
+                         : "memory");
+        }
+    }
 
     for (int base = 0; base < len; base += GG_CHUNK) {
         const int n = min(GG_CHUNK, len - base);
@@ -787,17 +801,22 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
 
     if (MODE == GG_RM_DENSE) {
         // Per-pixel scatter-add of the view's (H, W, C) scores into per-face sums; the raster never leaves the SM.
-        // The lanes are re-mapped from "8 pixels each" to (pixel group, channel): g = 32 / C pixels are read per
-        // step and lane l reads float  step * g*C + l  of the tile row, so every load instruction covers g*C*4
-        // contiguous bytes and a lane's channel never changes.  A lane sums in a register while the winning face
-        // stays the same and spills into its PRIVATE shared-memory slot s_acc[list position][lane] when it changes
-        // (no shared-memory atomics: float atomicAdd on shared memory is a CAS loop).  The tile then issues one
-        // float64 atomicAdd per (face, channel).
+        // The lanes are re-mapped from "8 pixels each" to (pixel group, channel block): a lane owns V consecutive
+        // channels (V = 2 when C is even and the rows are aligned, else 1) of every g-th pixel, g = 32 / (C / V), so
+        // every load instruction covers g*C contiguous elements of the tile row and a lane's channels never change.
+        // A lane sums in registers while the winning face stays the same and spills into its PRIVATE shared-memory
+        // slots s_acc[list position][lane*V + j] when it changes (no shared-memory float atomics: they are CAS
+        // loops).  The fast path adds the raw values; a null (NaN) or infinite score shows up in the tile's totals
+        // and sends the (rare) tile through the filtering loop instead.  The tile then issues one float64 atomicAdd
+        // per (face, channel).
         extern __shared__ float s_dyn[];
+        constexpr int V = (CT > 0 && CT % 2 == 0 && sizeof(T) * 2 <= 16) ? 2 : 1;  // channels per lane and load
+        constexpr int kSlots = 32 * V;              // accumulator slots per list position
+        constexpr int kPosCap = GG_CHUNK / V;       // list positions that have slots; later ones use direct atomics
         __shared__ unsigned char s_pos_all[GG_RASTER_WARPS][GG_TILE_W * GG_TILE_H];
         __shared__ int s_cnt_all[GG_RASTER_WARPS][GG_CHUNK];
         const int C = CT > 0 ? CT : dense.C;  // CT > 0: channel count known at compile time (fully unrolled rows)
-        float *s_acc = s_dyn + warp * (GG_CHUNK * 32);
+        float *s_acc = s_dyn + warp * GG_DENSE_ACC_FLOATS;
         unsigned char *s_pos = s_pos_all[warp];
         int *s_cnt = s_cnt_all[warp];
         const T *__restrict__ pred = (const T *)dense.preds.p[view];
@@ -805,14 +824,14 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
             unsigned lo = 0, hi = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const unsigned b = bp[i] < 0 ? 255u : (bp[i] < GG_CHUNK ? (unsigned)bp[i] : 254u);
+                const unsigned b = (bp[i] >= 0 && bp[i] < kPosCap) ? (unsigned)bp[i] : (unsigned)kPosCap;  // no slot
                 if (i < 4) lo |= b << (8 * i);
                 else hi |= b << (8 * (i - 4));
             }
             *reinterpret_cast<uint2 *>(&s_pos[ty * GG_TILE_W + tx0]) = make_uint2(lo, hi);
         }
-        const int nk = min(len, GG_CHUNK);
-        for (int i = lane; i < nk * 32; i += 32) s_acc[i] = 0.f;
+        const int nk = min(len, kPosCap);
+        for (int i = lane; i < nk * kSlots; i += 32) s_acc[i] = 0.f;
         s_cnt[lane] = 0;
         __syncwarp();
         {  // pixel counts per list position: integer shared-memory atomics are native, one per run of equal winners
@@ -820,7 +839,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const bool in_img = row_ok && (col + i < W);
-                if (in_img && bp[i] >= 0 && bp[i] < GG_CHUNK) {
+                if (in_img && bp[i] >= 0 && bp[i] < kPosCap) {
                     run += 1;
                     const bool last = (i == 7) || (bp[i + 1 < 8 ? i + 1 : 7] != bp[i]) || !(col + i + 1 < W);
                     if (last) {
@@ -830,54 +849,21 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                 }
             }
         }
-        const int g = 32 / C;                 // pixels per step (C <= 32 on this path)
-        const int gC = g * C;                 // floats per step
-        const int grp = lane / C, ch = lane - grp * C;
         const int cols = min(GG_TILE_W, W - tile_x0), rows = min(GG_TILE_H, H - tile_y0);
-        const int steps = (cols + g - 1) / g;
-        if (lane < gC && nk > 0) {
+        const bool index_kind = dense.index_kind != 0;
+
+        // -- general loop: any channel count <= 32, any tile width, class-index images, nulls filtered -----------
+        auto filtered_rows = [&]() {
+            const int g = 32 / C;   // pixels per step
+            const int gC = g * C;   // elements per step
+            const int grp = lane / C, ch = lane - grp * C;
+            const int steps = (cols + g - 1) / g;
+            if (lane >= gC) return;
             float acc = 0.f;
-            unsigned cur = 255u;
-            const bool index_kind = dense.index_kind != 0;
+            unsigned cur = (unsigned)kPosCap;
             const int stride = index_kind ? g : gC;     // elements per step
             const int first = index_kind ? grp : lane;  // this lane's element in step 0
-            auto to_score = [&](T raw) -> float {
-                if (index_kind) return ((int)raw == ch) ? 1.f : 0.f;
-                const float v = (float)raw;
-                return v == v ? v : 0.f;  // NaN = null -> contributes nothing
-            };
-            auto consume = [&](unsigned pp, float v) {
-                if (pp != cur) {
-                    if (cur < (unsigned)GG_CHUNK) s_acc[cur * 32 + lane] += acc;
-                    acc = 0.f;
-                    cur = pp;
-                }
-                acc += v;
-            };
             const int last = (index_kind ? cols : cols * C) - 1;  // last element of the tile row
-            if (CT > 0 && cols == GG_TILE_W) {
-                // Compile-time channel count and a full-width tile: the whole row (kSteps loads per lane) is issued
-                // from one base pointer with immediate offsets before anything is consumed.
-                constexpr int kG = CT > 0 ? 32 / CT : 1, kGC = kG * (CT > 0 ? CT : 1);
-                constexpr int kSteps = (GG_TILE_W + kG - 1) / kG;
-                for (int r = 0; r < rows; ++r) {
-                    const int64_t pix0 = (int64_t)(tile_y0 + r) * W + tile_x0;
-                    const T *__restrict__ lp = pred + (index_kind ? pix0 + grp : pix0 * CT + lane);
-                    const unsigned char *q = s_pos + r * GG_TILE_W + grp;
-                    const int kStride = index_kind ? kG : kGC;
-                    T raw[kSteps];
-#pragma unroll
-                    for (int u = 0; u < kSteps; ++u) {
-                        const bool in_row = (u + 1) * kG <= GG_TILE_W || u * kG + grp < GG_TILE_W;
-                        raw[u] = in_row ? lp[u * kStride] : (T)0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < kSteps; ++u) {
-                        const bool in_row = (u + 1) * kG <= GG_TILE_W || u * kG + grp < GG_TILE_W;
-                        if (in_row) consume(q[u * kG], to_score(raw[u]));
-                    }
-                }
-            } else
             for (int r = 0; r < rows; ++r) {
                 const int64_t pix0 = (int64_t)(tile_y0 + r) * W + tile_x0;
                 const T *__restrict__ rp = pred + (index_kind ? pix0 : pix0 * C);
@@ -892,31 +878,108 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                     for (int u = 0; u < 4; ++u) {
                         const int x = (j0 + u) * g + grp;
                         const unsigned pp = prow[min(x, GG_TILE_W - 1)];
-                        ps[u] = x < cols ? pp : 255u;
+                        ps[u] = x < cols ? pp : (unsigned)kPosCap;
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) consume(ps[u], ps[u] == 255u ? 0.f : to_score(raw[u]));
+                    for (int u = 0; u < 4; ++u) {
+                        float v;
+                        if (index_kind) v = ((int)raw[u] == ch) ? 1.f : 0.f;
+                        else {
+                            v = (float)raw[u];
+                            v = v == v ? v : 0.f;  // NaN = null -> contributes nothing
+                        }
+                        if (ps[u] != cur) {
+                            if (cur < (unsigned)kPosCap) s_acc[cur * kSlots + lane] += acc;
+                            acc = 0.f;
+                            cur = ps[u];
+                        }
+                        acc += v;
+                    }
                 }
             }
-            if (cur < (unsigned)GG_CHUNK) s_acc[cur * 32 + lane] += acc;
+            if (cur < (unsigned)kPosCap) s_acc[cur * kSlots + lane] += acc;
+        };
+
+        bool fast = false;
+        if (CT > 0) fast = cols == GG_TILE_W && nk > 0 && (V == 1 || dense.vec_ok);
+        if (CT > 0 && fast) {
+            // Compile-time channel count and a full-width tile: the whole row (kSteps loads per lane) is issued from
+            // one base pointer with immediate offsets, then every value is added, unfiltered, straight into the
+            // lane's private slot of its pixel's list position (pixels without a slot go to a scratch row): no state
+            // is carried from pixel to pixel, so lanes never diverge.
+            constexpr int kC = CT > 0 ? CT : 1;
+            constexpr int kLP = kC / V;                 // lanes per pixel
+            constexpr int kG = 32 / kLP;                // pixels per step
+            constexpr int kSteps = (GG_TILE_W + kG - 1) / kG;
+            struct alignas(sizeof(T) * V) Vec {
+                T v[V];
+            };
+            struct alignas(sizeof(float) * V) Acc {
+                float v[V];
+            };
+            const int grp = lane / kLP;
+            if (lane < kG * kLP) {
+                const Vec *__restrict__ lp = reinterpret_cast<const Vec *>(pred + ((int64_t)tile_y0 * W + tile_x0) * kC) + lane;
+                const int64_t row_stride = (int64_t)W * kLP;  // in Vec units
+                const unsigned char *q = s_pos + grp;
+                Acc *slot = reinterpret_cast<Acc *>(s_acc) + lane;
+                for (int r = 0; r < rows; ++r, lp += row_stride, q += GG_TILE_W) {
+                    Vec raw[kSteps];
+#pragma unroll
+                    for (int u = 0; u < kSteps; ++u) {
+                        const bool in_row = (u + 1) * kG <= GG_TILE_W || u * kG + grp < GG_TILE_W;
+                        if (in_row) raw[u] = lp[u * (kG * kLP)];
+                    }
+#pragma unroll
+                    for (int u = 0; u < kSteps; ++u) {
+                        const bool in_row = (u + 1) * kG <= GG_TILE_W || u * kG + grp < GG_TILE_W;
+                        if (in_row) {
+                            Acc *a = slot + (unsigned)q[u * kG] * 32;  // kSlots floats per list position
+                            Acc t = *a;
+#pragma unroll
+                            for (int j = 0; j < V; ++j) t.v[j] += (float)raw[u].v[j];
+                            *a = t;
+                        }
+                    }
+                }
+            }
+        } else if (nk > 0) {
+            filtered_rows();
         }
         __syncwarp();
+        // slot of (pixel group q, channel c) is q*C + c on both paths; groups beyond a path's own are zero
+        const int g_all = kSlots / C;
+        if (CT > 0 && fast) {
+            bool dirty = false;
+            for (int idx = lane; idx < nk * C; idx += 32) {
+                const int k = idx / C, cch = idx - k * C;
+                float total = 0.f;
+                for (int q = 0; q < g_all; ++q) total += s_acc[k * kSlots + q * C + cch];
+                dirty |= !(fabsf(total) <= 3.0e38f);
+            }
+            if (__any_sync(0xffffffffu, dirty)) {  // a null or infinite score somewhere in this tile: do it again, filtered
+                for (int i = lane; i < nk * kSlots; i += 32) s_acc[i] = 0.f;
+                __syncwarp();
+                filtered_rows();
+                __syncwarp();
+            }
+        }
         for (int idx = lane; idx < nk * C; idx += 32) {
             const int k = idx / C, cch = idx - k * C;
             const int n_px = s_cnt[k];
             float total = 0.f;
-            for (int q = 0; q < g; ++q) total += s_acc[k * 32 + q * C + cch];
+            for (int q = 0; q < g_all; ++q) total += s_acc[k * kSlots + q * C + cch];
             if (n_px > 0) {
                 const int64_t face = len <= GG_CHUNK ? s_faces[k].face : vs.bins[beg + k].face;
                 atomicAdd(&dense.sum[face * C + cch], (double)total);
                 if (cch == 0) atomicAdd(&dense.count[face], n_px);
             }
         }
-        // list positions beyond the shared-memory table (tiles with more than GG_CHUNK faces): direct atomics
-        if (len > GG_CHUNK) {
+        // list positions beyond the shared-memory table (tiles with more than kPosCap faces): direct atomics
+        if (len > kPosCap) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (bp[i] >= GG_CHUNK && row_ok && col + i < W) {
+                if (bp[i] >= kPosCap && row_ok && col + i < W) {
                     const int64_t pix = (int64_t)row * W + col + i;
                     for (int cch = 0; cch < C; ++cch)
                         atomicAdd(&dense.sum[(int64_t)bf[i] * C + cch], (double)dense_load<T>(pred, pix, C, cch, dense.index_kind));
@@ -1001,7 +1064,7 @@ int gg_launch_project(gg_context *ctx, const gg_camera *cams, int n, int32_t *dX
 template <typename T>
 static int launch_dense(gg_context *ctx, const GGCamBatch &cb, dim3 rgrid, int n_tiles, int32_t *d_pix2face,
                         const GGDenseArgs &da, cudaStream_t st) {
-    const size_t dyn = (size_t)GG_RASTER_WARPS * GG_CHUNK * 32 * sizeof(float);
+    const size_t dyn = (size_t)GG_RASTER_WARPS * GG_DENSE_ACC_FLOATS * sizeof(float);
 #define GG_DENSE_CASE(CT)                                                                                             \
     case CT:                                                                                                          \
         GG_LAUNCH(ctx, GG_ST_RASTER, st,                                                                              \
@@ -1090,6 +1153,10 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
         da.count = d_count;
         da.C = C;
         da.index_kind = pred_kind == GG_PRED_INDEX_U8;
+        da.vec_ok = 1;
+        for (int i = 0; i < n; ++i) da.vec_ok &= ((uintptr_t)h_pred[i] % 16) == 0;
+        const size_t elem = pred_kind == GG_PRED_F64 ? 8 : (pred_kind == GG_PRED_F32 ? 4 : 1);
+        da.l2_prefetch = ctx->dense_prefetch && da.vec_ok && !da.index_kind && ((size_t)W * C * elem) % 16 == 0;
         switch (pred_kind) {
             case GG_PRED_F32: return launch_dense<float>(ctx, cb, rgrid, n_tiles, d_pix2face, da, st);
             case GG_PRED_F64: return launch_dense<double>(ctx, cb, rgrid, n_tiles, d_pix2face, da, st);

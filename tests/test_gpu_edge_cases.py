@@ -217,3 +217,39 @@ def test_face_order_does_not_matter(torch, lib):
             ref = ora.rasterize(v32, fc, c)
             np.testing.assert_array_equal(p2f[i], ref)
     assert blocks["shuffled"] <= 1.25 * blocks["ordered"] + 8
+
+
+@pytest.mark.parametrize("kind,C", [("f32", 3), ("f32", 10), ("f32", 16), ("f64", 4), ("f64", 8), ("u8", 10), ("u8", 5)])
+def test_dense_mode_vector_path(torch, lib, kind, C):
+    """GG_MODE_PIXEL_SUM on the two-channels-per-load path (even channel counts, aligned images): image rows are
+    aligned here, the image has partial tiles on the right (general loop) and at the bottom (fewer rows), a block
+    of null scores sends some tiles through the filtering loop, and every element type is covered."""
+    verts, faces, c2ws, cfg = syn.make_survey("tiny")
+    origin = 0.5 * (verts.min(0) + verts.max(0))
+    v32 = (verts - origin).astype(np.float32)
+    W, H = 208, 117
+    cams = [ora.make_camera(T, cfg.f * 1.3, cfg.cx, cfg.cy, W, H, origin=origin) for T in c2ws[:3]]
+    ctx = _ctx(torch, lib, v32, faces)
+    gg_c = [_gg(lib, c) for c in cams]
+    p2f = ctx.rasterize(gg_c).cpu().numpy()
+    rng = np.random.default_rng(C)
+    np_dtype, pred_kind = {"f32": (np.float32, lib.PRED_F32), "f64": (np.float64, lib.PRED_F64), "u8": (np.uint8, lib.PRED_U8)}[kind]
+    if kind == "u8":
+        host = [rng.integers(0, 256, size=(H, W, C), dtype=np.uint8) for _ in cams]
+    else:
+        host = [rng.random((H, W, C)).astype(np_dtype) for _ in cams]
+        host[1][5:40, 3:70, :] = np.nan  # nulls contribute nothing
+    F = len(faces)
+    d_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda")
+    d_count = torch.zeros((F,), dtype=torch.int32, device="cuda")
+    ctx.project_aggregate(gg_c, [torch.from_numpy(h).cuda() for h in host], pred_kind, C, lib.MODE_PIXEL_SUM, 0, d_sum, d_count)
+    ref = np.zeros((F, C))
+    cnt = np.zeros(F, dtype=np.int64)
+    for k in range(len(cams)):
+        ids = p2f[k].ravel()
+        keep = ids >= 0
+        np.add.at(ref, ids[keep], np.nan_to_num(host[k].reshape(-1, C)[keep].astype(np.float32).astype(np.float64)))
+        np.add.at(cnt, ids[keep], 1)
+    np.testing.assert_array_equal(d_count.cpu().numpy(), cnt)
+    np.testing.assert_allclose(d_sum.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    assert (cnt > 0).sum() > 100
