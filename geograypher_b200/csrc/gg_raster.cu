@@ -849,6 +849,19 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                 }
             }
         }
+        // list positions beyond the shared-memory table (tiles with more than kPosCap faces): direct atomics
+        // (done first: the winners in bf / bp are not needed after this and their registers are free for the loads)
+        if (len > kPosCap) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (bp[i] >= kPosCap && row_ok && col + i < W) {
+                    const int64_t pix = (int64_t)row * W + col + i;
+                    for (int cch = 0; cch < C; ++cch)
+                        atomicAdd(&dense.sum[(int64_t)bf[i] * C + cch], (double)dense_load<T>(pred, pix, C, cch, dense.index_kind));
+                    atomicAdd(&dense.count[bf[i]], 1);
+                }
+            }
+        }
         const int cols = min(GG_TILE_W, W - tile_x0), rows = min(GG_TILE_H, H - tile_y0);
         const bool index_kind = dense.index_kind != 0;
 
@@ -923,23 +936,37 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                 const int64_t row_stride = (int64_t)W * kLP;  // in Vec units
                 const unsigned char *q = s_pos + grp;
                 Acc *slot = reinterpret_cast<Acc *>(s_acc) + lane;
-                for (int r = 0; r < rows; ++r, lp += row_stride, q += GG_TILE_W) {
-                    Vec raw[kSteps];
+                auto load_row = [&](Vec(&raw)[kSteps], int r) {
+                    const Vec *__restrict__ rp = lp + r * row_stride;
 #pragma unroll
                     for (int u = 0; u < kSteps; ++u) {
                         const bool in_row = (u + 1) * kG <= GG_TILE_W || u * kG + grp < GG_TILE_W;
-                        if (in_row) raw[u] = lp[u * (kG * kLP)];
+                        if (in_row) raw[u] = rp[u * (kG * kLP)];
                     }
+                };
+                auto add_row = [&](const Vec(&raw)[kSteps], int r) {
+                    const unsigned char *qr = q + r * GG_TILE_W;
 #pragma unroll
                     for (int u = 0; u < kSteps; ++u) {
                         const bool in_row = (u + 1) * kG <= GG_TILE_W || u * kG + grp < GG_TILE_W;
                         if (in_row) {
-                            Acc *a = slot + (unsigned)q[u * kG] * 32;  // kSlots floats per list position
+                            Acc *a = slot + (unsigned)qr[u * kG] * 32;  // kSlots floats per list position
                             Acc t = *a;
 #pragma unroll
                             for (int j = 0; j < V; ++j) t.v[j] += (float)raw[u].v[j];
                             *a = t;
                         }
+                    }
+                };
+                // two rows in flight: the loads of the next row are issued before the current one is added
+                Vec rawA[kSteps], rawB[kSteps];
+                load_row(rawA, 0);
+                for (int r = 0; r < rows; r += 2) {
+                    if (r + 1 < rows) load_row(rawB, r + 1);
+                    add_row(rawA, r);
+                    if (r + 1 < rows) {
+                        if (r + 2 < rows) load_row(rawA, r + 2);
+                        add_row(rawB, r + 1);
                     }
                 }
             }
@@ -973,18 +1000,6 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                 const int64_t face = len <= GG_CHUNK ? s_faces[k].face : vs.bins[beg + k].face;
                 atomicAdd(&dense.sum[face * C + cch], (double)total);
                 if (cch == 0) atomicAdd(&dense.count[face], n_px);
-            }
-        }
-        // list positions beyond the shared-memory table (tiles with more than kPosCap faces): direct atomics
-        if (len > kPosCap) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (bp[i] >= kPosCap && row_ok && col + i < W) {
-                    const int64_t pix = (int64_t)row * W + col + i;
-                    for (int cch = 0; cch < C; ++cch)
-                        atomicAdd(&dense.sum[(int64_t)bf[i] * C + cch], (double)dense_load<T>(pred, pix, C, cch, dense.index_kind));
-                    atomicAdd(&dense.count[bf[i]], 1);
-                }
             }
         }
     }
