@@ -462,7 +462,7 @@ def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, my_cams, dev, w
             "views": n_views * world, "seconds": dt,
             "api": "TexturedPhotogrammetryMesh.aggregate_projected_images(SegmentorPhotogrammetryCameraSet)",
             "note": ("float32 (H,W,C) score images stay in pinned HOST memory; last-pixel aggregation needs one row per "
-                     "visible face, which the resolve kernel reads over PCIe through unified addressing (h2d bytes = "
+                     "visible face, which a staging kernel fetches over PCIe through unified addressing, all rows of a batch in parallel (h2d bytes = "
                      "rows actually fetched, estimated from the per-face counts); the per-face float64 averages, sums "
                      "and counts are copied back at the end" if zero_copy else
                      "float32 (H,W,C) score images uploaded from host memory every view") +

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256) k_resolve_batch(const __grid_constant__ G
     const int n = n_recs + ((compat && vs.counters[5] < 0) ? 1 : 0);
     const bool keep_nan = (flags & GG_FLAG_KEEP_NAN) != 0;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        if (r < n_recs && vs.recs[r].dup) continue;  // second triangle of a clipped face: the first one speaks for it
         const int64_t f = r < n_recs ? (int64_t)vs.recs[r].face : F - 1;
         if (vs.winner[f] < 0) continue;
         bool earlier = false;
@@ -345,10 +346,95 @@ int gg_launch_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W
     return GG_OK;
 }
 
+// ---- prediction images in (pinned) HOST memory ------------------------------------------------------------------
+// The fused last-pixel / vote aggregation needs one row per visible face.  When the images were left in page-locked
+// host memory the rows are fetched over PCIe: first ALL of them, in parallel, into a device staging table (one thread
+// per element, so a warp's loads of one row share their sectors), then k_resolve_batch walks the views in order on
+// the staged copy.  The winners are re-pointed from pixel indices to staging rows in between.
+template <typename T>
+__global__ void __launch_bounds__(256) k_stage_rows(const __grid_constant__ GGViewBatch views, int n_views, int64_t F,
+                                                    const __grid_constant__ GGPredBatch preds, int E, int flags,
+                                                    T *__restrict__ stage, int64_t rows_per_view) {
+    for (int v = 0; v < n_views; ++v)
+        if (views.v[v].counters[3] != 0) return;
+    const int view = blockIdx.y;
+    const GGViewScratch &vs = views.v[view];
+    const int n_recs = vs.counters[1];
+    const bool compat = (flags & GG_FLAG_COMPAT_NEG) != 0;
+    const int n = n_recs + ((compat && vs.counters[5] < 0) ? 1 : 0);
+    const T *__restrict__ pred = (const T *)preds.p[view];
+    T *__restrict__ out = stage + (int64_t)view * rows_per_view * E;
+    const int64_t total = (int64_t)n * E;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / E), e = (int)(idx - (int64_t)r * E);
+        if (r < n_recs && vs.recs[r].dup) continue;
+        const int64_t f = r < n_recs ? (int64_t)vs.recs[r].face : F - 1;
+        const int p = vs.winner[f];
+        if (p < 0) continue;
+        out[(int64_t)r * E + e] = pred[(int64_t)p * E + e];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_stage_commit(const __grid_constant__ GGViewBatch views, int n_views, int64_t F,
+                                                      int flags) {
+    for (int v = 0; v < n_views; ++v)
+        if (views.v[v].counters[3] != 0) return;
+    const GGViewScratch &vs = views.v[blockIdx.y];
+    const int n_recs = vs.counters[1];
+    const bool compat = (flags & GG_FLAG_COMPAT_NEG) != 0;
+    const int n = n_recs + ((compat && vs.counters[5] < 0) ? 1 : 0);
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        if (r < n_recs && vs.recs[r].dup) continue;
+        const int64_t f = r < n_recs ? (int64_t)vs.recs[r].face : F - 1;
+        if (vs.winner[f] >= 0) vs.winner[f] = r;
+    }
+}
+
+template <typename T>
+static int stage_host_rows(gg_context *ctx, int n, GGPredBatch &pb, int E, int flags, cudaStream_t st) {
+    const int64_t rows_per_view = ctx->cap_recs + 1;
+    const size_t need = (size_t)n * rows_per_view * E * sizeof(T);
+    if (ctx->stage_bytes < need) {
+        if (ctx->d_stage) {
+            GG_CUDA(cudaDeviceSynchronize());
+            GG_CUDA(cudaFree(ctx->d_stage));
+            ctx->d_stage = nullptr;
+        }
+        GG_CUDA(cudaMalloc(&ctx->d_stage, need));
+        ctx->stage_bytes = need;
+    }
+    T *stage = (T *)ctx->d_stage;
+    const dim3 g((unsigned)(ctx->sm_count * 8), n);
+    GG_LAUNCH(ctx, GG_ST_RESOLVE, st,
+              k_stage_rows<T><<<g, 256, 0, st>>>(ctx->vset[ctx->cur], n, ctx->F, pb, E, flags, stage, rows_per_view));
+    GG_LAUNCH(ctx, GG_ST_RESOLVE, st,
+              k_stage_commit<<<dim3((unsigned)(ctx->sm_count * 2), n), 256, 0, st>>>(ctx->vset[ctx->cur], n, ctx->F, flags));
+    for (int i = 0; i < n; ++i) pb.p[i] = stage + (int64_t)i * rows_per_view * E;
+    return GG_OK;
+}
+
 int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, int pred_kind, int C, int mode, int flags,
                             double *d_sum, int32_t *d_count, cudaStream_t st) {
     GGPredBatch pb;
     for (int i = 0; i < GG_MAX_VIEWS_PER_CALL; ++i) pb.p[i] = i < n ? h_pred[i] : nullptr;
+    bool on_host = ctx->stage_host_rows != 0;
+    for (int i = 0; i < n && on_host; ++i) {
+        cudaPointerAttributes attr;
+        on_host = cudaPointerGetAttributes(&attr, h_pred[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    }
+    (void)cudaGetLastError();
+    if (on_host) {
+        const int E = (mode == GG_MODE_VOTE || pred_kind == GG_PRED_INDEX_U8) ? 1 : C;  // elements per pixel
+        int rc = GG_OK;
+        switch (pred_kind) {
+            case GG_PRED_F32: rc = stage_host_rows<float>(ctx, n, pb, E, flags, st); break;
+            case GG_PRED_F64: rc = stage_host_rows<double>(ctx, n, pb, E, flags, st); break;
+            case GG_PRED_U8:
+            case GG_PRED_INDEX_U8: rc = stage_host_rows<uint8_t>(ctx, n, pb, E, flags, st); break;
+            default: gg_set_error("gg_project_aggregate: bad pred_kind"); return GG_ERR_INVALID;
+        }
+        if (rc != GG_OK) return rc;
+    }
     const dim3 g((unsigned)(ctx->sm_count * 2), n);
     const int64_t F = ctx->F;
     switch (pred_kind) {

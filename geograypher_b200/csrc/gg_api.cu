@@ -202,6 +202,7 @@ int gg_create(int device, gg_context **out) {
     ctx->sm_count = prop.multiProcessorCount;
     memset(ctx->vset, 0, sizeof(ctx->vset));
     if (const char *e = getenv("GG_DENSE_PREFETCH")) ctx->dense_prefetch = atoi(e) != 0;
+    if (const char *e = getenv("GG_STAGE_HOST_ROWS")) ctx->stage_host_rows = atoi(e) != 0;
     GG_CUDA(cudaMalloc(&ctx->d_sticky, sizeof(int32_t)));
     GG_CUDA(cudaMemset(ctx->d_sticky, 0, sizeof(int32_t)));
     // the short, latency-bound binning kernels get the higher priority so that they slip in between the CTAs of the
@@ -232,6 +233,7 @@ void gg_destroy(gg_context *ctx) {
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_winner);
     cudaFree(ctx->d_wdense);
+    cudaFree(ctx->d_stage);
     cudaFree(ctx->d_sticky);
     cudaFree(ctx->d_raster);
     for (auto &p : ctx->prof.pending) {

@@ -34,7 +34,9 @@ struct __align__(16) GGFaceRec {  // one surviving face of one view, orientation
     uint16_t jmin, jmax, imin, imax;  // pixel-centre index range, clamped to the raster
     unsigned long long tmask;  // which tiles of the bounding box the triangle can touch (bit = row-major index in the
                                // box), or ~0 when the box has more than 64 tiles (the fill pass then re-tests)
-    int pad[6];                // one 128-byte line per record: written and read as 8 x 16 B
+    int dup;                   // 1: an earlier record of this view carries the same face (second triangle of a clipped
+                               // face): per-face passes over the records skip it
+    int pad[5];                // one 128-byte line per record: written and read as 8 x 16 B
 };
 static_assert(sizeof(GGFaceRec) == 128, "GGFaceRec layout");
 
@@ -131,6 +133,9 @@ struct gg_context {
     int64_t winner_cap = 0;
     int32_t *d_wdense = nullptr;  // [n_slots * F] per-view per-face winners of the fused aggregation
     int64_t wdense_cap = 0;
+    char *d_stage = nullptr;      // rows fetched from prediction images that live in host memory
+    size_t stage_bytes = 0;
+    int stage_host_rows = 1;      // GG_STAGE_HOST_ROWS=0: resolve reads the host images directly
     int32_t *d_raster = nullptr;  // internal n x H x W raster when the caller does not want pix2face back
     int64_t raster_cap = 0;
     int32_t *d_sticky = nullptr;  // OR of the overflow flags of every batch since the last gg_sync

@@ -383,11 +383,14 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__
                 n_tri = 2;
             }
         }
+        bool kept_before = false;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {  // every lane takes part in both rounds (warp-aggregated append)
             bool keep = false;
             GGFaceRec r;
             if (t < n_tri) keep = build_record(tri[t][0], tri[t][1], tri[t][2], face_id, c, r);
+            r.dup = kept_before ? 1 : 0;
+            kept_before = kept_before || keep;
             const int idx = warp_append(&vs.counters[1], keep);
             if (keep) {
                 if (idx < cap_recs) {

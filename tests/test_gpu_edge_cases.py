@@ -195,6 +195,25 @@ def test_near_plane_clipping(torch, lib, znear):
     assert crossing.sum() > 0
     if znear >= 0.75:
         assert np.isin(ref[ref >= 0], np.nonzero(crossing)[0]).sum() > 50
+    # a clipped face can become two triangles: it must still be aggregated (and counted) once, in every mode
+    C, F = 3, len(faces)
+    pred = np.random.default_rng(2).random((H, W, C)).astype(np.float32)
+    for mode in (lib.MODE_LAST_PIXEL, lib.MODE_PIXEL_SUM):
+        d_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda")
+        d_count = torch.zeros((F,), dtype=torch.int32, device="cuda")
+        ctx.project_aggregate([_gg(lib, cam)], [torch.from_numpy(pred).cuda()], lib.PRED_F32, C, mode, 0, d_sum, d_count)
+        ids = got.ravel()
+        keep = ids >= 0
+        if mode == lib.MODE_LAST_PIXEL:
+            want = ora.aggregate(got[None].astype(np.int64), [pred], F, compat_negative_index=False)
+            np.testing.assert_array_equal(d_count.cpu().numpy(), want[1].astype(np.int64))
+            np.testing.assert_array_equal(d_sum.cpu().numpy(), np.nan_to_num(want[2]))
+        else:
+            cnt = np.bincount(ids[keep], minlength=F)
+            ref_sum = np.zeros((F, C))
+            np.add.at(ref_sum, ids[keep], pred.reshape(-1, C)[keep].astype(np.float64))
+            np.testing.assert_array_equal(d_count.cpu().numpy(), cnt)
+            np.testing.assert_allclose(d_sum.cpu().numpy(), ref_sum, rtol=1e-5, atol=1e-5)
 
 
 def test_face_order_does_not_matter(torch, lib):
@@ -253,3 +272,38 @@ def test_dense_mode_vector_path(torch, lib, kind, C):
     np.testing.assert_array_equal(d_count.cpu().numpy(), cnt)
     np.testing.assert_allclose(d_sum.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
     assert (cnt > 0).sum() > 100
+
+
+@pytest.mark.parametrize("staging", ["1", "0"])
+def test_prediction_images_in_pinned_host_memory(torch, lib, staging, monkeypatch):
+    """Last-pixel / vote aggregation straight from page-locked host images (rows fetched over PCIe, staged on the
+    device or read in place) gives exactly what device-resident images give."""
+    monkeypatch.setenv("GG_STAGE_HOST_ROWS", staging)
+    v32, faces, cams = _scene()
+    H, W, C, F = cams[0].H, cams[0].W, 5, len(faces)
+    gg_c = [_gg(lib, c) for c in cams]
+    ctx = _ctx(torch, lib, v32, faces)
+    rng = np.random.default_rng(11)
+    soft = [rng.random((H, W, C)).astype(np.float32) for _ in cams]
+    soft[1][10:30, 20:90, 2] = np.nan
+    index = [syn.class_index_image(i, H, W, C, block=8, ignore_frac=0.1) for i in range(len(cams))]
+    votes = [rng.integers(0, C, size=(H, W)).astype(np.float32) for _ in cams]
+    votes[0][::7, ::3] = np.nan
+    cases = [(soft, lib.PRED_F32, lib.MODE_LAST_PIXEL, 0), (soft, lib.PRED_F32, lib.MODE_LAST_PIXEL, lib.FLAG_COMPAT_NEGATIVE_INDEX),
+             (index, lib.PRED_INDEX_U8, lib.MODE_LAST_PIXEL, 0), (votes, lib.PRED_F32, lib.MODE_VOTE, 0)]
+    for images, kind, mode, flags in cases:
+        out = []
+        for where in ("device", "host"):
+            if where == "device":
+                preds = [torch.from_numpy(a).cuda() for a in images]
+            else:
+                preds = [torch.from_numpy(a).pin_memory() for a in images]
+                assert all(p.is_pinned() for p in preds)
+            d_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda")
+            d_count = torch.zeros((F,), dtype=torch.int32, device="cuda")
+            ctx.project_aggregate(gg_c, preds, kind, C, mode, flags, d_sum, d_count)
+            ctx.sync()
+            out.append((d_sum.cpu().numpy(), d_count.cpu().numpy()))
+        np.testing.assert_array_equal(out[0][0], out[1][0])
+        np.testing.assert_array_equal(out[0][1], out[1][1])
+        assert out[0][1].sum() > 100
