@@ -610,15 +610,17 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                                                                        float *__restrict__ depth, int compat_bg,
                                                                        const __grid_constant__ GGDenseArgs dense) {
     constexpr bool WINNERS = (MODE == GG_RM_WINNERS);
-    const int view = blockIdx.y;
+    // grid: (groups of GG_RASTER_WARPS tiles along x, tile rows, views); one warp per tile
+    const int view = blockIdx.z;
     const gg_camera &c = cams.cam[view];
     const GGViewScratch &vs = views.v[view];
     const int W = c.W, H = c.H;
     const int tiles_x = (W + GG_TILE_W - 1) / GG_TILE_W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * GG_RASTER_WARPS + warp;
-    if (tile >= n_tiles) return;  // whole warp leaves; no block-level barriers below
-    const int tile_x0 = (tile % tiles_x) * GG_TILE_W, tile_y0 = (tile / tiles_x) * GG_TILE_H;
+    const int tile_x = blockIdx.x * GG_RASTER_WARPS + warp;
+    if (tile_x >= tiles_x) return;  // whole warp leaves; no block-level barriers below
+    const int tile = blockIdx.y * tiles_x + tile_x;
+    const int tile_x0 = tile_x * GG_TILE_W, tile_y0 = blockIdx.y * GG_TILE_H;
 
     __shared__ GGTileFace s_all[GG_RASTER_WARPS][GG_CHUNK];
     __shared__ int s_win_all[WINNERS ? GG_RASTER_WARPS : 1][GG_CHUNK];
@@ -657,12 +659,16 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
     for (int base = 0; base < len; base += GG_CHUNK) {
         const int n = min(GG_CHUNK, len - base);
         {  // stream n ready-made 64-byte setups into shared memory: 16 B per lane, 4 x (up to) 512 B per warp
-            const int4 *src = reinterpret_cast<const int4 *>(vs.bins + beg + base);
-            int4 *dst = reinterpret_cast<int4 *>(s_faces);
+            const int4 *src = reinterpret_cast<const int4 *>(vs.bins + beg + base) + lane;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(s_faces) + lane * 16;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int idx = q * 32 + lane;
-                if (idx < n * 4) dst[idx] = __ldg(src + idx);
+                if (q * 32 + lane < n * 4) {
+                    const int4 v = __ldg(src + q * 32);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + q * 512), "r"(v.x), "r"(v.y), "r"(v.z),
+                                 "r"(v.w)
+                                 : "memory");
+                }
             }
         }
         __syncwarp();
@@ -748,17 +754,32 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
         const int next_first = __shfl_down_sync(0xffffffffu, bp[0], 1);
         const bool has_next = (lane & 3) != 3;
         int bgmax = -1;
+        const int pix0 = row * W + col;
+        if (tile_x0 + GG_TILE_W <= W && tile_y0 + GG_TILE_H <= H) {  // tile entirely inside the image (warp-uniform)
+            const int after = has_next ? next_first : -2;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const bool in_img = row_ok && (col + i < W);
-            const int pix = row * W + col + i;
-            const int nxt = (i < 7) ? ((col + i + 1 < W) ? bp[i + 1] : -2) : ((has_next && col + 8 < W) ? next_first : -2);
-            if (in_img) {
+            for (int i = 0; i < 8; ++i) {
+                const int nxt = (i < 7) ? bp[i < 7 ? i + 1 : 7] : after;
                 if (bp[i] < 0) {
-                    bgmax = pix;  // pixel index grows with i
+                    bgmax = pix0 + i;  // pixel index grows with i
                 } else if (bp[i] != nxt) {
-                    if (bp[i] < GG_CHUNK) atomicMax(&s_win[bp[i]], pix);
-                    else atomicMax(&vs.winner[bf[i]], pix);
+                    if (bp[i] < GG_CHUNK) atomicMax(&s_win[bp[i]], pix0 + i);
+                    else atomicMax(&vs.winner[bf[i]], pix0 + i);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool in_img = row_ok && (col + i < W);
+                const int pix = pix0 + i;
+                const int nxt = (i < 7) ? ((col + i + 1 < W) ? bp[i + 1] : -2) : ((has_next && col + 8 < W) ? next_first : -2);
+                if (in_img) {
+                    if (bp[i] < 0) {
+                        bgmax = pix;  // pixel index grows with i
+                    } else if (bp[i] != nxt) {
+                        if (bp[i] < GG_CHUNK) atomicMax(&s_win[bp[i]], pix);
+                        else atomicMax(&vs.winner[bf[i]], pix);
+                    }
                 }
             }
         }
@@ -1162,7 +1183,7 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
     st = st_ras;
     if (want_winners)
         GG_CUDA(cudaMemsetAsync(ctx->vset[ctx->cur].v[0].winner, 0xFF, (size_t)n * ctx->F * 4, st));
-    const dim3 rgrid((n_tiles + GG_RASTER_WARPS - 1) / GG_RASTER_WARPS, n);
+    const dim3 rgrid((tiles_x + GG_RASTER_WARPS - 1) / GG_RASTER_WARPS, tiles_y, n);
     GGDenseArgs da;
     memset(&da, 0, sizeof(da));
     if (h_pred) {  // fused dense per-pixel sums
