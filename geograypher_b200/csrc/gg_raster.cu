@@ -982,15 +982,20 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
                         }
                     }
                 };
-                // two rows in flight: the loads of the next row are issued before the current one is added
-                Vec rawA[kSteps], rawB[kSteps];
+                // three rows in flight: the loads of the rows after next are issued before the current one is added
+                Vec rawA[kSteps], rawB[kSteps], rawC[kSteps];
                 load_row(rawA, 0);
-                for (int r = 0; r < rows; r += 2) {
-                    if (r + 1 < rows) load_row(rawB, r + 1);
+                if (1 < rows) load_row(rawB, 1);
+                for (int r = 0; r < rows; r += 3) {
+                    if (r + 2 < rows) load_row(rawC, r + 2);
                     add_row(rawA, r);
                     if (r + 1 < rows) {
-                        if (r + 2 < rows) load_row(rawA, r + 2);
+                        if (r + 3 < rows) load_row(rawA, r + 3);
                         add_row(rawB, r + 1);
+                    }
+                    if (r + 2 < rows) {
+                        if (r + 4 < rows) load_row(rawB, r + 4);
+                        add_row(rawC, r + 2);
                     }
                 }
             }
@@ -1000,30 +1005,38 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, GG_RASTER_MIN_BLOCKS) k_ras
         __syncwarp();
         // slot of (pixel group q, channel c) is q*C + c on both paths; groups beyond a path's own are zero
         const int g_all = kSlots / C;
-        if (CT > 0 && fast) {
-            bool dirty = false;
-            for (int idx = lane; idx < nk * C; idx += 32) {
+        // One float64 atomicAdd per (face, channel).  On the unfiltered path a total that is not finite means a null or
+        // infinite score somewhere under that face in this tile: those entries are held back, the tile is summed again
+        // by the filtering loop, and only they are added from the second pass.
+        unsigned redo = 0;
+        {
+            int it = 0;
+            for (int idx = lane; idx < nk * C; idx += 32, ++it) {
+                const int k = idx / C, cch = idx - k * C;
+                const int n_px = s_cnt[k];
+                float total = 0.f;
+                for (int q = 0; q < g_all; ++q) total += s_acc[k * kSlots + q * C + cch];
+                if (n_px > 0) {
+                    const int64_t face = len <= GG_CHUNK ? s_faces[k].face : vs.bins[beg + k].face;
+                    if (cch == 0) atomicAdd(&dense.count[face], n_px);
+                    if (CT > 0 && fast && !(fabsf(total) <= 3.0e38f)) redo |= 1u << it;
+                    else atomicAdd(&dense.sum[face * C + cch], (double)total);
+                }
+            }
+        }
+        if (CT > 0 && fast && __any_sync(0xffffffffu, redo != 0)) {
+            for (int i = lane; i < nk * kSlots; i += 32) s_acc[i] = 0.f;
+            __syncwarp();
+            filtered_rows();
+            __syncwarp();
+            int it = 0;
+            for (int idx = lane; idx < nk * C; idx += 32, ++it) {
+                if (!((redo >> it) & 1u)) continue;
                 const int k = idx / C, cch = idx - k * C;
                 float total = 0.f;
                 for (int q = 0; q < g_all; ++q) total += s_acc[k * kSlots + q * C + cch];
-                dirty |= !(fabsf(total) <= 3.0e38f);
-            }
-            if (__any_sync(0xffffffffu, dirty)) {  // a null or infinite score somewhere in this tile: do it again, filtered
-                for (int i = lane; i < nk * kSlots; i += 32) s_acc[i] = 0.f;
-                __syncwarp();
-                filtered_rows();
-                __syncwarp();
-            }
-        }
-        for (int idx = lane; idx < nk * C; idx += 32) {
-            const int k = idx / C, cch = idx - k * C;
-            const int n_px = s_cnt[k];
-            float total = 0.f;
-            for (int q = 0; q < g_all; ++q) total += s_acc[k * kSlots + q * C + cch];
-            if (n_px > 0) {
                 const int64_t face = len <= GG_CHUNK ? s_faces[k].face : vs.bins[beg + k].face;
                 atomicAdd(&dense.sum[face * C + cch], (double)total);
-                if (cch == 0) atomicAdd(&dense.count[face], n_px);
             }
         }
     }
