@@ -424,19 +424,26 @@ def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, my_cams, dev, w
     """aggregate_projected_images through the reference-facing API, prediction images in pinned host memory."""
     W, H = cfg.image_size
     C = cfg.n_classes
-    n_views = min(args.e2e_views, len(my_cams))
+    from geograypher_b200 import distributed as ggd
+
+    n_views = args.e2e_views  # per rank (weak scaling, like the device-resident leg): the rank's cameras, cycled
     n_host = min(4, n_views)
     host = []
     for i in range(n_host):
         t = torch.empty((H, W, C), dtype=torch.float32, pin_memory=True)
-        t.copy_(syn.softmax_predictions_device(my_cams[i], H, W, C, dev))
+        t.copy_(syn.softmax_predictions_device(my_cams[i % len(my_cams)], H, W, C, dev))
         host.append(t.numpy())
     torch.cuda.synchronize()
     intr = {0: dict(f=cfg.f, cx=cfg.cx, cy=cfg.cy, image_width=W, image_height=H, distortion_params={})}
-    cams = gg.PhotogrammetryCameraSet(cam_to_world_transforms=[c2ws[k] for k in my_cams[:n_views]],
+    # every rank describes the WHOLE job (world x n_views cameras, rank r owning the r-th contiguous block)
+    all_ids = []
+    for r in range(world):
+        block = shard(len(c2ws), r, world)
+        all_ids += [block[i % len(block)] for i in range(n_views)]
+    cams = gg.PhotogrammetryCameraSet(cam_to_world_transforms=[c2ws[k] for k in all_ids],
                                       intrinsic_params_per_sensor_type=intr)
     seg = gg.SegmentorPhotogrammetryCameraSet(
-        cams, gg.ArraySegmentor([host[i % n_host] for i in range(n_views)], num_classes=C))
+        cams, gg.ArraySegmentor([host[i % n_host] for i in range(len(all_ids))], num_classes=C))
     mesh = gg.TexturedPhotogrammetryMesh((verts, faces), device=dev.index, views_per_batch=args.views_per_step,
                                          log_level="WARNING")
     mesh.aggregate_projected_images(seg.get_subset_cameras(list(range(min(2, n_views)))))  # warm-up: mesh upload etc.
@@ -444,29 +451,36 @@ def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, my_cams, dev, w
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    avg, info = mesh.aggregate_projected_images(seg)
+    if world > 1:  # camera-sharded, one all-reduce, the result is copied to the host once (rank 0)
+        avg, info = ggd.aggregate_projected_images_distributed(mesh, seg, dst_rank=0)
+    else:
+        avg, info = mesh.aggregate_projected_images(seg)
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    seen = torch.tensor([float(info["projection_counts"].sum()) if info else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(seen, op=dist.ReduceOp.MAX)
     dt = float(dt.item())
     steps = -(-n_views // args.views_per_step)
     F = len(faces)
     zero_copy = all(torch.from_numpy(h).is_pinned() for h in host)
-    seen_per_view = float(info["projection_counts"].sum()) / max(n_views, 1)
+    seen_per_view = float(seen.item()) / max(n_views * world, 1)
     row_bytes = -(-C * 4 // 32) * 32  # PCIe reads are sector-granular
     h2d = seen_per_view * row_bytes * n_views / steps if zero_copy else H * W * C * 4 * n_views / steps
     return {"value": n_views * world / dt, "unit": "views/s",
             "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int((F * C * 8 * 2 + F * 4) / steps),
+            "d2h_bytes_per_step": int((F * C * 8 * 2 + F * 8) / steps),
             "views": n_views * world, "seconds": dt,
-            "api": "TexturedPhotogrammetryMesh.aggregate_projected_images(SegmentorPhotogrammetryCameraSet)",
+            "api": ("TexturedPhotogrammetryMesh.aggregate_projected_images(SegmentorPhotogrammetryCameraSet)" if world == 1 else
+                    "geograypher_b200.distributed.aggregate_projected_images_distributed(mesh, SegmentorPhotogrammetryCameraSet, dst_rank=0)"),
             "note": ("float32 (H,W,C) score images stay in pinned HOST memory; last-pixel aggregation needs one row per "
                      "visible face, which a staging kernel fetches over PCIe through unified addressing, all rows of a batch in parallel (h2d bytes = "
                      "rows actually fetched, estimated from the per-face counts); the per-face float64 averages, sums "
                      "and counts are copied back at the end" if zero_copy else
                      "float32 (H,W,C) score images uploaded from host memory every view") +
-                    "; per-rank results are not all-reduced in this leg"}
+                    ("; cameras sharded over the ranks, accumulators all-reduced (NCCL), result copied to the host by "
+                     "rank 0" if world > 1 else "")}
 
 
 def main():

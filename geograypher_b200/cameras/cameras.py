@@ -10,7 +10,7 @@ from __future__ import annotations
 import hashlib
 import json
 import os
-from copy import deepcopy
+from copy import copy, deepcopy
 from pathlib import Path
 from typing import Dict, List, Optional, Tuple, Union
 
@@ -239,8 +239,10 @@ class PhotogrammetryCameraSet:
     def get_image_folder(self):
         return self.image_folder
 
-    def get_subset_cameras(self, inds: List[int]):
-        subset = deepcopy(self)
+    def get_subset_cameras(self, inds: List[int], deep: bool = True):
+        """The cameras at ``inds`` as a new set (reference cameras.py: a deep copy).  ``deep=False`` (*new*) shares the
+        camera objects with this set instead of copying them."""
+        subset = deepcopy(self) if deep else copy(self)
         subset.cameras = [subset.cameras[i] for i in inds]
         return subset
 

@@ -1,7 +1,7 @@
 """Camera set whose "images" are segmentation results (reference: geograypher/cameras/segmentor.py)."""
 import inspect
 import typing
-from copy import deepcopy
+from copy import copy, deepcopy
 
 import numpy as np
 
@@ -58,11 +58,11 @@ class SegmentorPhotogrammetryCameraSet(PhotogrammetryCameraSet):
     def get_raw_image_by_index(self, index: int, image_scale: float = 1) -> np.ndarray:
         return self.base_camera_set.get_image_by_index(index=index, image_scale=image_scale)
 
-    def get_subset_cameras(self, inds: typing.List[int]):
-        subset = deepcopy(self)
+    def get_subset_cameras(self, inds: typing.List[int], deep: bool = True):
+        subset = deepcopy(self) if deep else copy(self)
         subset.cameras = [subset.cameras[i] for i in inds]
         subset._indices = [subset._indices[i] for i in inds]
-        subset.base_camera_set = subset.base_camera_set.get_subset_cameras(inds)
+        subset.base_camera_set = subset.base_camera_set.get_subset_cameras(inds, deep=deep)
         return subset
 
     def __getitem__(self, slice):

@@ -24,7 +24,11 @@ def shard_range(n_items: int, rank: int, world_size: int):
 
 def shard_cameras(cameras, rank: int, world_size: int):
     """The sub-set of a PhotogrammetryCameraSet (or of a SegmentorPhotogrammetryCameraSet) that ``rank`` owns."""
-    return cameras.get_subset_cameras(list(shard_range(len(cameras), rank, world_size)))
+    inds = list(shard_range(len(cameras), rank, world_size))
+    try:
+        return cameras.get_subset_cameras(inds, deep=False)  # the shard is only read: no need to copy the cameras
+    except TypeError:  # a camera-set class with the reference's signature
+        return cameras.get_subset_cameras(inds)
 
 
 def allreduce_accumulators(d_sum, d_count, group=None):
@@ -51,11 +55,12 @@ def finalize_host(summed, counts):
 
 
 def aggregate_projected_images_distributed(mesh, cameras, aggregate_img_scale: float = 1, return_argmax: bool = False,
-                                           group=None, **kwargs):
+                                           group=None, dst_rank=None, **kwargs):
     """``TexturedPhotogrammetryMesh.aggregate_projected_images`` over all ranks of ``group``.
 
-    Every rank passes the SAME full camera set and gets the same full result back; internally it only processes
-    its own block of cameras.  ``mesh.device`` must be this rank's GPU.
+    Every rank passes the SAME full camera set; internally it only processes its own block of cameras.  By default
+    every rank gets the full result back; with ``dst_rank`` only that rank copies it to the host (the others return
+    ``(None, {})``), which is what a job that writes the result once wants.  ``mesh.device`` must be this rank's GPU.
     """
     import torch.distributed as dist
 
@@ -79,8 +84,11 @@ def aggregate_projected_images_distributed(mesh, cameras, aggregate_img_scale: f
         d_count = torch.zeros((mesh.faces.shape[0],), dtype=torch.int32, device=dev)
     mesh._get_context().drain()  # accumulators are written on the library's internal streams
     allreduce_accumulators(d_sum, d_count, group)
+    if dst_rank is not None and rank != dst_rank:
+        return None, {}
     avg, argmax = mesh._get_context().finalize(d_sum, d_count, want_avg=True, want_argmax=return_argmax)
-    info = {"projection_counts": d_count.cpu().numpy().astype(float), "summed_projections": d_sum.cpu().numpy()}
+    h_avg, h_sum, h_count = mesh._to_host(avg, d_sum, d_count.double())
+    info = {"projection_counts": h_count, "summed_projections": h_sum}
     if return_argmax:
         info["argmax"] = argmax.cpu().numpy()
-    return avg.cpu().numpy(), info
+    return h_avg, info

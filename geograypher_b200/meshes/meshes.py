@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import hashlib
 import logging
+import os
 import sys
 import typing
 from pathlib import Path
@@ -556,8 +557,27 @@ class TexturedPhotogrammetryMesh:
                 stage[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             stage[key].copy_(t, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        jobs = []
         for i, t in enumerate(tensors):
-            outs.append(torch.empty(t.shape, dtype=t.dtype).copy_(stage[(i, t.dtype, tuple(t.shape))]).numpy())
+            src = stage[(i, t.dtype, tuple(t.shape))].numpy()
+            dst = np.empty(src.shape, dtype=src.dtype)
+            outs.append(dst)
+            s1, d1 = src.reshape(-1), dst.reshape(-1)
+            step = max(1 << 20, -(-s1.size // 32))
+            jobs += [(d1[a : a + step], s1[a : a + step]) for a in range(0, s1.size, step)]
+        # The copy into fresh (not yet touched) pages is page-fault bound: spread it over a few threads of our own
+        # (NumPy releases the GIL for these copies; OMP_NUM_THREADS, which torchrun sets to 1, does not matter).
+        n_threads = min(16, os.cpu_count() or 1, max(1, len(jobs)))
+        if n_threads > 1:
+            pool = self.__dict__.get("_copy_pool")
+            if pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                pool = self.__dict__["_copy_pool"] = ThreadPoolExecutor(max_workers=n_threads)
+            list(pool.map(lambda job: np.copyto(job[0], job[1]), jobs))
+        else:
+            for d, s_ in jobs:
+                np.copyto(d, s_)
         return outs
 
     def _fetch_prediction(self, cameras, k, scale, image_getter, index_getter):

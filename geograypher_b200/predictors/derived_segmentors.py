@@ -64,6 +64,16 @@ class ArraySegmentor(Segmentor):
         self.images = images
         self.one_hot = one_hot
 
+    def __deepcopy__(self, memo):
+        # Camera sets deep-copy themselves when they are sub-set (get_subset_cameras, as in the reference).  The
+        # images are inputs, never written: share them instead of duplicating gigabytes -- a copy would also lose the
+        # page-locking that lets the GPU read them in place.
+        clone = type(self).__new__(type(self))
+        memo[id(self)] = clone
+        clone.__dict__.update(self.__dict__)
+        clone.images = list(self.images) if isinstance(self.images, list) else self.images
+        return clone
+
     def segment_image_indices(self, image, index: int, **kwargs):
         if not self.one_hot:
             raise NotImplementedError("index images are only available when one_hot=True")

@@ -51,7 +51,10 @@ def full(src, dst, title):
         for D in rows[2:]:
             f.write("----\n")
             for i, h in enumerate(H):
-                if h in KEEP or h == "Kernel Name":
+                stall = h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio")
+                if stall and float(D[i] or 0) < 0.1:
+                    continue
+                if h in KEEP or h == "Kernel Name" or stall:
                     f.write(f"{h:80s} {U[i]:16s} {D[i][:110]}\n")
 
 

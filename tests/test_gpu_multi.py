@@ -51,6 +51,13 @@ def _worker(rank, world, port, out):
         np.testing.assert_array_equal(info["projection_counts"], a["counts2"])
         np.testing.assert_allclose(avg, a["avg2"], rtol=1e-12, atol=0, equal_nan=True)
         np.testing.assert_array_equal(info["argmax"], a["argmax2"][:, 0])
+        # result wanted on one rank only: the others skip the device-to-host copy
+        avg0, info0 = ggd.aggregate_projected_images_distributed(mesh, seg, dst_rank=0)
+        if rank == 0:
+            np.testing.assert_allclose(avg0, a["avg2"], rtol=1e-12, atol=0, equal_nan=True)
+            np.testing.assert_array_equal(info0["projection_counts"], a["counts2"])
+        else:
+            assert avg0 is None and info0 == {}
         out[rank] = 1
     finally:
         dist.destroy_process_group()
