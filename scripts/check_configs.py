@@ -16,9 +16,11 @@ def build(name, ncam):
     print(f"{name}: F={len(faces)} V={len(verts)} cams={len(cams)} {W}x{H} built in {time.time()-t:.1f}s", flush=True)
     return verts, faces, cfg, ctx, cams
 
-def timeit(fn, n):
+def timeit(fn, n, ctx):
     torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    e0.record(); [fn(i) for i in range(n)]; e1.record(); torch.cuda.synchronize()
+    e0.record(); [fn(i) for i in range(n)]
+    ctx.drain()  # gg_project_aggregate works on the library's own streams: make this stream wait for them
+    e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 
 if "c4" in sys.argv:
@@ -32,7 +34,7 @@ if "c4" in sys.argv:
         ctx.rasterize(cams[(i % 4) * B:(i % 4) * B + B], out=p2f, check=False)
         ctx.render_flat(p2f, tex, out_dtype=_lib.OUT_U8, out=out)
     step(0); ctx.sync()
-    ms = timeit(step, 8)
+    ms = timeit(step, 8, ctx)
     ctx.sync()
     ref = out.clone()
     print(f"c4 render_flat -> uint8 (two kernels): {ms/B*1e3:.1f} us/view, {B/ms*1e3:.0f} views/s; labelled px frac {(out>0).float().mean().item():.3f}")
@@ -40,7 +42,7 @@ if "c4" in sys.argv:
         ctx.rasterize_render_flat(cams[(i % 4) * B:(i % 4) * B + B], tex, out_dtype=_lib.OUT_U8, out=out, check=False)
     fused(7); ctx.sync()
     assert torch.equal(out, ref)
-    ms = timeit(fused, 8)
+    ms = timeit(fused, 8, ctx)
     ctx.sync()
     print(f"c4 render_flat -> uint8 (fused): {ms/B*1e3:.1f} us/view, {B/ms*1e3:.0f} views/s")
 
@@ -54,7 +56,7 @@ if "c5" in sys.argv:
         ctx.project_aggregate(cams[(i % 10) * B:(i % 10) * B + B], preds, _lib.PRED_INDEX_U8, C, _lib.MODE_LAST_PIXEL, 0, d_sum, d_count, check=False)
     step(0); ctx.sync(); print("stats", ctx.last_batch_stats(B).tolist())
     d_sum.zero_(); d_count.zero_()
-    ms = timeit(step, 10)
+    ms = timeit(step, 10, ctx)
     ctx.sync()
     avg, amax = ctx.finalize(d_sum, d_count)
     print(f"c5 one-hot aggregation: {ms/B*1e3:.1f} us/view, {B/ms*1e3:.0f} views/s, {B/ms*1e3*W*H/1e9:.1f} Gpix/s; faces observed {(d_count>0).sum().item()}; mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB torch")
