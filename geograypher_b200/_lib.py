@@ -29,7 +29,7 @@ EXPORTS = [
     "gg_last_batch_stats", "gg_set_mesh", "gg_project", "gg_rasterize", "gg_aggregate",
     "gg_project_aggregate", "gg_finalize", "gg_render_flat", "gg_stage_count", "gg_stage_name", "gg_profile",
     "gg_profile_read", "gg_drain", "gg_set_pipeline", "gg_build_warp_map", "gg_gather_i32",
-    "gg_label_polygons", "gg_get_capacity", "gg_rasterize_render_flat",
+    "gg_label_polygons", "gg_get_capacity", "gg_rasterize_render_flat", "gg_project_winners", "gg_accumulate_rows",
 ]
 
 
@@ -98,6 +98,8 @@ def load():
     lib.gg_rasterize.argtypes = [vp, camp, i32, vp, vp, vp]
     lib.gg_aggregate.argtypes = [vp, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]
     lib.gg_project_aggregate.argtypes = [vp, camp, i32, ctypes.POINTER(vp), i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.gg_project_winners.argtypes = [vp, camp, i32, i32, vp, i64, vp, vp]
+    lib.gg_accumulate_rows.argtypes = [vp, vp, i64, vp, i32, i32, i32, i32, vp, vp, vp]
     lib.gg_finalize.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp]
     lib.gg_render_flat.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp]
     lib.gg_rasterize_render_flat.argtypes = [vp, camp, i32, vp, i32, vp, i32, vp, vp]
@@ -274,6 +276,13 @@ class Context:
 
     def reserve(self, max_faces_per_view=0, max_bin_entries_per_view=0):
         _check(self.lib.gg_reserve(self.handle, int(max_faces_per_view), int(max_bin_entries_per_view)))
+        self._reserved_faces = int(max_faces_per_view)
+
+    def get_capacity(self):
+        """(face records, (tile, face) pairs) the scratch holds per view; zeros before the first rasterization."""
+        recs, bins = ctypes.c_int64(), ctypes.c_int64()
+        _check(self.lib.gg_get_capacity(self.handle, ctypes.byref(recs), ctypes.byref(bins)))
+        return int(recs.value), int(bins.value)
 
     def profile(self, enable: bool):
         """Bracket every kernel launch with CUDA events on its stream (per-stage timing for bench.py)."""
@@ -372,6 +381,30 @@ class Context:
                 if e.code != ERR_OVERFLOW or attempt == 3 or mode == MODE_PIXEL_SUM:
                     raise
                 self._grow_after_overflow(n)
+
+    def project_winners(self, cams, flags=0, stream=None):
+        """Rasterize up to 32 same-size views and list, per view, every visible face with its last pixel (row-major):
+        returns (pairs (n, cap, 2) int32 CUDA tensor of (face, pixel), counts (n,) int32 CUDA tensor).  Asynchronous;
+        an overflow of the scratch shows up at the next sync() (grow with _grow_after_overflow and call again)."""
+        t, n = self.torch, len(cams)
+        cap = self.capacity_hint(cams[0].W, cams[0].H)
+        pairs = t.empty((n, cap, 2), dtype=t.int32, device=self._dev())
+        counts = t.empty((n,), dtype=t.int32, device=self._dev())
+        _check(self.lib.gg_project_winners(self.handle, self._cam_array(cams), n, flags, pairs.data_ptr(), cap,
+                                           counts.data_ptr(), _stream_ptr(stream)))
+        return pairs, counts
+
+    def capacity_hint(self, W, H):
+        """Upper bound of the (face, pixel) pairs one view can produce with the current scratch: records + 1."""
+        faces = max(self.get_capacity()[0], getattr(self, "_reserved_faces", 0))
+        if faces <= 0:  # scratch not allocated yet: the library's default for this mesh
+            faces = self.n_faces if self.n_faces < (1 << 20) else max(self.n_faces // 8, 1 << 20)
+        return int(min(faces, self.n_faces, int(W) * int(H)) + 1)
+
+    def accumulate_rows(self, pairs, n_rows, rows, pred_kind, C, mode, flags, d_sum, d_count, stream=None):
+        """Apply ONE view's gathered rows (rows[i] belongs to face pairs[i, 0]); see gg_accumulate_rows."""
+        _check(self.lib.gg_accumulate_rows(self.handle, pairs.data_ptr(), int(n_rows), rows.data_ptr(), pred_kind, C, mode,
+                                           flags, d_sum.data_ptr(), d_count.data_ptr(), _stream_ptr(stream)))
 
     def finalize(self, d_sum, d_count, want_avg=True, want_argmax=True, stream=None):
         t = self.torch

@@ -413,6 +413,96 @@ static int stage_host_rows(gg_context *ctx, int n, GGPredBatch &pb, int E, int f
     return GG_OK;
 }
 
+// ---- the path split in two for prediction images that sit in PAGEABLE host memory ------------------------------
+// The GPU cannot read pageable memory and uploading a whole image costs 100x more than the path itself, so the host
+// gathers the few rows that matter: k_compact_winners lists, per view, (face, last pixel) of every visible face; the
+// host picks those rows out of its array and sends them back; k_accumulate_rows applies one view's rows.
+__global__ void __launch_bounds__(256) k_compact_winners(const __grid_constant__ GGViewBatch views, int n_views, int64_t F,
+                                                         int flags, int32_t *__restrict__ pairs, int64_t cap,
+                                                         int32_t *__restrict__ counts, int32_t *__restrict__ sticky) {
+    for (int v = 0; v < n_views; ++v)
+        if (views.v[v].counters[3] != 0) return;  // overflowed batch: counts stay 0, the sticky flag reports it
+    const int view = blockIdx.y;
+    const GGViewScratch &vs = views.v[view];
+    const int n_recs = vs.counters[1];
+    const bool compat = (flags & GG_FLAG_COMPAT_NEG) != 0;
+    const int n = n_recs + ((compat && vs.counters[5] < 0) ? 1 : 0);
+    for (int r0 = blockIdx.x * blockDim.x; r0 < n; r0 += gridDim.x * blockDim.x) {
+        const int r = r0 + threadIdx.x;
+        int f = -1, p = -1;
+        if (r < n && !(r < n_recs && vs.recs[r].dup)) {
+            f = r < n_recs ? vs.recs[r].face : (int)(F - 1);
+            p = vs.winner[f];
+        }
+        const bool keep = p >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        int base = 0;
+        if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(&counts[view], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) {
+            const int64_t idx = base + __popc(m & ((1u << (threadIdx.x & 31)) - 1));
+            if (idx < cap) {
+                pairs[2 * ((int64_t)view * cap + idx)] = f;
+                pairs[2 * ((int64_t)view * cap + idx) + 1] = p;
+            } else {
+                atomicOr(sticky, 1);
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_accumulate_rows(const int32_t *__restrict__ pairs, int64_t n_rows,
+                                                         const T *__restrict__ rows, int C, int pred_kind, int mode,
+                                                         int flags, double *__restrict__ sum, int32_t *__restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const int64_t f = pairs[2 * i];
+    const bool keep_nan = (flags & GG_FLAG_KEEP_NAN) != 0;
+    if (mode == GG_MODE_VOTE) {
+        const double v = (double)rows[i];
+        if (!isfinite(v)) return;
+        const long long cls = (long long)v;
+        if (cls >= 0 && cls < C) sum[f * C + cls] += 1.0;
+        count[f] += 1;
+    } else if (pred_kind == GG_PRED_INDEX_U8) {
+        const int cls = (int)rows[i];
+        if (cls < C) sum[f * C + cls] += 1.0;
+        count[f] += 1;
+    } else {
+        bool fin = false;
+        for (int c = 0; c < C; ++c) {
+            const double v = (double)rows[i * C + c];
+            fin = fin || isfinite(v);
+            if (!isnan(v) || keep_nan) sum[f * C + c] += v;
+        }
+        count[f] += fin ? 1 : 0;
+    }
+}
+
+int gg_launch_compact_winners(gg_context *ctx, int n, int flags, int32_t *d_pairs, int64_t cap, int32_t *d_counts,
+                              cudaStream_t st) {
+    GG_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)n * sizeof(int32_t), st));
+    GG_LAUNCH(ctx, GG_ST_RESOLVE, st,
+              k_compact_winners<<<dim3((unsigned)(ctx->sm_count * 2), n), 256, 0, st>>>(ctx->vset[ctx->cur], n, ctx->F, flags,
+                                                                                      d_pairs, cap, d_counts, ctx->d_sticky));
+    return GG_OK;
+}
+
+int gg_launch_accumulate_rows(gg_context *ctx, const int32_t *d_pairs, int64_t n_rows, const void *d_rows, int pred_kind,
+                              int C, int mode, int flags, double *d_sum, int32_t *d_count, cudaStream_t st) {
+    if (n_rows == 0) return GG_OK;
+    const unsigned g = (unsigned)((n_rows + 255) / 256);
+    switch (pred_kind) {
+        case GG_PRED_F32: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_accumulate_rows<float><<<g, 256, 0, st>>>(d_pairs, n_rows, (const float *)d_rows, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_F64: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_accumulate_rows<double><<<g, 256, 0, st>>>(d_pairs, n_rows, (const double *)d_rows, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        case GG_PRED_U8:
+        case GG_PRED_INDEX_U8: GG_LAUNCH(ctx, GG_ST_RESOLVE, st, k_accumulate_rows<uint8_t><<<g, 256, 0, st>>>(d_pairs, n_rows, (const uint8_t *)d_rows, C, pred_kind, mode, flags, d_sum, d_count)); break;
+        default: gg_set_error("gg_accumulate_rows: bad pred_kind"); return GG_ERR_INVALID;
+    }
+    return GG_OK;
+}
+
 int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, int pred_kind, int C, int mode, int flags,
                             double *d_sum, int32_t *d_count, cudaStream_t st) {
     GGPredBatch pb;

@@ -560,6 +560,39 @@ int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const 
     return GG_OK;
 }
 
+int gg_project_winners(gg_context *ctx, const gg_camera *h_cams, int n, int flags, int32_t *d_pairs,
+                       int64_t cap_pairs_per_view, int32_t *d_counts, void *stream) {
+    int rc = check_ctx(ctx, true);
+    if (rc != GG_OK) return rc;
+    rc = check_cams(h_cams, n);
+    if (rc != GG_OK) return rc;
+    if (!d_pairs || !d_counts || cap_pairs_per_view < 1) {
+        gg_set_error("gg_project_winners: bad arguments");
+        return GG_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = gg_pipeline_drain(ctx, st);
+    if (rc != GG_OK) return rc;
+    rc = gg_launch_rasterize(ctx, h_cams, n, nullptr, nullptr, 1, flags & GG_FLAG_COMPAT_NEG, st, st);
+    if (rc != GG_OK) return rc;
+    return gg_launch_compact_winners(ctx, n, flags, d_pairs, cap_pairs_per_view, d_counts, st);
+}
+
+int gg_accumulate_rows(gg_context *ctx, const int32_t *d_pairs, int64_t n_rows, const void *d_rows, int pred_kind, int C,
+                       int mode, int flags, double *d_sum, int32_t *d_count, void *stream) {
+    int rc = check_ctx(ctx, true);
+    if (rc != GG_OK) return rc;
+    if (n_rows < 0 || (n_rows > 0 && (!d_pairs || !d_rows)) || !d_sum || !d_count || C < 1 ||
+        (mode != GG_MODE_LAST_PIXEL && mode != GG_MODE_VOTE)) {
+        gg_set_error("gg_accumulate_rows: bad arguments (modes: GG_MODE_LAST_PIXEL, GG_MODE_VOTE)");
+        return GG_ERR_INVALID;
+    }
+    rc = gg_pipeline_drain(ctx, (cudaStream_t)stream);
+    if (rc != GG_OK) return rc;
+    return gg_launch_accumulate_rows(ctx, d_pairs, n_rows, d_rows, pred_kind, C, mode, flags, d_sum, d_count,
+                                     (cudaStream_t)stream);
+}
+
 int gg_finalize(gg_context *ctx, double *d_sum, const int32_t *d_count, int64_t F, int C, double *d_avg,
                 double *d_argmax, void *stream) {
     int rc = check_ctx(ctx, false);

@@ -193,6 +193,10 @@ int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, i
 int gg_launch_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred,
                         int pred_kind, int C, int mode, int compat, double *d_sum, int32_t *d_count,
                         cudaStream_t st);
+int gg_launch_compact_winners(gg_context *ctx, int n, int flags, int32_t *d_pairs, int64_t cap, int32_t *d_counts,
+                              cudaStream_t st);
+int gg_launch_accumulate_rows(gg_context *ctx, const int32_t *d_pairs, int64_t n_rows, const void *d_rows, int pred_kind,
+                              int C, int mode, int flags, double *d_sum, int32_t *d_count, cudaStream_t st);
 int gg_launch_finalize(gg_context *ctx, double *d_sum, const int32_t *d_count, int64_t F, int C, double *d_avg,
                        double *d_argmax, cudaStream_t st);
 int gg_launch_render_flat(gg_context *ctx, const int32_t *d_pix2face, int64_t P, const double *d_tex, int D,

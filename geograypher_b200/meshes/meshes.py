@@ -96,6 +96,8 @@ class TexturedPhotogrammetryMesh:
         device: int = 0,
         compat_negative_index: bool = False,
         views_per_batch: int = 8,
+        use_principal_point: bool = True,
+        sparse_host_gather: bool = True,
     ):
         """A mesh with per-vertex / per-face textures that can be rendered into, and painted from, posed cameras.
 
@@ -113,6 +115,12 @@ class TexturedPhotogrammetryMesh:
             compat_negative_index (*new*): reproduce meshes.py:2000, where background pixels (-1) index the last
                 face.  Off by default; results then differ from the reference on face F-1 only.
             views_per_batch (*new*): how many views are rasterized per launch (<= 32).
+            use_principal_point (*new*): project with the cameras' principal-point offsets cx, cy, like the
+                reference's PyTorch3D renderer and its ``ideal_to_warped`` (derived_meshes.py:772-780).  False
+                reproduces the base class, whose pyvista camera has no principal point (cameras.py:446-477).
+            sparse_host_gather (*new*): prediction images in ordinary (pageable) NumPy arrays are not uploaded; the
+                GPU lists the one pixel per visible face that the aggregation needs and the host gathers those rows.
+                False uploads whole images.  Page-locked arrays are read in place by the GPU either way.
         """
         if downsample_target != 1.0 or ROI is not None:
             raise NotImplementedError(
@@ -127,6 +135,8 @@ class TexturedPhotogrammetryMesh:
         self.device = int(device)
         self.compat_negative_index = bool(compat_negative_index)
         self.views_per_batch = int(max(1, min(views_per_batch, _lib.MAX_VIEWS_PER_CALL)))
+        self.use_principal_point = bool(use_principal_point)
+        self.sparse_host_gather = bool(sparse_host_gather)
         self._context = None
         self._local_cache = None
 
@@ -340,8 +350,9 @@ class TexturedPhotogrammetryMesh:
         sizes = {c.get_image_size(scale) for c in cam_list}
         if len(sizes) != 1:
             raise ValueError("Not all cameras have the same image size")  # derived_meshes.py:811-813
+        pp = 1.0 if self.use_principal_point else 0.0
         return [
-            _lib.make_camera(c.world_to_cam_transform, c.f, c.cx, c.cy, c.image_width, c.image_height,
+            _lib.make_camera(c.world_to_cam_transform, c.f, pp * c.cx, pp * c.cy, c.image_width, c.image_height,
                              render_img_scale=scale, origin=local.origin)
             for c in cam_list
         ]
@@ -580,6 +591,72 @@ class TexturedPhotogrammetryMesh:
                 np.copyto(d, s_)
         return outs
 
+    # -- pageable host images: the GPU lists the pixels it needs, the host gathers them -----------------------------
+    def _pinned(self, name, shape, dtype):
+        """Grow-only page-locked staging tensor kept on the mesh object."""
+        import torch
+
+        stage = self.__dict__.setdefault("_sparse_stage", {})
+        need = int(np.prod(shape))
+        buf = stage.get(name)
+        if buf is None or buf.dtype != dtype or buf.numel() < need:
+            buf = stage[name] = torch.empty((max(need, 1),), dtype=dtype, pin_memory=True)
+        return buf[:need].view(*shape)
+
+    def _accumulate_sparse(self, ctx, gg, arrays, kind, C, mode, flags, d_sum, d_count):
+        """One batch whose prediction images sit in ordinary (pageable) NumPy arrays.  Uploading a 20-Mpx score image
+        costs ~100x the path itself, and the aggregation only needs the row of each visible face's last pixel, so:
+        rasterize and list (face, pixel) per view on the GPU (gg_project_winners), copy that short list to the host,
+        pick the rows out of the arrays with a few threads, send them back and apply them view by view
+        (gg_accumulate_rows) -- the same arithmetic, in the same order, as the fused path."""
+        import torch
+
+        n = len(gg)
+        E = 1 if (mode == _lib.MODE_VOTE or kind == _lib.PRED_INDEX_U8) else C  # elements per pixel
+        pairs, counts = ctx.project_winners(gg, flags)
+        h_counts = self._pinned("counts", (n,), torch.int32)
+        h_counts.copy_(counts, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        m = [int(x) for x in h_counts.tolist()]
+        cap = pairs.shape[1]
+        if max(m, default=0) > cap:  # the list did not fit: reported as an overflow by the next sync, then replayed
+            return
+        offs = np.concatenate([[0], np.cumsum(m)]).astype(np.int64)
+        total = int(offs[-1])
+        if total == 0:
+            return
+        h_pairs = self._pinned("pairs", (total, 2), torch.int32)
+        for v in range(n):
+            if m[v]:
+                h_pairs[offs[v] : offs[v + 1]].copy_(pairs[v, : m[v]], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        np_dtype = arrays[0].dtype
+        t_dtype = torch.from_numpy(np.empty(0, dtype=np_dtype)).dtype
+        h_rows = self._pinned("rows_" + str(np_dtype), (total, E), t_dtype)
+        rows_np, pairs_np = h_rows.numpy(), h_pairs.numpy()
+
+        def gather(job):
+            v, a, b = job
+            flat = arrays[v].reshape(-1, E)
+            np.take(flat, pairs_np[a:b, 1], axis=0, out=rows_np[a:b], mode="clip")
+
+        jobs = []
+        for v in range(n):  # split every view into a few chunks so that all threads have work
+            step = max(2048, -(-m[v] // 4))
+            jobs += [(v, int(offs[v]) + a, int(offs[v]) + min(a + step, m[v])) for a in range(0, m[v], step)]
+        pool = self.__dict__.get("_copy_pool")
+        if pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            pool = self.__dict__["_copy_pool"] = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+        list(pool.map(gather, jobs))
+        d_rows = h_rows.to(d_sum.device, non_blocking=True)
+        for v in range(n):  # view order = the reference's summation order
+            if m[v]:
+                ctx.accumulate_rows(pairs[v], m[v], d_rows[offs[v] : offs[v + 1]], kind, C, mode, flags, d_sum, d_count)
+        # the staging buffers are reused by the next batch: the copies out of them must have finished
+        torch.cuda.current_stream().synchronize()
+
     def _fetch_prediction(self, cameras, k, scale, image_getter, index_getter):
         """(array, pred_kind, C) of view k: a caller-supplied getter, else the segmentor's class-index image when
         it offers one (expanded on the GPU), else whatever get_image_by_index returns."""
@@ -632,7 +709,18 @@ class TexturedPhotogrammetryMesh:
                             kind = this_kind
                         elif kind != this_kind:
                             raise ValueError("all prediction images of a batch must share one dtype / layout")
-                        preds.append(self._to_device_or_mapped(arr, dev, zero_copy=not apply_distortion))
+                        preds.append(arr)
+                    sparse = (not apply_distortion and self.sparse_host_gather and mode != _lib.MODE_PIXEL_SUM
+                              and len({a.dtype for a in preds}) == 1
+                              and not any(torch.from_numpy(a).is_pinned() for a in preds))
+                    if sparse:
+                        if in_flight:  # the fused calls queued so far use the library's own streams
+                            ctx.sync()
+                            in_flight.clear()
+                        self._accumulate_sparse(ctx, self._gg_cameras(batch, mesh, aggregate_img_scale), preds, kind, C,
+                                                mode, flags, d_sum, d_count)
+                        continue
+                    preds = [self._to_device_or_mapped(a, dev, zero_copy=not apply_distortion) for a in preds]
                     if apply_distortion:
                         p2f = self._pix2face_for_aggregation(batch[0], mesh, aggregate_img_scale, pix2face_kwargs)
                         ctx.aggregate(p2f[0], preds[0], kind, C, mode, flags, d_sum, d_count)

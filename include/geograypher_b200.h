@@ -146,6 +146,19 @@ int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const 
                          int pred_kind, int C, int mode, int flags, double *d_sum, int32_t *d_count,
                          int32_t *d_pix2face, void *stream);
 
+/* ---- the fused path split in two, for prediction images in PAGEABLE host memory (which the GPU cannot read in
+        place and which cost ~100x the path to upload whole).  gg_project_winners rasterizes n views and lists, per
+        view, every visible face with its last pixel in row-major order (the pixel whose value project_images keeps,
+        meshes.py:2001): d_pairs[(view*cap + i)*2 + {0,1}] = {face, pixel}, i < d_counts[view] (order unspecified).
+        With GG_FLAG_COMPAT_NEG the last background pixel is listed for face F-1 (meshes.py:2000).  The host gathers
+        pred[pixel, :] for those pairs and gg_accumulate_rows applies ONE view's rows (row i belongs to the face of
+        pair i; C elements per row, one element for GG_PRED_INDEX_U8 and GG_MODE_VOTE) with the arithmetic of
+        gg_aggregate.  Call it view by view, in view order, to get the reference's float64 sums bit for bit. ------- */
+int gg_project_winners(gg_context *ctx, const gg_camera *h_cams, int n, int flags, int32_t *d_pairs,
+                       int64_t cap_pairs_per_view, int32_t *d_counts, void *stream);
+int gg_accumulate_rows(gg_context *ctx, const int32_t *d_pairs, int64_t n_rows, const void *d_rows, int pred_kind, int C,
+                       int mode, int flags, double *d_sum, int32_t *d_count, void *stream);
+
 /* ---- epilogue of aggregate_projected_images (meshes.py:2069-2082) + find_argmax_nonzero_value
         (utils/indexing.py:9-32): avg = sum / count (NaN rows where count == 0; d_sum rows with count == 0 are
         set to NaN in place like meshes.py:2070), argmax as float64 with NaN for all-zero / non-finite rows.

@@ -22,6 +22,12 @@ KEEP = [
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__throughput.avg.pct_of_peak_sustained_active",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    # atomics: global reductions (RED) at L2 and shared-memory atomics
+    "smsp__inst_executed_op_global_red.sum", "smsp__inst_executed_op_shared_atom.sum",
+    "lts__t_requests_srcunit_tex_op_red.sum", "lts__t_sectors_srcunit_tex_op_red.sum",
+    "lts__t_sectors_srcunit_tex_op_red.sum.per_second", "lts__t_sectors_srcunit_tex_op_red.sum.pct_of_peak_sustained_elapsed",
+    "lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum", "lts__t_sector_hit_rate.pct",
 ]
 
 

@@ -42,6 +42,23 @@ def test_pix2face_contract(scene):
         mesh.pix2face(cameras=cams, cache_folder=None, distortion_set=cams, apply_distortion=True)
 
 
+def test_principal_point_switch(scene):
+    """use_principal_point=False is the base class's pyvista camera (no cx, cy: cameras.py:446-477); the default
+    projects like the PyTorch3D renderer and ideal_to_warped (derived_meshes.py:772-780)."""
+    g, cams = scene
+    f, cx, cy, W, H = g["intrinsics"]
+    assert cx != 0 or cy != 0
+    centred = gg.PhotogrammetryCameraSet(
+        cameras=[gg.PhotogrammetryCamera(None, T, f, 0.0, 0.0, int(W), int(H)) for T in g["c2ws"]],
+        local_to_epsg_4978_transform=np.eye(4),
+    )
+    with_pp = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]))
+    without = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), use_principal_point=False)
+    a = without.pix2face(cams, apply_distortion=False)
+    np.testing.assert_array_equal(a, with_pp.pix2face(centred, apply_distortion=False))
+    assert (a != with_pp.pix2face(cams, apply_distortion=False)).any()
+
+
 def test_local_frame_transform(scene):
     """get_mesh_in_cameras_coords: an ECEF-like mesh + a similarity local->ECEF transform give the same rasters."""
     g, cams0 = scene
@@ -62,11 +79,15 @@ def test_local_frame_transform(scene):
     assert (p2f != g["pix2face"]).mean() < 2e-3
 
 
-def test_aggregate_matches_reference_outputs(scene, golden_aggregate):
+@pytest.mark.parametrize("sparse", [True, False])
+def test_aggregate_matches_reference_outputs(scene, golden_aggregate, sparse):
+    """NumPy (pageable) prediction arrays: by default the host gathers the rows the GPU asks for (sparse=True),
+    else whole images are uploaded; both give the reference's numbers."""
     g, cams = scene
     a = golden_aggregate
     C = a["avg1"].shape[1]
-    mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), compat_negative_index=True, views_per_batch=2)
+    mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), compat_negative_index=True, views_per_batch=2,
+                                         sparse_host_gather=sparse)
     # class-index segmentor -> on-the-fly one-hot on the GPU
     seg = gg.SegmentorPhotogrammetryCameraSet(cams, gg.ArraySegmentor(list(a["idx_imgs"]), num_classes=C, one_hot=True))
     avg, info = mesh.aggregate_projected_images(seg, return_argmax=True)
@@ -84,16 +105,18 @@ def test_aggregate_matches_reference_outputs(scene, golden_aggregate):
     avg, info = mesh.aggregate_projected_images(seg2.get_subset_cameras([0]))
     _eq(avg, a["avg2s"]); _eq(info["summed_projections"], a["summed2s"])
     # default (bug-free) mode differs from the reference on the last face only
-    mesh2 = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]))
+    mesh2 = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), sparse_host_gather=sparse)
     avg, info = mesh2.aggregate_projected_images(seg2)
     _eq(avg[:-1], a["avg2"][:-1]); _eq(info["projection_counts"][:-1], a["counts2"][:-1])
 
 
-def test_votes_match_reference_outputs(scene, golden_aggregate):
+@pytest.mark.parametrize("sparse", [True, False])
+def test_votes_match_reference_outputs(scene, golden_aggregate, sparse):
     g, cams = scene
     a = golden_aggregate
     nv = int(a["n_vote_classes"])
-    mesh = gg.TexturedPhotogrammetryMeshIndexPredictions((g["verts"], g["faces"]), compat_negative_index=True)
+    mesh = gg.TexturedPhotogrammetryMeshIndexPredictions((g["verts"], g["faces"]), compat_negative_index=True,
+                                                         sparse_host_gather=sparse)
     seg = gg.SegmentorPhotogrammetryCameraSet(cams, gg.ArraySegmentor(list(a["vote_imgs"])))
     avg, info = mesh.aggregate_projected_images(seg, n_classes=nv)
     _eq(avg.toarray(), a["avg3"])
