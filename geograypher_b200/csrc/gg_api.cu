@@ -110,36 +110,43 @@ __global__ void __launch_bounds__(256) k_permute_faces(const int4 *__restrict__ 
 static int sort_faces_spatially(gg_context *ctx, cudaStream_t st) {
     const int64_t F = ctx->F, V = ctx->V;
     if (F < 2 * GG_BLOCK_FACES || V == 0) return GG_OK;  // a single cull block: nothing to gain
-    float *d_lohi = nullptr;
-    unsigned *d_codes = nullptr, *d_codes_out = nullptr;
-    int *d_order = nullptr, *d_order_out = nullptr;
-    int4 *d_sorted = nullptr;
-    void *d_tmp = nullptr;
+    // one allocation for all temporaries, so that every exit path frees exactly one pointer
+    const size_t nF = (size_t)F;
+    const size_t off_codes = 256, off_codes_out = off_codes + nF * 4, off_order = off_codes_out + nF * 4,
+                 off_order_out = off_order + nF * 4;
     size_t tmp_bytes = 0;
-    GG_CUDA(cudaMalloc(&d_lohi, 6 * sizeof(float)));
-    GG_CUDA(cudaMalloc(&d_codes, (size_t)F * 4));
-    GG_CUDA(cudaMalloc(&d_codes_out, (size_t)F * 4));
-    GG_CUDA(cudaMalloc(&d_order, (size_t)F * 4));
-    GG_CUDA(cudaMalloc(&d_order_out, (size_t)F * 4));
-    GG_CUDA(cudaMalloc(&d_sorted, (size_t)F * sizeof(int4)));
-    k_vertex_bounds_init<<<1, 32, 0, st>>>(d_lohi);
-    k_vertex_bounds<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->d_verts, V, d_lohi);
-    k_morton_codes<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(ctx->d_verts, ctx->d_faces, F, d_lohi, d_codes, d_order);
-    GG_CUDA(cudaGetLastError());
-    GG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_codes, d_codes_out, d_order, d_order_out, (int)F, 0, 30, st));
-    GG_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
-    GG_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_codes, d_codes_out, d_order, d_order_out, (int)F, 0, 30, st));
-    k_permute_faces<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(ctx->d_faces, d_order_out, F, d_sorted);
-    GG_CUDA(cudaGetLastError());
-    GG_CUDA(cudaStreamSynchronize(st));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned *)nullptr, (unsigned *)nullptr,
+                                                    (const int *)nullptr, (int *)nullptr, (int)F, 0, 30, st);
+    if (e != cudaSuccess) return gg_cuda_fail(e, "cub::DeviceRadixSort::SortPairs (size query)");
+    const size_t off_tmp = (off_order_out + nF * 4 + 255) / 256 * 256;
+    char *buf = nullptr;
+    int4 *d_sorted = nullptr;
+    GG_CUDA(cudaMalloc(&buf, off_tmp + tmp_bytes));
+    e = cudaMalloc(&d_sorted, nF * sizeof(int4));
+    if (e == cudaSuccess) {
+        float *d_lohi = (float *)buf;
+        unsigned *d_codes = (unsigned *)(buf + off_codes), *d_codes_out = (unsigned *)(buf + off_codes_out);
+        int *d_order = (int *)(buf + off_order), *d_order_out = (int *)(buf + off_order_out);
+        k_vertex_bounds_init<<<1, 32, 0, st>>>(d_lohi);
+        k_vertex_bounds<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->d_verts, V, d_lohi);
+        k_morton_codes<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(ctx->d_verts, ctx->d_faces, F, d_lohi, d_codes, d_order);
+        e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = cub::DeviceRadixSort::SortPairs(buf + off_tmp, tmp_bytes, d_codes, d_codes_out, d_order, d_order_out, (int)F, 0,
+                                                30, st);
+        if (e == cudaSuccess) {
+            k_permute_faces<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(ctx->d_faces, d_order_out, F, d_sorted);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(buf);
+    if (e != cudaSuccess) {
+        cudaFree(d_sorted);
+        return gg_cuda_fail(e, "sorting the faces along the Z-order curve");
+    }
     cudaFree(ctx->d_faces);
     ctx->d_faces = d_sorted;
-    cudaFree(d_lohi);
-    cudaFree(d_codes);
-    cudaFree(d_codes_out);
-    cudaFree(d_order);
-    cudaFree(d_order_out);
-    cudaFree(d_tmp);
     return GG_OK;
 }
 

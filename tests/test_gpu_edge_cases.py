@@ -208,6 +208,18 @@ def test_near_plane_clipping(torch, lib, znear):
             want = ora.aggregate(got[None].astype(np.int64), [pred], F, compat_negative_index=False)
             np.testing.assert_array_equal(d_count.cpu().numpy(), want[1].astype(np.int64))
             np.testing.assert_array_equal(d_sum.cpu().numpy(), np.nan_to_num(want[2]))
+            # the same through the two-step path for pageable host images (GPU lists pixels, host gathers rows)
+            pairs, counts = ctx.project_winners([_gg(lib, cam)], 0)
+            ctx.sync()
+            m = int(counts[0].item())
+            fp = pairs[0, :m].cpu().numpy()
+            assert len(np.unique(fp[:, 0])) == m  # every visible face once, also the ones split in two
+            rows = torch.from_numpy(pred.reshape(-1, C)[fp[:, 1]]).cuda()
+            s2 = torch.zeros_like(d_sum)
+            c2 = torch.zeros_like(d_count)
+            ctx.accumulate_rows(pairs[0], m, rows, lib.PRED_F32, C, mode, 0, s2, c2)
+            ctx.sync()
+            assert torch.equal(s2, d_sum) and torch.equal(c2, d_count)
         else:
             cnt = np.bincount(ids[keep], minlength=F)
             ref_sum = np.zeros((F, C))
