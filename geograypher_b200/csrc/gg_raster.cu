@@ -691,15 +691,12 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
                 const float gx = __int_as_float(q2.z);
                 const float wrow = fmaf(gx, ftx0, fmaf(__int_as_float(q2.w), fty, __int_as_float(q2.y)));
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if ((e0 | e1 | e2) >= 0) {
-                        const float w = fmaf(gx, (float)i, wrow);
-                        if (w > bw[i] || (w == bw[i] && face < bf[i])) {
-                            bw[i] = w;
-                            bf[i] = face;
-                            bp[i] = pos;
-                        }
-                    }
+                for (int i = 0; i < 8; ++i) {  // branch-free: selects cost less than the divergence bookkeeping
+                    const float w = fmaf(gx, (float)i, wrow);
+                    const bool upd = ((e0 | e1 | e2) >= 0) & ((w > bw[i]) | ((w == bw[i]) & (face < bf[i])));
+                    bw[i] = upd ? w : bw[i];
+                    bf[i] = upd ? face : bf[i];
+                    bp[i] = upd ? pos : bp[i];
                     e0 += s0;
                     e1 += s1;
                     e2 += s2;
