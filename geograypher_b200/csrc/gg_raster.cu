@@ -755,17 +755,18 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
         const bool has_next = (lane & 3) != 3;
         int bgmax = -1;
         const int pix0 = row * W + col;
-        if (tile_x0 + GG_TILE_W <= W && tile_y0 + GG_TILE_H <= H) {  // tile entirely inside the image (warp-uniform)
+        if (tile_x0 + GG_TILE_W <= W && tile_y0 + GG_TILE_H <= H && len <= GG_CHUNK) {
+            // tile entirely inside the image and every list position has a shared-memory slot (warp-uniform): one
+            // predicated shared-memory atomic per run-end, nothing else
             const int after = has_next ? next_first : -2;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int nxt = (i < 7) ? bp[i < 7 ? i + 1 : 7] : after;
-                if (bp[i] < 0) {
-                    bgmax = pix0 + i;  // pixel index grows with i
-                } else if (bp[i] != nxt) {
-                    if (bp[i] < GG_CHUNK) atomicMax(&s_win[bp[i]], pix0 + i);
-                    else atomicMax(&vs.winner[bf[i]], pix0 + i);
-                }
+                if ((bp[i] >= 0) & (bp[i] != nxt)) atomicMax(&s_win[bp[i]], pix0 + i);
+            }
+            if (compat_bg) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bgmax = bp[i] < 0 ? pix0 + i : bgmax;  // pixel index grows with i
             }
         } else {
 #pragma unroll
