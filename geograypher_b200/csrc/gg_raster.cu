@@ -633,12 +633,14 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
     const int tx0 = (lane & 3) * 8;  // this lane: pixels tx0..tx0+7 of row ty
     const int ty = lane >> 2;
 
-    float bw[8];
-    int bf[8], bp[8];  // winning face ID and its position in the tile's list, -1 = none
+    // Per pixel: the winner's key (bits of its 1/z, which is positive -> ordered like the float; then ~face so that the
+    // lower ID wins a tie) compared as ONE 64-bit unsigned integer, and its position in the tile's list (-1 = none).
+    unsigned kw[8], kf[8];
+    int bp[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        bw[i] = 0.f;
-        bf[i] = -1;
+        kw[i] = 0u;
+        kf[i] = 0u;  // ~(-1)
         bp[i] = -1;
     }
     if (WINNERS) s_win[lane] = -1;
@@ -678,7 +680,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
         for (int k = 0; k < n; ++k) {
             const int4 q3 = *reinterpret_cast<const int4 *>(&s_faces[k].lanemask);  // lanemask face rec fast
             if (!((((unsigned)q3.x) >> lane) & 1u)) continue;
-            const int face = q3.y;
+            const unsigned nface = ~(unsigned)q3.y;
             const int pos = base + k;
             if (q3.w) {
                 const int4 q0 = *reinterpret_cast<const int4 *>(&s_faces[k].e[0]);   // e0 e1 e2 sx0
@@ -693,9 +695,11 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {  // branch-free: selects cost less than the divergence bookkeeping
                     const float w = fmaf(gx, (float)i, wrow);
-                    const bool upd = ((e0 | e1 | e2) >= 0) & ((w > bw[i]) | ((w == bw[i]) & (face < bf[i])));
-                    bw[i] = upd ? w : bw[i];
-                    bf[i] = upd ? face : bf[i];
+                    const unsigned wb = __float_as_uint(w);
+                    const bool upd = ((e0 | e1 | e2) >= 0) &
+                                     ((((unsigned long long)wb << 32) | nface) > (((unsigned long long)kw[i] << 32) | kf[i]));
+                    kw[i] = upd ? wb : kw[i];
+                    kf[i] = upd ? nface : kf[i];
                     bp[i] = upd ? pos : bp[i];
                     e0 += s0;
                     e1 += s1;
@@ -706,10 +710,11 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {  // unrolled so that bw / bf / br stay in registers
                     float w;
-                    if (exact_cover(r, tile_x0 + tx0 + i, tile_y0 + ty, w)) {
-                        if (w > bw[i] || (w == bw[i] && face < bf[i])) {
-                            bw[i] = w;
-                            bf[i] = face;
+                    if (exact_cover(r, tile_x0 + tx0 + i, tile_y0 + ty, w) && w > 0.f) {
+                        const unsigned wb = __float_as_uint(w);
+                        if ((((unsigned long long)wb << 32) | nface) > (((unsigned long long)kw[i] << 32) | kf[i])) {
+                            kw[i] = wb;
+                            kf[i] = nface;
                             bp[i] = pos;
                         }
                     }
@@ -717,6 +722,14 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
             }
         }
         __syncwarp();
+    }
+
+    float bw[8];
+    int bf[8];  // 1/z and face ID of the winners, -1 = none
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        bw[i] = __uint_as_float(kw[i]);
+        bf[i] = (int)~kf[i];
     }
 
     // ---- write the 8 pixels of this lane ----
