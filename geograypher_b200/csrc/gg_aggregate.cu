@@ -364,14 +364,14 @@ __global__ void __launch_bounds__(256) k_stage_rows(const __grid_constant__ GGVi
     const int n = n_recs + ((compat && vs.counters[5] < 0) ? 1 : 0);
     const T *__restrict__ pred = (const T *)preds.p[view];
     T *__restrict__ out = stage + (int64_t)view * rows_per_view * E;
-    const int64_t total = (int64_t)n * E;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int r = (int)(idx / E), e = (int)(idx - (int64_t)r * E);
+    // block = (elements of a row padded to a power of two) x (rows): no index division, a row's loads sit in
+    // neighbouring lanes and share their sectors
+    for (int r = blockIdx.x * blockDim.y + threadIdx.y; r < n; r += gridDim.x * blockDim.y) {
         if (r < n_recs && vs.recs[r].dup) continue;
         const int64_t f = r < n_recs ? (int64_t)vs.recs[r].face : F - 1;
         const int p = vs.winner[f];
         if (p < 0) continue;
-        out[(int64_t)r * E + e] = pred[(int64_t)p * E + e];
+        for (int e = threadIdx.x; e < E; e += blockDim.x) out[(int64_t)r * E + e] = pred[(int64_t)p * E + e];
     }
 }
 
@@ -404,9 +404,11 @@ static int stage_host_rows(gg_context *ctx, int n, GGPredBatch &pb, int E, int f
         ctx->stage_bytes = need;
     }
     T *stage = (T *)ctx->d_stage;
-    const dim3 g((unsigned)(ctx->sm_count * 8), n);
+    int e_pad = 1;
+    while (e_pad < E && e_pad < 32) e_pad <<= 1;
+    const dim3 g((unsigned)(ctx->sm_count * 8), n), b(e_pad, 256 / e_pad);
     GG_LAUNCH(ctx, GG_ST_RESOLVE, st,
-              k_stage_rows<T><<<g, 256, 0, st>>>(ctx->vset[ctx->cur], n, ctx->F, pb, E, flags, stage, rows_per_view));
+              k_stage_rows<T><<<g, b, 0, st>>>(ctx->vset[ctx->cur], n, ctx->F, pb, E, flags, stage, rows_per_view));
     GG_LAUNCH(ctx, GG_ST_RESOLVE, st,
               k_stage_commit<<<dim3((unsigned)(ctx->sm_count * 2), n), 256, 0, st>>>(ctx->vset[ctx->cur], n, ctx->F, flags));
     for (int i = 0; i < n; ++i) pb.p[i] = stage + (int64_t)i * rows_per_view * E;
