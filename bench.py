@@ -281,6 +281,17 @@ def run_ours(args):
     mode = _lib.MODE_LAST_PIXEL
 
     my_cams = shard(len(c2ws), rank, world)
+    # The page-locked host images of the end-to-end leg are allocated first, while the host's memory is still
+    # unfragmented: the GPU reads scattered rows out of them over PCIe, and that runs measurably slower from pinned
+    # buffers that were allocated late in a process (after the legs below) than from these.
+    e2e_host = None
+    if not args.no_e2e:
+        e2e_host = []
+        for i in range(min(4, args.e2e_views)):
+            t = torch.empty((H, W, C), dtype=torch.float32, pin_memory=True)
+            t.copy_(syn.softmax_predictions_device(my_cams[i % len(my_cams)], H, W, C, dev))
+            e2e_host.append(t.numpy())
+        torch.cuda.synchronize()
     ctx = _lib.Context(local_rank)
     ctx.set_mesh(torch.from_numpy((verts - origin).astype(np.float32)).to(dev), torch.from_numpy(faces).to(dev))
     w2c = [np.linalg.inv(T) for T in c2ws]
@@ -381,7 +392,7 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, my_cams, dev, world)
+        e2e = run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, my_cams, dev, world, e2e_host)
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------------------
     cpu = None
@@ -420,20 +431,14 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, my_cams, dev, world):
+def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, my_cams, dev, world, host):
     """aggregate_projected_images through the reference-facing API, prediction images in pinned host memory."""
     W, H = cfg.image_size
     C = cfg.n_classes
     from geograypher_b200 import distributed as ggd
 
     n_views = args.e2e_views  # per rank (weak scaling, like the device-resident leg): the rank's cameras, cycled
-    n_host = min(4, n_views)
-    host = []
-    for i in range(n_host):
-        t = torch.empty((H, W, C), dtype=torch.float32, pin_memory=True)
-        t.copy_(syn.softmax_predictions_device(my_cams[i % len(my_cams)], H, W, C, dev))
-        host.append(t.numpy())
-    torch.cuda.synchronize()
+    n_host = len(host)
     intr = {0: dict(f=cfg.f, cx=cfg.cx, cy=cfg.cy, image_width=W, image_height=H, distortion_params={})}
     # every rank describes the WHOLE job (world x n_views cameras, rank r owning the r-th contiguous block)
     all_ids = []
@@ -452,7 +457,10 @@ def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, my_cams, dev, w
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     if world > 1:  # camera-sharded, one all-reduce, the result is copied to the host once (rank 0)
-        avg, info = ggd.aggregate_projected_images_distributed(mesh, seg, dst_rank=0)
+        timings = {} if os.environ.get("GG_BENCH_DEBUG") else None
+        avg, info = ggd.aggregate_projected_images_distributed(mesh, seg, dst_rank=0, timings=timings)
+        if timings is not None:
+            print(f"[e2e rank {dist.get_rank()}] " + ", ".join(f"{k} {v:.3f}s" for k, v in timings.items()), file=sys.stderr, flush=True)
     else:
         avg, info = mesh.aggregate_projected_images(seg)
     torch.cuda.synchronize()

@@ -55,20 +55,33 @@ def finalize_host(summed, counts):
 
 
 def aggregate_projected_images_distributed(mesh, cameras, aggregate_img_scale: float = 1, return_argmax: bool = False,
-                                           group=None, dst_rank=None, **kwargs):
+                                           group=None, dst_rank=None, timings=None, **kwargs):
     """``TexturedPhotogrammetryMesh.aggregate_projected_images`` over all ranks of ``group``.
 
     Every rank passes the SAME full camera set; internally it only processes its own block of cameras.  By default
     every rank gets the full result back; with ``dst_rank`` only that rank copies it to the host (the others return
     ``(None, {})``), which is what a job that writes the result once wants.  ``mesh.device`` must be this rank's GPU.
+    ``timings`` (a dict) receives this rank's seconds per phase (each phase ends with a device synchronisation).
     """
+    import time
+
+    import torch
+
+    def mark(name, t0):
+        if timings is not None:
+            torch.cuda.synchronize()
+            timings[name] = time.perf_counter() - t0
+        return time.perf_counter()
+
     import torch.distributed as dist
 
     from geograypher_b200 import _lib
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    t0 = time.perf_counter()
     mine = shard_cameras(cameras, rank, world)
+    t0 = mark("shard", t0)
     pix2face_kwargs = {k: v for k, v in kwargs.items() if k != "check_null_image"}
     n_total = len(cameras)
     if len(mine) > 0:
@@ -83,7 +96,9 @@ def aggregate_projected_images_distributed(mesh, cameras, aggregate_img_scale: f
         d_sum = torch.zeros((mesh.faces.shape[0], C), dtype=torch.float64, device=dev)
         d_count = torch.zeros((mesh.faces.shape[0],), dtype=torch.int32, device=dev)
     mesh._get_context().drain()  # accumulators are written on the library's internal streams
+    t0 = mark("accumulate", t0)
     allreduce_accumulators(d_sum, d_count, group)
+    t0 = mark("allreduce", t0)
     if dst_rank is not None and rank != dst_rank:
         return None, {}
     avg, argmax = mesh._get_context().finalize(d_sum, d_count, want_avg=True, want_argmax=return_argmax)
@@ -91,4 +106,5 @@ def aggregate_projected_images_distributed(mesh, cameras, aggregate_img_scale: f
     info = {"projection_counts": h_count, "summed_projections": h_sum}
     if return_argmax:
         info["argmax"] = argmax.cpu().numpy()
+    mark("to_host", t0)
     return h_avg, info
