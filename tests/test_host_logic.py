@@ -75,6 +75,28 @@ def test_segmentor_camera_set(golden_aggregate):
     assert gg.SegmentorPhotogrammetryCameraSet(cams, RefStyle()).get_image_by_index(0)[0, 0] == 7.0
 
 
+def test_subsets_share_the_prediction_arrays(golden_aggregate):
+    """Sub-setting a segmentor camera set deep-copies the cameras (like the reference) but never the in-memory
+    prediction images -- a copy would cost gigabytes and lose their page-locking; the shards of the multi-GPU path
+    do not copy the cameras either."""
+    from geograypher_b200 import distributed as ggd
+
+    a = golden_aggregate
+    cams, _ = _camera_set(3)
+    C = a["avg1"].shape[1]
+    images = list(a["idx_imgs"])
+    seg = gg.SegmentorPhotogrammetryCameraSet(cams, gg.ArraySegmentor(images, num_classes=C, one_hot=True))
+    deep = seg.get_subset_cameras([2, 0])
+    assert deep.segmentor.images[2] is images[2] and deep[0] is not seg[2]
+    assert deep.get_class_index_image_by_index(0) is images[2]
+    for rank, want in ((0, [0, 1]), (1, [2])):
+        shard = ggd.shard_cameras(seg, rank, 2)
+        assert len(shard) == len(want) and shard[0] is seg[want[0]]
+        for k, orig in enumerate(want):
+            assert shard.get_class_index_image_by_index(k) is images[orig]
+    assert len(seg) == 3
+
+
 def test_find_argmax_matches_reference(golden_aggregate):
     a = golden_aggregate
     np.testing.assert_array_equal(gg.find_argmax_nonzero_value(a["avg1"]), a["argmax1"])
