@@ -4,16 +4,20 @@
 // (/root/reference/geograypher/meshes/meshes.py:1776-1836) and the PyTorch3D MeshRasterizer call of
 // TexturedPhotogrammetryMeshPyTorch3dRendering.pix2face (derived_meshes.py:691-737).
 //
-// Per batch of views (all kernels are batched over the views with blockIdx.y / blockIdx.z):
-//   k_cull_blocks   frustum-cull 128-face blocks by their bounding boxes          -> visible block list
-//   k_setup_faces   gather + project the 3 vertices of every face of a visible block (contract C1/C2),
-//                   reject faces that cover no pixel centre, emit a 48-byte record, count tiles
-//   k_scan_tiles    exclusive scan of the per-tile counts
-//   k_fill_bins     write record indices into per-tile lists
-//   k_raster_tiles  one CTA per 64x32-pixel tile: stage the tile's face records in shared memory, every
-//                   thread owns 8 consecutive pixels of one row and keeps (depth, face) in registers;
-//                   exact integer edge functions with top-left rule (C3), nearest 1/z wins, ties -> lowest
-//                   face ID (C4); writes int32 face IDs coalesced.
+// Per batch of up to 32 views (every kernel is batched over the views with blockIdx.y / blockIdx.z; the cameras travel
+// as a __grid_constant__ kernel parameter):
+//   k_reset_views   zero the per-tile counts and the counters of the batch's scratch slots
+//   k_cull_blocks   frustum-cull blocks of 128 consecutive (Z-ordered) faces by their bounding boxes -> visible blocks
+//   k_setup_faces   gather + project the 3 vertices of every face of a visible block (contract C1/C2), clip against the
+//                   near plane (C5: up to two triangles per face), reject faces that cover no pixel centre, emit a
+//                   128-byte record (edge equations, float64 1/z plane, tile mask), count the tiles it touches
+//   k_reserve_tiles warp-scan of the tile counts + one atomicAdd per warp reserves each tile's list (no global scan)
+//   k_fill_bins     one 64-byte tile-relative setup per (tile, face) pair, 8 lanes per record
+//   k_raster_tiles  one WARP per 32x8-pixel tile: streams the tile's setups through shared memory, every lane owns 8
+//                   consecutive pixels of one row and keeps (1/z, face, list position) in registers; exact integer
+//                   edge functions with top-left rule (C3), nearest 1/z wins, ties -> lowest face ID (C4).  Epilogues
+//                   by mode: face-ID / depth rasters, last pixel per face (fused last-pixel / vote aggregation),
+//                   dense per-pixel score sums, fused render_flat gather.
 // The result does not depend on the order in which faces land in a tile list, so the atomics used for
 // compaction do not make it non-deterministic.
 #include <cstring>
