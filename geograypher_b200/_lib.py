@@ -376,7 +376,7 @@ class Context:
                 self.sync(stream)
                 return
             except GeograypherB200Error as e:
-                # In the fused modes an overflowing batch accumulates nothing (k_resolve_recs bails out), so it can be
+                # In the fused modes an overflowing batch accumulates nothing (k_resolve_batch bails out), so it can be
                 # replayed after growing the scratch.  pixel_sum is not replayable.
                 if e.code != ERR_OVERFLOW or attempt == 3 or mode == MODE_PIXEL_SUM:
                     raise
