@@ -1227,6 +1227,11 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
         for (int i = 0; i < n; ++i) da.vec_ok &= ((uintptr_t)h_pred[i] % 16) == 0;
         const size_t elem = pred_kind == GG_PRED_F64 ? 8 : (pred_kind == GG_PRED_F32 ? 4 : 1);
         da.l2_prefetch = ctx->dense_prefetch && da.vec_ok && !da.index_kind && ((size_t)W * C * elem) % 16 == 0;
+        for (int i = 0; i < n && da.l2_prefetch; ++i) {  // only device memory is prefetched into L2
+            cudaPointerAttributes attr;
+            da.l2_prefetch = cudaPointerGetAttributes(&attr, h_pred[i]) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+        }
+        (void)cudaGetLastError();
         switch (pred_kind) {
             case GG_PRED_F32: return launch_dense<float>(ctx, cb, rgrid, n_tiles, d_pix2face, da, st);
             case GG_PRED_F64: return launch_dense<double>(ctx, cb, rgrid, n_tiles, d_pix2face, da, st);

@@ -58,6 +58,12 @@ if "c5" in sys.argv:
     d_sum.zero_(); d_count.zero_()
     ms = timeit(step, 10, ctx)
     ctx.sync()
+    ctx.profile(True)
+    for i in range(10):
+        step(i)
+    ctx.sync()
+    print("c5 stage ms per batch of", B, "views:", {k: round(v[0] / 10, 3) for k, v in ctx.profile_read().items() if v[1]})
+    ctx.profile(False)
     avg, amax = ctx.finalize(d_sum, d_count)
     print(f"c5 one-hot aggregation: {ms/B*1e3:.1f} us/view, {B/ms*1e3:.0f} views/s, {B/ms*1e3*W*H/1e9:.1f} Gpix/s; faces observed {(d_count>0).sum().item()}; mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB torch")
     # oracle spot check on one oblique rig camera

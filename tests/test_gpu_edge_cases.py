@@ -319,3 +319,22 @@ def test_prediction_images_in_pinned_host_memory(torch, lib, staging, monkeypatc
         np.testing.assert_array_equal(out[0][0], out[1][0])
         np.testing.assert_array_equal(out[0][1], out[1][1])
         assert out[0][1].sum() > 100
+
+
+def test_dense_mode_from_pinned_host_images(torch, lib):
+    """GG_MODE_PIXEL_SUM also accepts page-locked host images (every score then crosses PCIe: slow, but the same sums)."""
+    v32, faces, cams = _scene()
+    H, W, C, F = cams[0].H, cams[0].W, 4, len(faces)
+    gg_c = [_gg(lib, c) for c in cams]
+    ctx = _ctx(torch, lib, v32, faces)
+    rng = np.random.default_rng(4)
+    images = [rng.integers(0, 32, size=(H, W, C)).astype(np.float32) for _ in cams]
+    out = []
+    for preds in ([torch.from_numpy(a).cuda() for a in images], [torch.from_numpy(a).pin_memory() for a in images]):
+        d_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda")
+        d_count = torch.zeros((F,), dtype=torch.int32, device="cuda")
+        ctx.project_aggregate(gg_c, preds, lib.PRED_F32, C, lib.MODE_PIXEL_SUM, 0, d_sum, d_count)
+        ctx.sync()
+        out.append((d_sum.cpu().numpy(), d_count.cpu().numpy()))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
