@@ -730,7 +730,11 @@ class TexturedPhotogrammetryMesh:
                     # on the library's internal streams.  Queued predictions are kept alive until the next sync.
                     ctx.project_aggregate(gg, preds, kind, C, mode, flags, d_sum, d_count, check=False)
                     in_flight.append(preds)
-                    if (bi + 1) % window == 0:
+                    # Synchronise now and then: it bounds the device memory held by queued (uploaded) predictions and
+                    # surfaces a scratch overflow early.  Page-locked host images hold no device memory, so their
+                    # queue may run much deeper -- every synchronisation is a bubble in the pipeline.
+                    uploaded = sum(1 for b in in_flight for q in b if not isinstance(q, _HostMapped))
+                    if uploaded >= window * B or len(in_flight) >= 8 * window:
                         ctx.sync()
                         in_flight.clear()
                 ctx.sync()  # raises GG_ERR_OVERFLOW if any batch since the last sync outgrew the scratch
