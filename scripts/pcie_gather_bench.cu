@@ -61,7 +61,7 @@ __global__ void v4_vec16(const float *__restrict__ src, const int *__restrict__ 
     }
 }
 
-int main() {
+int main(int argc, char **argv) {
     const long long P = 19961856;
     const int n = 250000;
     float *h = nullptr;
@@ -69,20 +69,31 @@ int main() {
     for (long long i = 0; i < P * C; i += 1024) h[i] = (float)i;
     std::vector<int> pix(n);
     srand(1);
-    for (int v = 0; v < 10; ++v) {  // 10 views x 25k winners, each view sorted like the records of a Z-ordered mesh
+    const int order = argc > 1 ? atoi(argv[1]) : 0;  // 0: sorted by pixel, 1: random, 2: Z-order of 32x32-pixel cells
+    const int W = 5472;
+    for (int v = 0; v < 10; ++v) {  // 10 views x 25k winners
         std::vector<int> p(n / 10);
         for (auto &x : p) x = (int)(((long long)rand() * 32768 + rand()) % P);
-        std::sort(p.begin(), p.end());
+        if (order == 0) std::sort(p.begin(), p.end());
+        if (order == 2) {
+            auto key = [&](int q) {
+                unsigned x = (q % W) / 32, y = (q / W) / 32, k = 0;
+                for (int b = 0; b < 10; ++b) k |= ((x >> b) & 1u) << (2 * b) | ((y >> b) & 1u) << (2 * b + 1);
+                return k;
+            };
+            std::sort(p.begin(), p.end(), [&](int a, int b) { return key(a) < key(b); });
+        }
         std::copy(p.begin(), p.end(), pix.begin() + v * (n / 10));
     }
+    printf("order %d (0 sorted by pixel, 1 random, 2 Z-order of 32x32 cells)\n", order);
     int *d_pix; float *d_dst;
     CK(cudaMalloc(&d_pix, n * 4)); CK(cudaMalloc(&d_dst, (size_t)n * C * 4));
     CK(cudaMemcpy(d_pix, pix.data(), n * 4, cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    struct V { const char *name; int id; } vs[] = {{"v1 thread/element 4B", 1}, {"v2 thread/row 5x8B", 2}, {"v3 8 lanes/row full lines", 3}, {"v4 4 lanes/row 16B", 4}};
+    struct V { const char *name; int id; } vs[] = {{"v1 thread/element 4B", 1}, {"v4 4 lanes/row 16B", 4}};
     for (int rep = 0; rep < 2; ++rep)
         for (auto &v : vs) {
-            for (int blocks : {148 * 2, 148 * 8, 148 * 32}) {
+            for (int blocks : {148 * 8, 148 * 32}) {
                 CK(cudaMemset(d_dst, 0, (size_t)n * C * 4));
                 CK(cudaEventRecord(e0));
                 for (int it = 0; it < 5; ++it) {
