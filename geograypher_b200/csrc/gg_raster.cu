@@ -24,6 +24,13 @@
 
 #include "gg_internal.cuh"
 
+#ifndef GG_SETUP_MIN_BLOCKS
+#define GG_SETUP_MIN_BLOCKS 8  // 64 registers: the binning kernels are latency bound, occupancy matters more than spills
+#endif
+#ifndef GG_FILL_MIN_BLOCKS
+#define GG_FILL_MIN_BLOCKS 4
+#endif
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------------
@@ -333,7 +340,7 @@ __device__ __forceinline__ bool build_record(const Cam3 &qa, const Cam3 &qb, con
 // ------------------------------------------------------------------------------------------------------
 // Face setup: one thread per face of a visible block.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__restrict__ verts,
+__global__ void __launch_bounds__(GG_BLOCK_FACES, GG_SETUP_MIN_BLOCKS) k_setup_faces(const float4 *__restrict__ verts,
                                                                const int4 *__restrict__ faces, int64_t F,
                                                                int64_t cap_recs, int32_t *__restrict__ sticky,
                                                                const __grid_constant__ GGCamBatch cams,
@@ -403,12 +410,34 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES) k_setup_faces(const float4 *__
                     const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
                     unsigned long long tmask = 0;
                     const bool small = ntx * nty <= 64;
-                    for (int ty = ty0; ty <= ty1; ++ty)
-                        for (int tx = tx0; tx <= tx1; ++tx) {
-                            if (!tile_may_touch(r, tx, ty)) continue;
-                            atomicAdd(&vs.tile_count[ty * tiles_x + tx], 1);
-                            if (small) tmask |= 1ull << ((ty - ty0) * ntx + (tx - tx0));
+                    // tile_may_touch for every tile of the box, evaluated incrementally: the three edge functions at
+                    // each tile's innermost corner differ from tile to tile by constants (same int64 values)
+                    long long e_row[3], dex[3], dey[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int xc = tx0 * GG_TILE_W + (r.A[k] > 0 ? GG_TILE_W - 1 : 0);
+                        const int yc = ty0 * GG_TILE_H + (r.B[k] > 0 ? GG_TILE_H - 1 : 0);
+                        e_row[k] = r.C[k] + (long long)r.A[k] * GG_SUBPIX * xc + (long long)r.B[k] * GG_SUBPIX * yc;
+                        dex[k] = (long long)r.A[k] * (GG_SUBPIX * GG_TILE_W);
+                        dey[k] = (long long)r.B[k] * (GG_SUBPIX * GG_TILE_H);
+                    }
+                    int bit = 0;
+                    for (int ty = ty0; ty <= ty1; ++ty) {
+                        long long e0 = e_row[0], e1 = e_row[1], e2 = e_row[2];
+                        int32_t *row_count = vs.tile_count + ty * tiles_x;
+                        for (int tx = tx0; tx <= tx1; ++tx, ++bit) {
+                            if ((e0 | e1 | e2) >= 0) {
+                                atomicAdd(&row_count[tx], 1);
+                                if (small) tmask |= 1ull << bit;
+                            }
+                            e0 += dex[0];
+                            e1 += dex[1];
+                            e2 += dex[2];
                         }
+                        e_row[0] += dey[0];
+                        e_row[1] += dey[1];
+                        e_row[2] += dey[2];
+                    }
                     r.tmask = small ? tmask : ~0ull;
                     store_vec16(&vs.recs[idx], r);
                     if (r.face == (int32_t)(F - 1)) vs.counters[5] = idx;
@@ -490,7 +519,7 @@ __device__ __forceinline__ GGTileFace setup_tile_face(const GGFaceRec &r, int re
     return tf;
 }
 
-__global__ void __launch_bounds__(256) k_fill_bins(int64_t cap_bins, int32_t *__restrict__ sticky,
+__global__ void __launch_bounds__(256, GG_FILL_MIN_BLOCKS) k_fill_bins(int64_t cap_bins, int32_t *__restrict__ sticky,
                                                    const __grid_constant__ GGCamBatch cams,
                                                    const __grid_constant__ GGViewBatch views) {
     const int view = blockIdx.y;
