@@ -544,18 +544,16 @@ __global__ void __launch_bounds__(256, GG_FILL_MIN_BLOCKS) k_fill_bins(int64_t c
         const int ntx = tx1 - tx0 + 1;
         const unsigned long long tmask = rec.tmask;
         if (tmask != ~0ull) {
-            // lane `sub` takes the set bits number sub, sub + 8, ...: skip ahead first so that all lanes of the warp
-            // reach the (expensive) setup code together
-            unsigned long long m = tmask;
-            for (int s = 0; s < sub && m; ++s) m &= m - 1;
-            while (m) {
-                const int b = __ffsll((long long)m) - 1;
-                const int by = b / ntx;
+            // lane `sub` looks at bits sub, sub + 8, ... of the mask (a box of up to 64 tiles): no bit counting, and the
+            // 8 lanes of a record stay in step
+            const float inv_ntx = 1.0f / (float)ntx;
+            for (int b = sub; b < 64 && (tmask >> b) != 0; b += 8) {
+                if (!((tmask >> b) & 1ull)) continue;
+                const int by = (int)(((float)b + 0.5f) * inv_ntx);  // b / ntx, exact for these small integers
                 const int tx = tx0 + (b - by * ntx), ty = ty0 + by;
                 const int t = ty * tiles_x + tx;
                 store_vec16(&vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)],
                             setup_tile_face(rec, r, tx * GG_TILE_W, ty * GG_TILE_H));
-                for (int s = 0; s < 8 && m; ++s) m &= m - 1;
             }
         } else {
             const int total = ntx * (ty1 - ty0 + 1);
