@@ -57,7 +57,7 @@ struct GGCamBatch {  // passed by value as a __grid_constant__ kernel parameter 
 struct GGViewScratch {  // device pointers of one batch slot
     int32_t *vis_blocks;   // [n_blocks]
     GGFaceRec *recs;       // [cap_recs]
-    int32_t *tile_count;   // [n_tiles]   faces per tile (zeroed by the reserve pass, rebuilt by the fill pass)
+    int32_t *tile_count;   // [n_tiles]   faces per tile after setup; fill cursor (list start .. list end) afterwards
     int32_t *tile_offset;  // [n_tiles]   start of the tile's list in bins (lists are not in tile order)
     GGTileFace *bins;      // [cap_bins]  per-(tile, face) setups grouped by tile
     int32_t *winner;       // [F]  last (row-major) pixel won by each FACE in this view, -1 = none (fused aggregation)

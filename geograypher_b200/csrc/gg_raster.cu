@@ -452,8 +452,8 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES, GG_SETUP_MIN_BLOCKS) k_setup_f
 
 // ------------------------------------------------------------------------------------------------------
 // Reserve list space per tile.  Lists need not be stored in tile order, so instead of a scan every warp sums its
-// 32 counts and claims a range with one atomicAdd.  Zeroes tile_count for use as the fill cursor (the fill pass
-// brings it back to the list length).
+// 32 counts and claims a range with one atomicAdd.  tile_count becomes the fill pass's cursor (start of the list; the
+// fill pass leaves it at the end of the list).
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_reserve_tiles(int n_tiles, int64_t cap_recs,
                                                        const __grid_constant__ GGViewBatch views) {
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256) k_reserve_tiles(int n_tiles, int64_t cap_
     base = __shfl_sync(0xffffffffu, base, 31);
     if (t < n_tiles) {
         vs.tile_offset[t] = base + x - v;
-        vs.tile_count[t] = 0;
+        vs.tile_count[t] = base + x - v;  // the fill pass's cursor: absolute, so that one atomicAdd yields the slot
     }
 }
 
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(256, GG_FILL_MIN_BLOCKS) k_fill_bins(int64_t c
                 const int by = (int)(((float)b + 0.5f) * inv_ntx);  // b / ntx, exact for these small integers
                 const int tx = tx0 + (b - by * ntx), ty = ty0 + by;
                 const int t = ty * tiles_x + tx;
-                store_vec16(&vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)],
+                store_vec16(&vs.bins[atomicAdd(&vs.tile_count[t], 1)],
                             setup_tile_face(rec, r, tx * GG_TILE_W, ty * GG_TILE_H));
             }
         } else {
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(256, GG_FILL_MIN_BLOCKS) k_fill_bins(int64_t c
                 const int tx = tx0 + i % ntx, ty = ty0 + i / ntx;
                 if (!tile_may_touch(rec, tx, ty)) continue;
                 const int t = ty * tiles_x + tx;
-                store_vec16(&vs.bins[vs.tile_offset[t] + atomicAdd(&vs.tile_count[t], 1)],
+                store_vec16(&vs.bins[atomicAdd(&vs.tile_count[t], 1)],
                             setup_tile_face(rec, r, tx * GG_TILE_W, ty * GG_TILE_H));
             }
         }
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
 
     const bool overflow = vs.counters[3] != 0;
     const int beg = vs.tile_offset[tile];
-    const int len = overflow ? 0 : vs.tile_count[tile];
+    const int len = overflow ? 0 : vs.tile_count[tile] - beg;  // the fill cursor ends at the end of the list
 
     if (MODE == GG_RM_DENSE) {
         // The epilogue will stream this tile's scores: ask for them now (one bulk L2 prefetch per tile row, issued by
