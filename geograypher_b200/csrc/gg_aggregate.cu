@@ -346,6 +346,24 @@ int gg_launch_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W
     return GG_OK;
 }
 
+// The winner arrays are dense per face and only ~1.5 % of their entries are written per view: instead of clearing them
+// before every batch, whoever consumed a batch's winners puts the touched entries back to -1.  Runs also for a batch
+// that was voided by a scratch overflow (the views that did not overflow have written their winners).
+__global__ void __launch_bounds__(256) k_reset_winners(const __grid_constant__ GGViewBatch views, int64_t F, int flags) {
+    const GGViewScratch &vs = views.v[blockIdx.y];
+    const int n_recs = vs.counters[1];
+    const bool compat = (flags & GG_FLAG_COMPAT_NEG) != 0;
+    const int n = n_recs + (compat ? 1 : 0);
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+        vs.winner[r < n_recs ? (int64_t)vs.recs[r].face : F - 1] = -1;
+}
+
+static int launch_reset_winners(gg_context *ctx, int n, int flags, cudaStream_t st) {
+    GG_LAUNCH(ctx, GG_ST_RESOLVE, st,
+              k_reset_winners<<<dim3((unsigned)(ctx->sm_count * 2), n), 256, 0, st>>>(ctx->vset[ctx->cur], ctx->F, flags));
+    return GG_OK;
+}
+
 // ---- prediction images in (pinned) HOST memory ------------------------------------------------------------------
 // The fused last-pixel / vote aggregation needs one row per visible face.  When the images were left in page-locked
 // host memory the rows are fetched over PCIe: first ALL of them, in parallel, into a device staging table (one thread
@@ -488,7 +506,7 @@ int gg_launch_compact_winners(gg_context *ctx, int n, int flags, int32_t *d_pair
     GG_LAUNCH(ctx, GG_ST_RESOLVE, st,
               k_compact_winners<<<dim3((unsigned)(ctx->sm_count * 2), n), 256, 0, st>>>(ctx->vset[ctx->cur], n, ctx->F, flags,
                                                                                       d_pairs, cap, d_counts, ctx->d_sticky));
-    return GG_OK;
+    return launch_reset_winners(ctx, n, flags, st);
 }
 
 int gg_launch_accumulate_rows(gg_context *ctx, const int32_t *d_pairs, int64_t n_rows, const void *d_rows, int pred_kind,
@@ -505,8 +523,8 @@ int gg_launch_accumulate_rows(gg_context *ctx, const int32_t *d_pairs, int64_t n
     return GG_OK;
 }
 
-int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, int pred_kind, int C, int mode, int flags,
-                            double *d_sum, int32_t *d_count, cudaStream_t st) {
+static int resolve_batch_body(gg_context *ctx, int n, const void *const *h_pred, int pred_kind, int C, int mode, int flags,
+                              double *d_sum, int32_t *d_count, cudaStream_t st) {
     GGPredBatch pb;
     for (int i = 0; i < GG_MAX_VIEWS_PER_CALL; ++i) pb.p[i] = i < n ? h_pred[i] : nullptr;
     bool on_host = ctx->stage_host_rows != 0;
@@ -537,6 +555,13 @@ int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, i
         default: gg_set_error("gg_project_aggregate: bad pred_kind"); return GG_ERR_INVALID;
     }
     return GG_OK;
+}
+
+int gg_launch_resolve_batch(gg_context *ctx, int n, const void *const *h_pred, int pred_kind, int C, int mode, int flags,
+                            double *d_sum, int32_t *d_count, cudaStream_t st) {
+    const int rc = resolve_batch_body(ctx, n, h_pred, pred_kind, C, mode, flags, d_sum, d_count, st);
+    const int rc_reset = launch_reset_winners(ctx, n, flags, st);  // also when the body failed: the arrays must end clean
+    return rc != GG_OK ? rc : rc_reset;
 }
 
 int gg_launch_finalize(gg_context *ctx, double *d_sum, const int32_t *d_count, int64_t F, int C, double *d_avg,

@@ -1216,6 +1216,9 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
                 ctx->d_wdense = nullptr;
             }
             GG_CUDA(cudaMalloc(&ctx->d_wdense, (size_t)2 * n * ctx->F * 4));
+            // -1 = "not seen".  Set once: every consumer of a batch's winners (gg_launch_resolve_batch,
+            // gg_launch_compact_winners) puts back the entries the batch touched, which is ~1 % of a full clear.
+            GG_CUDA(cudaMemset(ctx->d_wdense, 0xFF, (size_t)2 * n * ctx->F * 4));
             ctx->wdense_cap = (int64_t)n * ctx->F;
         }
         for (int i = 0; i < n; ++i)
@@ -1239,8 +1242,6 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
         GG_CUDA(cudaStreamWaitEvent(st_ras, ctx->ev_bin[ctx->cur], 0));
     }
     st = st_ras;
-    if (want_winners)
-        GG_CUDA(cudaMemsetAsync(ctx->vset[ctx->cur].v[0].winner, 0xFF, (size_t)n * ctx->F * 4, st));
     const dim3 rgrid((tiles_x + GG_RASTER_WARPS - 1) / GG_RASTER_WARPS, tiles_y, n);
     GGDenseArgs da;
     memset(&da, 0, sizeof(da));
