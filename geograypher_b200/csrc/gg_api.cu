@@ -501,6 +501,18 @@ int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const 
         gg_set_error("gg_project_aggregate: raster larger than 2^31 pixels");
         return GG_ERR_INVALID;
     }
+    for (int i = 0; i < n; ++i) {  // the kernels dereference these: refuse what the GPU cannot read
+        cudaPointerAttributes attr;
+        const bool ok = h_pred[i] && cudaPointerGetAttributes(&attr, h_pred[i]) == cudaSuccess &&
+                        (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeHost ||
+                         attr.type == cudaMemoryTypeManaged);
+        (void)cudaGetLastError();
+        if (!ok) {
+            gg_set_error("gg_project_aggregate: prediction image is not in device or page-locked host memory "
+                         "(for pageable arrays use gg_project_winners + gg_accumulate_rows)");
+            return GG_ERR_INVALID;
+        }
+    }
     const bool fused = (mode == GG_MODE_LAST_PIXEL || mode == GG_MODE_VOTE) || (mode == GG_MODE_PIXEL_SUM && C <= 32);
     if (fused) {
         // Fused: the rasters never touch HBM unless the caller asked for them.  Last-pixel / vote: the rasterizer

@@ -338,3 +338,18 @@ def test_dense_mode_from_pinned_host_images(torch, lib):
         out.append((d_sum.cpu().numpy(), d_count.cpu().numpy()))
     np.testing.assert_array_equal(out[0][0], out[1][0])
     np.testing.assert_array_equal(out[0][1], out[1][1])
+
+
+def test_pageable_pointers_are_refused_by_the_fused_entry_point(torch, lib):
+    """The C entry point dereferences the prediction pointers on the GPU: a pageable host array must be an error, not
+    a crash (the Python API routes such arrays through gg_project_winners / gg_accumulate_rows)."""
+    v32, faces, cams = _scene()
+    H, W, C, F = cams[0].H, cams[0].W, 3, len(faces)
+    ctx = _ctx(torch, lib, v32, faces)
+    pageable = torch.zeros((H, W, C), dtype=torch.float32)  # ordinary host memory
+    d_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda")
+    d_count = torch.zeros((F,), dtype=torch.int32, device="cuda")
+    with pytest.raises(lib.GeograypherB200Error, match="page-locked"):
+        ctx.project_aggregate([_gg(lib, cams[0])], [pageable], lib.PRED_F32, C, lib.MODE_LAST_PIXEL, 0, d_sum, d_count)
+    ctx.sync()
+    assert int(d_count.sum()) == 0
