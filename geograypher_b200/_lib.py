@@ -30,6 +30,7 @@ EXPORTS = [
     "gg_project_aggregate", "gg_finalize", "gg_render_flat", "gg_stage_count", "gg_stage_name", "gg_profile",
     "gg_profile_read", "gg_drain", "gg_set_pipeline", "gg_build_warp_map", "gg_gather_i32",
     "gg_label_polygons", "gg_get_capacity", "gg_rasterize_render_flat", "gg_project_winners", "gg_accumulate_rows",
+    "gg_overflow_info",
 ]
 
 
@@ -92,6 +93,7 @@ def load():
     lib.gg_sync.argtypes = [vp, vp]
     lib.gg_reserve.argtypes = [vp, i64, i64]
     lib.gg_last_batch_stats.argtypes = [vp, i32, vp]
+    lib.gg_overflow_info.argtypes = [vp, vp]
     lib.gg_get_capacity.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
     lib.gg_set_mesh.argtypes = [vp, vp, i64, vp, i64, vp]
     lib.gg_project.argtypes = [vp, camp, i32, vp, vp, vp, vp, vp]
@@ -331,6 +333,8 @@ class Context:
         if out is None:
             out = t.empty((n, H, W), dtype=t.int32, device=self._dev())
         depth = t.empty((n, H, W), dtype=t.float32, device=self._dev()) if want_depth else None
+        if check:
+            self.sync(stream)  # an overflow left behind by earlier unchecked batches belongs to them: raise it now
         for attempt in range(4):
             _check(self.lib.gg_rasterize(self.handle, self._cam_array(cams), n, out.data_ptr(),
                                          depth.data_ptr() if depth is not None else None, _stream_ptr(stream)))
@@ -345,15 +349,27 @@ class Context:
                 self._grow_after_overflow(n)
         return (out, depth) if want_depth else out
 
-    def _grow_after_overflow(self, n):
-        stats = self.last_batch_stats(n)
-        recs, bins = ctypes.c_int64(), ctypes.c_int64()
-        _check(self.lib.gg_get_capacity(self.handle, ctypes.byref(recs), ctypes.byref(bins)))
-        # counters keep counting past the capacity, so they tell how much the last batch needed; an earlier batch may
-        # have been the one that overflowed, hence at least a doubling
-        need_recs = max(int(stats[:, 1].max() * 1.5) + 4096, 2 * recs.value if stats[:, 1].max() >= recs.value else recs.value)
-        need_bins = max(int(stats[:, 2].max() * 1.5) + 4096, 2 * bins.value)
-        self.reserve(need_recs, need_bins)
+    def overflow_info(self):
+        """(flags, face records wanted, tile entries wanted) found by the last sync() that raised ERR_OVERFLOW, over
+        every batch enqueued since the sync before it."""
+        out = np.zeros(3, dtype=np.int64)
+        _check(self.lib.gg_overflow_info(self.handle, out.ctypes.data))
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def _grow_after_overflow(self, n=None):
+        """Grow what overflowed -- and only that -- after a sync() raised ERR_OVERFLOW.  The sizes come from the
+        high-water marks the kernels keep over ALL batches since the previous sync (the overflowing batch is usually
+        not the last one); each grown capacity at least doubles, so a few attempts always suffice.  Records dropped
+        by a face-record overflow were never binned, so the tile-entry mark may still be too low: the caller's retry
+        loop covers that."""
+        del n
+        flags, want_recs, want_bins = self.overflow_info()
+        recs, bins = self.get_capacity()
+        new_recs = max(int(want_recs * 1.25) + 4096, 2 * recs) if flags & 1 else recs
+        new_bins = max(int(want_bins * 1.25) + 4096, 2 * bins) if flags & 2 else bins
+        if not flags & 3:  # no information (should not happen): fall back to doubling both
+            new_recs, new_bins = 2 * recs, 2 * bins
+        self.reserve(min(new_recs, max(self.n_faces * 2, 1)), new_bins)
 
     # -- stage 3 -------------------------------------------------------------------------------------------
     def aggregate(self, pix2face, pred, pred_kind, C, mode, flags, d_sum, d_count, stream=None):
@@ -365,6 +381,8 @@ class Context:
                           stream=None, check=True):
         n = len(cams)
         ptrs = (ctypes.c_void_p * n)(*[p.data_ptr() for p in preds])
+        if check:
+            self.sync(stream)  # see rasterize()
         for attempt in range(4):
             _check(self.lib.gg_project_aggregate(self.handle, self._cam_array(cams), n, ptrs, pred_kind, C, mode,
                                                  flags, d_sum.data_ptr(), d_count.data_ptr(),
@@ -424,6 +442,8 @@ class Context:
         dt = {OUT_F64: t.float64, OUT_F32: t.float32, OUT_U8: t.uint8}[out_dtype]
         if out is None:
             out = t.empty((n, H, W, D), dtype=dt, device=self._dev())
+        if check:
+            self.sync(stream)  # see rasterize()
         for attempt in range(4):
             _check(self.lib.gg_rasterize_render_flat(self.handle, self._cam_array(cams), n, face_tex64.data_ptr(), D,
                                                      out.data_ptr(), out_dtype,

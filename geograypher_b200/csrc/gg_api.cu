@@ -210,8 +210,8 @@ int gg_create(int device, gg_context **out) {
     memset(ctx->vset, 0, sizeof(ctx->vset));
     if (const char *e = getenv("GG_DENSE_PREFETCH")) ctx->dense_prefetch = atoi(e) != 0;
     if (const char *e = getenv("GG_STAGE_HOST_ROWS")) ctx->stage_host_rows = atoi(e) != 0;
-    GG_CUDA(cudaMalloc(&ctx->d_sticky, sizeof(int32_t)));
-    GG_CUDA(cudaMemset(ctx->d_sticky, 0, sizeof(int32_t)));
+    GG_CUDA(cudaMalloc(&ctx->d_sticky, 4 * sizeof(int32_t)));
+    GG_CUDA(cudaMemset(ctx->d_sticky, 0, 4 * sizeof(int32_t)));
     // the short, latency-bound binning kernels get the higher priority so that they slip in between the CTAs of the
     // rasterizer that is still running for the previous batch
     int prio_lo = 0, prio_hi = 0;
@@ -269,10 +269,14 @@ int gg_sync(gg_context *ctx, void *stream) {
     ctx->ras_pending[0] = ctx->ras_pending[1] = false;
     GG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     GG_CUDA(cudaGetLastError());
-    int32_t sticky = 0;
-    GG_CUDA(cudaMemcpy(&sticky, ctx->d_sticky, sizeof(sticky), cudaMemcpyDeviceToHost));
+    int32_t st4[4] = {0, 0, 0, 0};
+    GG_CUDA(cudaMemcpy(st4, ctx->d_sticky, sizeof(st4), cudaMemcpyDeviceToHost));
+    if (st4[1] != 0 || st4[2] != 0 || st4[0] != 0) GG_CUDA(cudaMemset(ctx->d_sticky, 0, 4 * sizeof(int32_t)));
+    const int32_t sticky = st4[0];
     if (sticky != 0) {
-        GG_CUDA(cudaMemset(ctx->d_sticky, 0, sizeof(int32_t)));
+        ctx->last_overflow[0] = sticky;
+        ctx->last_overflow[1] = st4[1];
+        ctx->last_overflow[2] = st4[2];
         char buf[320];
         snprintf(buf, sizeof(buf),
                  "scratch overflow since the last gg_sync (%s%s; capacity: %lld face records, %lld tile entries per "
@@ -357,6 +361,17 @@ int gg_get_capacity(gg_context *ctx, int64_t *h_faces_per_view, int64_t *h_bin_e
     return GG_OK;
 }
 
+int gg_overflow_info(gg_context *ctx, int64_t *h_out3) {
+    int rc = check_ctx(ctx, false);
+    if (rc != GG_OK) return rc;
+    if (!h_out3) {
+        gg_set_error("gg_overflow_info: null output");
+        return GG_ERR_INVALID;
+    }
+    for (int i = 0; i < 3; ++i) h_out3[i] = ctx->last_overflow[i];
+    return GG_OK;
+}
+
 int gg_last_batch_stats(gg_context *ctx, int n, int64_t *h_out) {
     int rc = check_ctx(ctx, false);
     if (rc != GG_OK) return rc;
@@ -387,6 +402,14 @@ int gg_set_mesh(gg_context *ctx, const float *d_verts, int64_t V, const int32_t 
     cudaFree(ctx->d_block_hi);
     cudaFree(ctx->d_winner);
     cudaFree(ctx->d_wdense);
+    // the scratch slots are laid out for THIS mesh (visible-block lists are sized by its block count): start over
+    cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    ctx->n_slots = 0;
+    ctx->slot_tiles = 0;
+    ctx->cap_recs = ctx->cap_bins = 0;
+    ctx->ras_pending[0] = ctx->ras_pending[1] = false;
     ctx->d_wdense = nullptr;
     ctx->wdense_cap = 0;
     ctx->d_verts = nullptr;

@@ -138,7 +138,9 @@ struct gg_context {
     int stage_host_rows = 1;      // GG_STAGE_HOST_ROWS=0: resolve reads the host images directly
     int32_t *d_raster = nullptr;  // internal n x H x W raster when the caller does not want pix2face back
     int64_t raster_cap = 0;
-    int32_t *d_sticky = nullptr;  // OR of the overflow flags of every batch since the last gg_sync
+    int32_t *d_sticky = nullptr;  // [4] since the last gg_sync: OR of the batches' overflow flags, most face records any
+                                  // view wanted, most tile entries any view wanted, unused
+    int64_t last_overflow[3] = {0, 0, 0};  // what the last failing gg_sync read from d_sticky (gg_overflow_info)
     int last_batch_n = 0;
     int sm_count = 148;
 };

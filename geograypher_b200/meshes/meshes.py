@@ -346,11 +346,15 @@ class TexturedPhotogrammetryMesh:
             return [cameras]
         return list(cameras.cameras)
 
-    def _gg_cameras(self, cam_list, local: LocalMesh, scale: float):
+    def _gg_cameras(self, cam_list, local: LocalMesh, scale: float, warp_follows: bool = False):
+        """``warp_follows``: the raster will be pushed through the lens model afterwards.  The Metashape model takes an
+        ideal raster centred at (W/2, H/2) and adds cx, cy itself (derived_cameras.py:171-208; the reference warps
+        only the pyvista render, which has no principal point, cameras.py:449), so the principal point must not be
+        applied twice."""
         sizes = {c.get_image_size(scale) for c in cam_list}
         if len(sizes) != 1:
             raise ValueError("Not all cameras have the same image size")  # derived_meshes.py:811-813
-        pp = 1.0 if self.use_principal_point else 0.0
+        pp = 1.0 if (self.use_principal_point and not warp_follows) else 0.0
         return [
             _lib.make_camera(c.world_to_cam_transform, c.f, pp * c.cx, pp * c.cy, c.image_width, c.image_height,
                              render_img_scale=scale, origin=local.origin)
@@ -366,14 +370,16 @@ class TexturedPhotogrammetryMesh:
     # ------------------------------------------------------------------------------------------------
     # pix2face
     # ------------------------------------------------------------------------------------------------
-    def pix2face_device(self, cameras, mesh: LocalMesh = None, render_img_scale: float = 1, out=None):
-        """pix2face as an (n, h, w) int32 CUDA tensor (-1 = no face); no host round trip."""
+    def pix2face_device(self, cameras, mesh: LocalMesh = None, render_img_scale: float = 1, out=None,
+                        warp_follows: bool = False):
+        """pix2face as an (n, h, w) int32 CUDA tensor (-1 = no face); no host round trip.  ``warp_follows``: see
+        ``_gg_cameras``."""
         import torch
 
         if mesh is None:
             mesh = self.get_mesh_in_cameras_coords(cameras)
         cam_list = self._camera_list(cameras)
-        gg = self._gg_cameras(cam_list, mesh, render_img_scale)
+        gg = self._gg_cameras(cam_list, mesh, render_img_scale, warp_follows=warp_follows)
         n, H, W = len(gg), gg[0].H, gg[0].W
         if out is None:
             out = torch.empty((n, H, W), dtype=torch.int32, device=torch.device("cuda", self.device))
@@ -409,7 +415,7 @@ class TexturedPhotogrammetryMesh:
             apply_distortion = False
 
         single = isinstance(cameras, PhotogrammetryCamera) or not hasattr(cameras, "cameras")
-        p2f = self.pix2face_device(cameras, mesh=mesh, render_img_scale=render_img_scale)
+        p2f = self.pix2face_device(cameras, mesh=mesh, render_img_scale=render_img_scale, warp_follows=apply_distortion)
         if apply_distortion:
             p2f = self._warp_device(p2f, self._camera_list(cameras), distortion_set, render_img_scale)
         p2f = p2f.to(dtype=__import__("torch").int64).cpu().numpy()
@@ -463,7 +469,7 @@ class TexturedPhotogrammetryMesh:
         if isinstance(cameras, PhotogrammetryCamera):
             cameras = PhotogrammetryCameraSet([cameras])
         elif not self._is_camera_or_set(cameras) or not hasattr(cameras, "cameras"):
-            raise TypeError()
+            raise TypeError("cameras must be a PhotogrammetryCamera or a PhotogrammetryCameraSet")
         apply_distortion = pix2face_kwargs.get("apply_distortion", True)
         distortion_set = pix2face_kwargs.get("distortion_set", None)
         if distortion_set is None and apply_distortion:
@@ -534,8 +540,9 @@ class TexturedPhotogrammetryMesh:
 
         apply_distortion = pix2face_kwargs.get("apply_distortion", True)
         distortion_set = pix2face_kwargs.get("distortion_set", None)
-        p2f = self.pix2face_device(cameras, mesh=mesh, render_img_scale=scale)
-        if distortion_set is None or not apply_distortion:
+        warp = distortion_set is not None and apply_distortion
+        p2f = self.pix2face_device(cameras, mesh=mesh, render_img_scale=scale, warp_follows=warp)
+        if not warp:
             return p2f
         return self._warp_device(p2f, self._camera_list(cameras), distortion_set, scale)
 
@@ -743,10 +750,25 @@ class TexturedPhotogrammetryMesh:
                 # An overflowing batch is skipped as a whole, so the accumulators are consistent but incomplete: grow
                 # the scratch and redo the aggregation.
                 if e.code != _lib.ERR_OVERFLOW or attempt == 3:
+                    self._quiesce(ctx)
                     raise
-                ctx._grow_after_overflow(min(B, n))
+                ctx._grow_after_overflow()
                 C = n_channels
+            except BaseException:
+                # queued batches still read the prediction tensors and write d_sum / d_count on the library's own
+                # streams: they must finish before those tensors go back to torch's allocator
+                self._quiesce(ctx)
+                raise
         return d_sum, d_count, C
+
+    @staticmethod
+    def _quiesce(ctx):
+        """Wait for everything the context has in flight; a pending overflow report is dropped (the caller is
+        already unwinding with another error)."""
+        try:
+            ctx.sync()
+        except _lib.GeograypherB200Error:
+            pass
 
     def aggregate_projected_images(self, cameras, batch_size: int = 1, aggregate_img_scale: float = 1,
                                    return_all: bool = False, return_argmax: bool = False, **kwargs):

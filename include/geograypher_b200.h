@@ -99,6 +99,10 @@ int gg_get_capacity(gg_context *ctx, int64_t *h_faces_per_view, int64_t *h_bin_e
 /* Counters of the most recent rasterization batch, valid after gg_sync: per view [n_visible_blocks,
    n_face_records, n_bin_entries, overflow_flag].  out must hold 4*n int64. */
 int gg_last_batch_stats(gg_context *ctx, int n, int64_t *h_out);
+/* What the most recent gg_sync that returned GG_ERR_OVERFLOW found, over ALL batches enqueued since the sync before
+   it (the batch that overflowed is usually not the last one): h_out3 = [flags (1 = face records, 2 = tile entries),
+   most face records any view wanted, most tile entries any view wanted].  Grow only what overflowed. */
+int gg_overflow_info(gg_context *ctx, int64_t *h_out3);
 
 /* ---- instrumentation: every kernel launch is counted per stage; with gg_profile(ctx, 1) each launch is also
         bracketed by CUDA events on its stream.  gg_profile_read synchronises the device and returns the

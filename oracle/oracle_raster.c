@@ -30,7 +30,7 @@
  * (tests/test_derived_meshes.py:23-76, tests/test_derived_cameras.py:339-415) in
  * tests/test_oracle_reference_pins.py.
  *
- * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC).
+ * Build: see oracle/Makefile (gcc -O3 -march=native -ffp-contract=off -fopenmp -shared -fPIC).
  * -ffp-contract=off is REQUIRED: contract C1 forbids fused multiply-add in the projection.
  */
 #include <math.h>
@@ -180,14 +180,15 @@ static void raster_tri(const float *pa, const float *pb, const float *pc, int32_
     const int64_t A2 = -(y0 - y2), B2 = (x0 - x2);
     const int inc0 = edge_inclusive(A0, B0), inc1 = edge_inclusive(A1, B1), inc2 = edge_inclusive(A2, B2);
     const double inv_area = 1.0 / (double)area2;
+    const int64_t dE0 = A0 * ORA_SUBPIX, dE1 = A1 * ORA_SUBPIX, dE2 = A2 * ORA_SUBPIX; /* step per pixel along a row */
     for (int64_t i = imin; i <= imax; ++i) {
         const int64_t Py = ORA_SUBPIX * i + ORA_HALF;
-        for (int64_t j = jmin; j <= jmax; ++j) {
-            const int64_t Px = ORA_SUBPIX * j + ORA_HALF;
-            const int64_t E0 = B0 * (Py - y0) + A0 * (Px - x0);
-            const int64_t E1 = B1 * (Py - y1) + A1 * (Px - x1);
-            const int64_t E2 = B2 * (Py - y2) + A2 * (Px - x2);
-            if (E0 < 0 || E1 < 0 || E2 < 0) continue;
+        const int64_t Px0 = ORA_SUBPIX * jmin + ORA_HALF;
+        int64_t E0 = B0 * (Py - y0) + A0 * (Px0 - x0); /* exact integers: stepping them is exact too */
+        int64_t E1 = B1 * (Py - y1) + A1 * (Px0 - x1);
+        int64_t E2 = B2 * (Py - y2) + A2 * (Px0 - x2);
+        for (int64_t j = jmin; j <= jmax; ++j, E0 += dE0, E1 += dE1, E2 += dE2) {
+            if ((E0 | E1 | E2) < 0) continue;
             if ((E0 == 0 && !inc0) || (E1 == 0 && !inc1) || (E2 == 0 && !inc2)) continue;
             /* barycentric weights: E1 -> v0, E2 -> v1, E0 -> v2 */
             const double w = ((double)E1 * w0 + (double)E2 * w1 + (double)E0 * w2) * inv_area;
@@ -203,80 +204,178 @@ static void raster_tri(const float *pa, const float *pb, const float *pc, int32_
     }
 }
 
+/* Up to two camera-space sub-triangles of face fi after clipping against z = znear (contract C5).  Returns their
+ * number (0: dropped).  tri[t][k] points to 3 floats; clipped points live in buf. */
+static int face_subtris(const float *PC, const int32_t *faces, int64_t V, int64_t fi, float znear,
+                        const float *tri[2][3], float buf[4][3]) {
+    const int32_t idx[3] = {faces[3 * fi], faces[3 * fi + 1], faces[3 * fi + 2]};
+    if (idx[0] < 0 || idx[1] < 0 || idx[2] < 0 || idx[0] >= V || idx[1] >= V || idx[2] >= V) return 0;
+    const float *p[3] = {PC + 3 * (size_t)idx[0], PC + 3 * (size_t)idx[1], PC + 3 * (size_t)idx[2]};
+    int front[3], nfront = 0, finite = 1;
+    for (int k = 0; k < 3; ++k) {
+        finite = finite && isfinite(p[k][0]) && isfinite(p[k][1]) && isfinite(p[k][2]);
+        front[k] = p[k][2] >= znear;
+        nfront += front[k];
+    }
+    if (!finite || nfront == 0) return 0;
+    if (nfront == 3) {
+        tri[0][0] = p[0];
+        tri[0][1] = p[1];
+        tri[0][2] = p[2];
+        return 1;
+    }
+    if (nfront == 1) { /* C5: rotate so that the vertex in front comes first: (A, B, C) */
+        const int a = front[0] ? 0 : (front[1] ? 1 : 2);
+        const float *A = p[a], *B = p[(a + 1) % 3], *C = p[(a + 2) % 3];
+        clip_edge(A, B, znear, buf[0]);
+        clip_edge(A, C, znear, buf[1]);
+        tri[0][0] = A;
+        tri[0][1] = buf[0];
+        tri[0][2] = buf[1];
+        return 1;
+    }
+    /* two in front: rotate so that the vertex behind comes last: (A, B, C) */
+    const int c = !front[0] ? 0 : (!front[1] ? 1 : 2);
+    const float *A = p[(c + 1) % 3], *B = p[(c + 2) % 3], *C = p[c];
+    clip_edge(B, C, znear, buf[2]);
+    clip_edge(A, C, znear, buf[3]);
+    tri[0][0] = A;
+    tri[0][1] = B;
+    tri[0][2] = buf[2];
+    tri[1][0] = A;
+    tri[1][1] = buf[2];
+    tri[1][2] = buf[3];
+    return 2;
+}
+
+/* Rows [*i0, *i1] whose pixel centres a sub-triangle can cover (the same arithmetic as raster_tri's bounding box);
+ * returns 0 when it cannot cover any pixel centre of the W x H raster. */
+static int subtri_rows(const float *pa, const float *pb, const float *pc, const ora_camera *cam, int *i0, int *i1) {
+    int32_t X[3], Y[3];
+    float IZ[3];
+    if (!to_screen(pa, cam, &X[0], &Y[0], &IZ[0]) || !to_screen(pb, cam, &X[1], &Y[1], &IZ[1]) ||
+        !to_screen(pc, cam, &X[2], &Y[2], &IZ[2]))
+        return 0;
+    int64_t xmin = X[0], xmax = X[0], ymin = Y[0], ymax = Y[0];
+    for (int k = 1; k < 3; ++k) {
+        if (X[k] < xmin) xmin = X[k];
+        if (X[k] > xmax) xmax = X[k];
+        if (Y[k] < ymin) ymin = Y[k];
+        if (Y[k] > ymax) ymax = Y[k];
+    }
+    int64_t jmin = floordiv(xmin - ORA_HALF + ORA_SUBPIX - 1, ORA_SUBPIX), jmax = floordiv(xmax - ORA_HALF, ORA_SUBPIX);
+    int64_t imin = floordiv(ymin - ORA_HALF + ORA_SUBPIX - 1, ORA_SUBPIX), imax = floordiv(ymax - ORA_HALF, ORA_SUBPIX);
+    if (jmin < 0) jmin = 0;
+    if (jmax > cam->W - 1) jmax = cam->W - 1;
+    if (imin < 0) imin = 0;
+    if (imax > cam->H - 1) imax = cam->H - 1;
+    if (jmin > jmax || imin > imax) return 0;
+    *i0 = (int)imin;
+    *i1 = (int)imax;
+    return 1;
+}
+
 /*
  * Rasterize one view.
  *   pix2face : H*W int32, -1 = no face                                  (required)
  *   depth_w  : H*W double, best 1/z_cam (0 where no face)               (optional)
  *   margin   : H*W double, (w_best - w_second)/w_best, 1 if no runner-up (optional; contract: a pixel is
  *              "depth-safe" iff margin > eps_depth)
- * Faces are visited in increasing ID inside every row band.
+ * The raster is cut into row bands (one per task); every band visits, in increasing face ID, the faces whose rows
+ * reach into it (a per-view culling pass lists them), so the total work does not grow with the number of threads.
  */
 void ora_rasterize(const float *verts, int64_t V, const int32_t *faces, int64_t F, const ora_camera *cam,
                    int32_t *pix2face, double *depth_w, double *margin, int nthreads) {
     const int W = cam->W, H = cam->H;
-    float *PC = (float *)malloc(sizeof(float) * 3 * (size_t)V); /* camera-space vertices */
+    float *PC = (float *)malloc(sizeof(float) * 3 * (size_t)(V > 0 ? V : 1)); /* camera-space vertices */
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < V; ++i) cam_space(verts + 3 * i, cam, PC + 3 * i);
 
     const size_t P = (size_t)W * (size_t)H;
     double *wbest = (double *)malloc(sizeof(double) * P);
     double *wsecond = margin ? (double *)malloc(sizeof(double) * P) : NULL;
-    for (size_t p = 0; p < P; ++p) {
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < (int64_t)P; ++p) {
         pix2face[p] = -1;
         wbest[p] = 0.0;
+        if (wsecond) wsecond[p] = 0.0;
     }
-    if (wsecond) memset(wsecond, 0, sizeof(double) * P);
 
 #ifdef _OPENMP
     if (nthreads <= 0) nthreads = omp_get_max_threads();
 #else
     nthreads = 1;
 #endif
-    int nbands = nthreads * 4;
+    int nbands = nthreads * 8;
     if (nbands > H) nbands = H;
     if (nbands < 1) nbands = 1;
     const float znear = cam->znear;
+
+    /* culling pass: first / last band of every face (-1: the face covers no pixel centre) */
+    int32_t *b0 = (int32_t *)malloc(sizeof(int32_t) * (size_t)(F > 0 ? F : 1));
+    int32_t *b1 = (int32_t *)malloc(sizeof(int32_t) * (size_t)(F > 0 ? F : 1));
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t fi = 0; fi < F; ++fi) {
+        const float *tri[2][3];
+        float buf[4][3];
+        const int nt = face_subtris(PC, faces, V, fi, znear, tri, buf);
+        int lo = H, hi = -1;
+        for (int t = 0; t < nt; ++t) {
+            int i0, i1;
+            if (subtri_rows(tri[t][0], tri[t][1], tri[t][2], cam, &i0, &i1)) {
+                if (i0 < lo) lo = i0;
+                if (i1 > hi) hi = i1;
+            }
+        }
+        if (hi < 0) {
+            b0[fi] = b1[fi] = -1;
+        } else { /* band of row r = the b with H*b/nbands <= r < H*(b+1)/nbands */
+            int ba = (int)(((int64_t)lo * nbands) / H), bb = (int)(((int64_t)hi * nbands) / H);
+            while (ba > 0 && (int64_t)H * ba / nbands > lo) --ba;
+            while (ba + 1 < nbands && (int64_t)H * (ba + 1) / nbands <= lo) ++ba;
+            while (bb > 0 && (int64_t)H * bb / nbands > hi) --bb;
+            while (bb + 1 < nbands && (int64_t)H * (bb + 1) / nbands <= hi) ++bb;
+            b0[fi] = ba;
+            b1[fi] = bb;
+        }
+    }
+    /* per-band face lists in increasing face ID (counting sort; the fill is a single ordered sweep) */
+    int64_t *start = (int64_t *)calloc((size_t)nbands + 1, sizeof(int64_t));
+    for (int64_t fi = 0; fi < F; ++fi)
+        if (b0[fi] >= 0)
+            for (int b = b0[fi]; b <= b1[fi]; ++b) start[b + 1] += 1;
+    for (int b = 0; b < nbands; ++b) start[b + 1] += start[b];
+    int32_t *list = (int32_t *)malloc(sizeof(int32_t) * (size_t)(start[nbands] > 0 ? start[nbands] : 1));
+    int64_t *cursor = (int64_t *)malloc(sizeof(int64_t) * (size_t)nbands);
+    for (int b = 0; b < nbands; ++b) cursor[b] = start[b];
+    for (int64_t fi = 0; fi < F; ++fi)
+        if (b0[fi] >= 0)
+            for (int b = b0[fi]; b <= b1[fi]; ++b) list[cursor[b]++] = (int32_t)fi;
 
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
     for (int band = 0; band < nbands; ++band) {
         const int r0 = (int)((int64_t)H * band / nbands);
         const int r1 = (int)((int64_t)H * (band + 1) / nbands);
-        for (int64_t fi = 0; fi < F; ++fi) {
-            const int32_t idx[3] = {faces[3 * fi], faces[3 * fi + 1], faces[3 * fi + 2]};
-            if (idx[0] < 0 || idx[1] < 0 || idx[2] < 0 || idx[0] >= V || idx[1] >= V || idx[2] >= V) continue;
-            const float *p[3] = {PC + 3 * (size_t)idx[0], PC + 3 * (size_t)idx[1], PC + 3 * (size_t)idx[2]};
-            int front[3], nfront = 0, finite = 1;
-            for (int k = 0; k < 3; ++k) {
-                finite = finite && isfinite(p[k][0]) && isfinite(p[k][1]) && isfinite(p[k][2]);
-                front[k] = p[k][2] >= znear;
-                nfront += front[k];
-            }
-            if (!finite || nfront == 0) continue;
-            if (nfront == 3) {
-                raster_tri(p[0], p[1], p[2], (int32_t)fi, cam, r0, r1, pix2face, wbest, wsecond);
-            } else if (nfront == 1) { /* C5: rotate so that the vertex in front comes first: (A, B, C) */
-                const int a = front[0] ? 0 : (front[1] ? 1 : 2);
-                const float *A = p[a], *B = p[(a + 1) % 3], *C = p[(a + 2) % 3];
-                float rab[3], rac[3];
-                clip_edge(A, B, znear, rab);
-                clip_edge(A, C, znear, rac);
-                raster_tri(A, rab, rac, (int32_t)fi, cam, r0, r1, pix2face, wbest, wsecond);
-            } else { /* two in front: rotate so that the vertex behind comes last: (A, B, C) */
-                const int c = !front[0] ? 0 : (!front[1] ? 1 : 2);
-                const float *A = p[(c + 1) % 3], *B = p[(c + 2) % 3], *C = p[c];
-                float rbc[3], rac[3];
-                clip_edge(B, C, znear, rbc);
-                clip_edge(A, C, znear, rac);
-                raster_tri(A, B, rbc, (int32_t)fi, cam, r0, r1, pix2face, wbest, wsecond);
-                raster_tri(A, rbc, rac, (int32_t)fi, cam, r0, r1, pix2face, wbest, wsecond);
-            }
+        for (int64_t q = start[band]; q < start[band + 1]; ++q) {
+            const int64_t fi = list[q];
+            const float *tri[2][3];
+            float buf[4][3];
+            const int nt = face_subtris(PC, faces, V, fi, znear, tri, buf);
+            for (int t = 0; t < nt; ++t)
+                raster_tri(tri[t][0], tri[t][1], tri[t][2], (int32_t)fi, cam, r0, r1, pix2face, wbest, wsecond);
         }
     }
     if (depth_w) memcpy(depth_w, wbest, sizeof(double) * P);
     if (margin) {
-        for (size_t p = 0; p < P; ++p)
+#pragma omp parallel for schedule(static)
+        for (int64_t p = 0; p < (int64_t)P; ++p)
             margin[p] = (pix2face[p] >= 0) ? (wbest[p] - wsecond[p]) / wbest[p] : 1.0;
     }
+    free(cursor);
+    free(list);
+    free(start);
+    free(b0);
+    free(b1);
     free(wbest);
     if (wsecond) free(wsecond);
     free(PC);

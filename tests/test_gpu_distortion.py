@@ -134,7 +134,14 @@ def test_aggregation_with_distortion(cams, golden_scene, golden_aggregate):
     p = dict(f=f, cx=cx, cy=cy, image_width=W, image_height=H, **dp)
     rows, cols = ora.exact_inverse_coordinates(p, 1.0)
     src = ora.nearest_source_index(rows, cols, H, W)
-    warped = np.stack([ora.warp_ids(g["pix2face"][k].astype(np.int64), src, fill=-1) for k in range(len(cam_list))])
+    # The lens model takes an IDEAL raster centred at (W/2, H/2) and adds cx, cy itself (reference
+    # derived_cameras.py:171-208; the reference warps only the pyvista render, which has no principal point): the
+    # expected value is the oracle raster with cx = cy = 0, warped through the model WITH cx, cy.  (The golden raster
+    # was made with the principal point and must differ, or this test could not see a double application.)
+    v32 = (g["verts"] - g["origin"]).astype(np.float32)
+    ideal = [ora.rasterize(v32, g["faces"], ora.make_camera(T, f, 0.0, 0.0, W, H, origin=g["origin"])) for T in g["c2ws"]]
+    assert any((ideal[k] != g["pix2face"][k]).any() for k in range(len(cam_list)))
+    warped = np.stack([ora.warp_ids(ideal[k].astype(np.int64), src, fill=-1) for k in range(len(cam_list))])
     ref_avg, ref_cnt, ref_sum = ora.aggregate(warped, a["soft"], len(g["faces"]))
     np.testing.assert_array_equal(mesh.pix2face(cams, distortion_set=cams, apply_distortion=True), warped)
     np.testing.assert_array_equal(avg, ref_avg)

@@ -1,7 +1,8 @@
-"""Full-size checks (BASELINE.json configurations c2 and c5) through properties that need no CPU oracle: the oracle
-cannot rasterize 20-Mpx views of a 2M-face mesh in test time, but the path's own invariants can be checked with plain
-torch ops on the GPU.
+"""Full-size checks (BASELINE.json configurations c2 and c5).
 
+  * pix2face at full size against the CPU oracle (a 20-Mpx view of the 2M-face mesh takes the oracle a fraction of a
+    second per view on the box's host cores, a 45-Mpx view of the 20M-face mesh a few seconds): c2 views including
+    ones at the edge of the mesh, c5 nadir + oblique rig views -- every pixel, depth-margin mask as everywhere else;
   * the reference's aggregation rule restated with torch scatter ops on the full-size rasters (last pixel of every
     face, row-major: meshes.py:2001; NaN -> 0 and count of finite rows: meshes.py:2057-2067) -- bit-exact;
   * ID round trip: render_flat of the texture "face f has value f" gives back pix2face (meshes.py:1921-1937);
@@ -12,10 +13,12 @@ import numpy as np
 import pytest
 
 from geograypher_b200 import synthetic as syn
+from oracle import oracle as ora
 
 pytestmark = pytest.mark.gpu
 
 N_VIEWS = 6
+EPS_DEPTH = 1e-5  # the contract's depth-margin mask
 
 
 @pytest.fixture(scope="module")
@@ -33,14 +36,37 @@ def lib():
     return _lib
 
 
+_HOST = {}  # name -> (float32 vertices, faces, [cam_to_world], origin) kept for the oracle comparisons
+
+
 def _build(torch, lib, name, n_cams):
     verts, faces, c2ws, cfg = syn.make_survey(name, n_cams)
     origin = 0.5 * (verts.min(0) + verts.max(0))
     W, H = cfg.image_size
+    v32 = (verts - origin).astype(np.float32)
     ctx = lib.Context(0)
-    ctx.set_mesh(torch.from_numpy((verts - origin).astype(np.float32)).cuda(), torch.from_numpy(faces).cuda())
+    ctx.set_mesh(torch.from_numpy(v32).cuda(), torch.from_numpy(faces).cuda())
     cams = [lib.make_camera(np.linalg.inv(T), cfg.f, cfg.cx, cfg.cy, W, H, origin=origin) for T in c2ws]
+    _HOST[name] = (v32, faces, c2ws, origin)
     return ctx, cams, cfg, len(faces)
+
+
+def _assert_matches_oracle(name, cfg, view, gpu_ids, label):
+    """Every pixel of one full-size view against the oracle; IDs may differ only inside the depth-margin mask."""
+    v32, faces, c2ws, origin = _HOST[name]
+    W, H = cfg.image_size
+    cam = ora.make_camera(c2ws[view], cfg.f, cfg.cx, cfg.cy, W, H, origin=origin)
+    ref, _, margin = ora.rasterize(v32, faces, cam, want_depth=True, want_margin=True)
+    gpu = gpu_ids.cpu().numpy()
+    assert gpu.shape == ref.shape == (H, W)
+    diff = gpu != ref
+    bad = diff & (margin > EPS_DEPTH)
+    assert not bad.any(), (f"{label}: {int(bad.sum())} pixels differ outside the depth-margin mask (first at "
+                           f"{np.argwhere(bad)[0]}, gpu={gpu[bad][0]}, oracle={ref[bad][0]})")
+    masked = int((margin <= EPS_DEPTH).sum())
+    assert masked < 1e-3 * ref.size, f"{label}: {masked} pixels inside the depth-margin mask"
+    assert (ref >= 0).mean() > 0.3  # the view does look at the mesh
+    return int(diff.sum()), masked
 
 
 @pytest.fixture(scope="module")
@@ -50,6 +76,14 @@ def c2(torch, lib):
     p2f = ctx.rasterize(cams)  # (n, H, W) int32
     assert tuple(p2f.shape) == (N_VIEWS, H, W) == (N_VIEWS, 3648, 5472) and F == 2_000_000
     return ctx, cams, cfg, F, p2f
+
+
+@pytest.mark.parametrize("view", [0, 3, 5])
+def test_c2_pix2face_matches_the_oracle_at_full_size(c2, view):
+    """5472 x 3648 rasters of the 2M-face canopy mesh, every pixel: 171 x 456 tile grids, > 30 k face records per
+    view, 32-bit fast-path edge values at full scale.  View 0 sits at the corner of the mesh (background pixels)."""
+    _, _, cfg, _, p2f = c2
+    _assert_matches_oracle("c2", cfg, view, p2f[view], f"c2 view {view}")
 
 
 def _last_pixel(torch, ids, F):
@@ -178,9 +212,24 @@ def test_c2_dense_mode_checksums(torch, lib, c2):
     assert torch.equal(c1.long(), torch.bincount(ids[keep], minlength=F))
 
 
-def test_c5_votes_equal_the_reference_rule(torch, lib):
+@pytest.fixture(scope="module")
+def c5(torch, lib):
+    return _build(torch, lib, "c5", 5)  # station 0 of the rig: nadir + four obliques pitched 30 degrees
+
+
+@pytest.mark.parametrize("view", [0, 2])
+def test_c5_pix2face_matches_the_oracle_at_full_size(torch, c5, view):
+    """8192 x 5460 rasters of the 20M-face mesh: the nadir camera of a rig station and one of its obliques (long
+    tile lists towards the far end of the footprint)."""
+    ctx, cams, cfg, F = c5
+    p2f = ctx.rasterize([cams[view]])
+    _assert_matches_oracle("c5", cfg, view, p2f[0], f"c5 view {view}")
+
+
+def test_c5_votes_equal_the_reference_rule(torch, lib, c5):
     """20M faces, 8192 x 5460 rig views, class-index images with ignore values: one-hot votes per face."""
-    ctx, cams, cfg, F = _build(torch, lib, "c5", 3)
+    ctx, cams, cfg, F = c5
+    cams = cams[:3]
     W, H = cfg.image_size
     C = cfg.n_classes
     assert (W, H) == (8192, 5460) and F > 19_000_000

@@ -385,3 +385,76 @@ def test_pipelined_batches_equal_serial(torch, lib):
         results.append((avg.clone(), d_count.clone(), argmax.clone()))
     for a, b in zip(*results):
         assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+
+
+def test_overflow_in_an_earlier_batch_grows_the_right_capacity(torch, lib):
+    """the batch that overflows is usually not the last one before the sync.  Batch 1 (wide view: many
+    face records) overflows a small record capacity, batch 2 (a camera that sees a handful of faces) does not; the
+    high-water marks kept over ALL batches since the previous sync must drive the growth (records only: the tile
+    capacity is not touched), and the API-level retry must end with the unconstrained result."""
+    v32, faces, cams, cfg = _scene("c1", 2)
+    W, H = cfg.image_size
+    F, C = len(faces), cfg.n_classes
+    gg = [_to_gg(lib, c) for c in cams]
+    far = lib.GGCamera()  # same camera, looking at a corner: sees almost nothing
+    for k in range(12):
+        far.m[k] = gg[0].m[k]
+    far.f, far.px, far.py, far.W, far.H, far.znear = gg[0].f * 40, gg[0].px, gg[0].py, W, H, gg[0].znear
+    idx = [torch.from_numpy(syn.class_index_image(k, H, W, C)).cuda() for k in range(2)]
+    ctx = _context(torch, lib, v32, faces)
+    ref_sum = torch.zeros((F, C), dtype=torch.float64, device="cuda")
+    ref_cnt = torch.zeros((F,), dtype=torch.int32, device="cuda")
+    ctx.project_aggregate([gg[0]], idx[:1], lib.PRED_INDEX_U8, C, lib.MODE_LAST_PIXEL, 0, ref_sum, ref_cnt)
+    ctx.project_aggregate([far], idx[1:], lib.PRED_INDEX_U8, C, lib.MODE_LAST_PIXEL, 0, ref_sum, ref_cnt)
+    need = int(ctx.last_batch_stats(1)[0, 1])
+    small = _context(torch, lib, v32, faces)
+    small.reserve(2000, 0)
+    d_sum, d_cnt = torch.zeros_like(ref_sum), torch.zeros_like(ref_cnt)
+    small.project_aggregate([gg[0]], idx[:1], lib.PRED_INDEX_U8, C, lib.MODE_LAST_PIXEL, 0, d_sum, d_cnt, check=False)
+    small.project_aggregate([far], idx[1:], lib.PRED_INDEX_U8, C, lib.MODE_LAST_PIXEL, 0, d_sum, d_cnt, check=False)
+    with pytest.raises(lib.GeograypherB200Error, match="overflow"):
+        small.sync()
+    flags, want_recs, _ = small.overflow_info()
+    assert flags == 1 and want_recs > 2000 and want_recs >= need
+    bins_before = small.get_capacity()[1]
+    small._grow_after_overflow()
+    d_sum.zero_()
+    d_cnt.zero_()
+    small.project_aggregate([gg[0]], idx[:1], lib.PRED_INDEX_U8, C, lib.MODE_LAST_PIXEL, 0, d_sum, d_cnt, check=False)
+    small.project_aggregate([far], idx[1:], lib.PRED_INDEX_U8, C, lib.MODE_LAST_PIXEL, 0, d_sum, d_cnt, check=False)
+    small.sync()  # one growth step was enough
+    assert small.get_capacity()[0] >= want_recs and small.get_capacity()[1] == bins_before
+    assert torch.equal(d_sum, ref_sum) and torch.equal(d_cnt, ref_cnt)
+
+
+def test_checked_call_reports_an_earlier_unchecked_overflow(torch, lib):
+    """a checked call must not swallow (and then replay only itself after) an overflow that an earlier
+    unchecked batch raised: it raises it before doing anything."""
+    v32, faces, cams, cfg = _scene("c1", 1)
+    gg = [_to_gg(lib, c) for c in cams]
+    small = _context(torch, lib, v32, faces)
+    small.reserve(0, 1000)
+    out = torch.empty((1, cfg.image_size[1], cfg.image_size[0]), dtype=torch.int32, device="cuda")
+    small.rasterize(gg, out=out, check=False)  # overflows, unnoticed
+    with pytest.raises(lib.GeograypherB200Error, match="overflow"):
+        small.rasterize(gg, out=out)
+    small._grow_after_overflow()
+    ref = _context(torch, lib, v32, faces).rasterize(gg)
+    assert torch.equal(small.rasterize(gg), ref)
+
+
+def test_set_mesh_again_with_a_larger_mesh(torch, lib):
+    """the scratch slots are laid out for a mesh's block count; a second gg_set_mesh with a larger mesh
+    (same record capacity class) must start the scratch over instead of writing past the visible-block lists."""
+    small_v, small_f, _, _ = _scene("tiny", 1)
+    v32, faces, cams, cfg = _scene("c1", 2)
+    gg = [_to_gg(lib, c) for c in cams]
+    ctx = _context(torch, lib, small_v, small_f)
+    tcams = [_to_gg(lib, c) for c in _scene("tiny", 1)[2]]
+    ctx.reserve(4096, 1 << 20)  # the same explicit capacities before and after: only the block count changes
+    ctx.rasterize(tcams)
+    ctx.set_mesh(torch.from_numpy(v32).cuda(), torch.from_numpy(faces.astype(np.int32)).cuda())
+    ctx.reserve(1 << 17, 1 << 20)
+    got = ctx.rasterize(gg)
+    ref = _context(torch, lib, v32, faces).rasterize(gg)
+    assert torch.equal(got, ref)
