@@ -660,27 +660,19 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
 
     __shared__ GGTileFace s_all[GG_RASTER_WARPS][GG_CHUNK];
     __shared__ int s_win_all[WINNERS ? GG_RASTER_WARPS : 1][GG_CHUNK];
-    __shared__ int s_rface_all[GG_RASTER_WARPS][GG_CHUNK];       // face ID of the r-th setup of an ordered tile
-    __shared__ unsigned char s_rank_all[GG_RASTER_WARPS][GG_CHUNK];  // list index of the r-th setup
     GGTileFace *s_faces = s_all[warp];
     int *s_win = s_win_all[WINNERS ? warp : 0];  // last pixel won by the first GG_CHUNK list positions
-    int *s_rface = s_rface_all[warp];
-    unsigned char *s_rank = s_rank_all[warp];
 
     const int tx0 = (lane & 3) * 8;  // this lane: pixels tx0..tx0+7 of row ty
     const int ty = lane >> 2;
 
-    // Per pixel: the winner's 1/z (> 0; 0 = none) and its position in the tile's list (-1 = none).
-    //  * Tiles whose list fits one chunk (almost all of them) are ORDERED: the warp ranks the setups by face ID
-    //    while staging them, so faces are visited in increasing ID and "strictly nearer replaces" IS the
-    //    lowest-ID tie-break of contract C4 (the rule of the oracle's loop) -- no face ID in the per-pixel state.
-    //  * Longer lists keep the face ID per pixel: (1/z bits, ~face) compared as one 64-bit unsigned integer.
-    float kw[8];
-    unsigned kf[8];
+    // Per pixel: the winner's key (bits of its 1/z, which is positive -> ordered like the float; then ~face so that the
+    // lower ID wins a tie) compared as ONE 64-bit unsigned integer, and its position in the tile's list (-1 = none).
+    unsigned kw[8], kf[8];
     int bp[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        kw[i] = 0.f;
+        kw[i] = 0u;
         kf[i] = 0u;  // ~(-1)
         bp[i] = -1;
     }
@@ -690,7 +682,6 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
     const bool overflow = vs.counters[3] != 0;
     const int beg = vs.tile_offset[tile];
     const int len = overflow ? 0 : vs.tile_count[tile] - beg;  // the fill cursor ends at the end of the list
-    const bool ordered = len <= GG_CHUNK;
 
     if (MODE == GG_RM_DENSE) {
         // The epilogue will stream this tile's scores: ask for them now (one bulk L2 prefetch per tile row, issued by
@@ -719,28 +710,11 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
             }
         }
         __syncwarp();
-        if (ordered) {
-            // rank of every setup among the tile's face IDs (a clipped face may appear twice: list order decides);
-            // s_rank[r] = list index of the setup with rank r, s_rface[r] = its face ID
-            const int myf = s_faces[lane < n ? lane : 0].face;
-            int rank = 0;
-#pragma unroll 2
-            for (int j = 0; j < n; ++j)  // (fj, j) < (myf, lane) lexicographically
-                rank += (s_faces[j].face < myf + (j < lane ? 1 : 0)) ? 1 : 0;
-            if (lane < n) {
-                s_rank[rank] = (unsigned char)lane;
-                s_rface[rank] = myf;
-            }
-            __syncwarp();
-        }
-        int k_next = ordered ? (int)s_rank[0] : 0;
-        for (int r = 0; r < n; ++r) {
-            const int k = k_next;  // the index of the next setup is fetched one iteration ahead
-            k_next = ordered ? (int)s_rank[r + 1 < n ? r + 1 : r] : r + 1;
+        for (int k = 0; k < n; ++k) {
             const int4 q3 = *reinterpret_cast<const int4 *>(&s_faces[k].lanemask);  // lanemask face rec fast
             if (!((((unsigned)q3.x) >> lane) & 1u)) continue;
             const unsigned nface = ~(unsigned)q3.y;
-            const int pos = base + r;  // ordered tiles: the rank
+            const int pos = base + k;
             if (q3.w) {
                 const int4 q0 = *reinterpret_cast<const int4 *>(&s_faces[k].e[0]);   // e0 e1 e2 sx0
                 const int4 q1 = *reinterpret_cast<const int4 *>(&s_faces[k].sx[1]);  // sx1 sx2 sy0 sy1
@@ -751,45 +725,28 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
                 int e2 = q0.z + s2 * tx0 + q2.x * ty;
                 const float gx = __int_as_float(q2.z);
                 const float wrow = fmaf(gx, ftx0, fmaf(__int_as_float(q2.w), fty, __int_as_float(q2.y)));
-                if (ordered) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {  // branch-free: selects cost less than the divergence bookkeeping
-                        const float w = fmaf(gx, (float)i, wrow);
-                        const bool upd = ((e0 | e1 | e2) >= 0) & (w > kw[i]);
-                        kw[i] = upd ? w : kw[i];
-                        bp[i] = upd ? pos : bp[i];
-                        e0 += s0;
-                        e1 += s1;
-                        e2 += s2;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float w = fmaf(gx, (float)i, wrow);
-                        const unsigned wb = __float_as_uint(w);
-                        const bool upd = ((e0 | e1 | e2) >= 0) & (w > 0.f) &
-                                         ((((unsigned long long)wb << 32) | nface) >
-                                          (((unsigned long long)__float_as_uint(kw[i]) << 32) | kf[i]));
-                        kw[i] = upd ? w : kw[i];
-                        kf[i] = upd ? nface : kf[i];
-                        bp[i] = upd ? pos : bp[i];
-                        e0 += s0;
-                        e1 += s1;
-                        e2 += s2;
-                    }
+                for (int i = 0; i < 8; ++i) {  // branch-free: selects cost less than the divergence bookkeeping
+                    const float w = fmaf(gx, (float)i, wrow);
+                    const unsigned wb = __float_as_uint(w);
+                    const bool upd = ((e0 | e1 | e2) >= 0) &
+                                     ((((unsigned long long)wb << 32) | nface) > (((unsigned long long)kw[i] << 32) | kf[i]));
+                    kw[i] = upd ? wb : kw[i];
+                    kf[i] = upd ? nface : kf[i];
+                    bp[i] = upd ? pos : bp[i];
+                    e0 += s0;
+                    e1 += s1;
+                    e2 += s2;
                 }
             } else {
                 const GGFaceRec &r = vs.recs[q3.z];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {  // unrolled so that the per-pixel state stays in registers
+                for (int i = 0; i < 8; ++i) {  // unrolled so that bw / bf / br stay in registers
                     float w;
                     if (exact_cover(r, tile_x0 + tx0 + i, tile_y0 + ty, w) && w > 0.f) {
                         const unsigned wb = __float_as_uint(w);
-                        const bool upd = ordered ? (w > kw[i])
-                                                 : ((((unsigned long long)wb << 32) | nface) >
-                                                    (((unsigned long long)__float_as_uint(kw[i]) << 32) | kf[i]));
-                        if (upd) {
-                            kw[i] = w;
+                        if ((((unsigned long long)wb << 32) | nface) > (((unsigned long long)kw[i] << 32) | kf[i])) {
+                            kw[i] = wb;
                             kf[i] = nface;
                             bp[i] = pos;
                         }
@@ -804,8 +761,8 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
     int bf[8];  // 1/z and face ID of the winners, -1 = none
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        bw[i] = kw[i];
-        bf[i] = ordered ? (bp[i] >= 0 ? s_rface[bp[i]] : -1) : (int)~kf[i];
+        bw[i] = __uint_as_float(kw[i]);
+        bf[i] = (int)~kf[i];
     }
 
     // ---- write the 8 pixels of this lane ----
@@ -876,7 +833,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
         __syncwarp();
         if (lane < len) {  // len > GG_CHUNK: the first chunk's setups were overwritten, fetch the face ID again
             const int p = s_win[lane];
-            if (p >= 0) atomicMax(&vs.winner[len <= GG_CHUNK ? s_rface[lane] : vs.bins[beg + lane].face], p);
+            if (p >= 0) atomicMax(&vs.winner[len <= GG_CHUNK ? s_faces[lane].face : vs.bins[beg + lane].face], p);
         }
         if (compat_bg) {  // meshes.py:2000: background pixels index the last face
             bgmax = __reduce_max_sync(0xffffffffu, bgmax);
@@ -1107,7 +1064,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
                 float total = 0.f;
                 for (int q = 0; q < g_all; ++q) total += s_acc[k * kSlots + q * C + cch];
                 if (n_px > 0) {
-                    const int64_t face = len <= GG_CHUNK ? s_rface[k] : vs.bins[beg + k].face;
+                    const int64_t face = len <= GG_CHUNK ? s_faces[k].face : vs.bins[beg + k].face;
                     if (cch == 0) atomicAdd(&dense.count[face], n_px);
                     if (CT > 0 && fast && !(fabsf(total) <= 3.0e38f)) redo |= 1u << it;
                     else atomicAdd(&dense.sum[face * C + cch], (double)total);
@@ -1125,7 +1082,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
                 const int k = idx / C, cch = idx - k * C;
                 float total = 0.f;
                 for (int q = 0; q < g_all; ++q) total += s_acc[k * kSlots + q * C + cch];
-                const int64_t face = len <= GG_CHUNK ? s_rface[k] : vs.bins[beg + k].face;
+                const int64_t face = len <= GG_CHUNK ? s_faces[k].face : vs.bins[beg + k].face;
                 atomicAdd(&dense.sum[face * C + cch], (double)total);
             }
         }

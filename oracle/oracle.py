@@ -48,8 +48,11 @@ class OraCamera(ctypes.Structure):
 def build(force: bool = False) -> Path:
     """Compile oracle_raster.c with the committed Makefile (gcc, -ffp-contract=off, OpenMP)."""
     so = _HERE / "liboracle_raster.so"
-    src = _HERE / "oracle_raster.c"
-    if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+    stale = force
+    for name in ("oracle_raster", "oracle_raycast"):
+        lib, src = _HERE / f"lib{name}.so", _HERE / f"{name}.c"
+        stale = stale or not lib.exists() or lib.stat().st_mtime < src.stat().st_mtime
+    if stale:
         subprocess.run(["make", "-C", str(_HERE), "-B"], check=True, capture_output=True)
     return so
 
@@ -185,6 +188,34 @@ def rasterize(verts32, faces, cam: OraCamera, want_depth=False, want_margin=Fals
     if want_depth or want_margin:
         return p2f, depth, margin
     return p2f
+
+
+_RAYCAST = None
+
+
+def raycast(verts32, faces, cam: OraCamera, eps_edge: float = 2.0**-7, nthreads=0):
+    """The INDEPENDENT second oracle (oracle_raycast.c): per-pixel-centre ray casting in float64 camera space
+    (Moeller-Trumbore), no snapping / edge functions / fill rule.  Returns ``(pix2face int64 (H, W), edge_safe bool,
+    depth_margin float64)``: ``edge_safe`` is False where a silhouette or shared edge passes within ``eps_edge`` px
+    of the pixel centre (the four corner rays of that square disagree with the centre ray)."""
+    global _RAYCAST
+    if _RAYCAST is None:
+        build()
+        lib = ctypes.CDLL(str(_HERE / "liboracle_raycast.so"))
+        lib.orc_raycast.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                    ctypes.POINTER(OraCamera), ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_int]
+        lib.orc_raycast.restype = None
+        _RAYCAST = lib
+    verts32 = np.ascontiguousarray(verts32, dtype=np.float32)
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    H, W = int(cam.H), int(cam.W)
+    ids = np.empty((H, W), np.int32)
+    safe = np.empty((H, W), np.uint8)
+    margin = np.empty((H, W), np.float64)
+    _RAYCAST.orc_raycast(verts32.ctypes.data, verts32.shape[0], faces.ctypes.data, faces.shape[0], ctypes.byref(cam),
+                         float(eps_edge), ids.ctypes.data, safe.ctypes.data, margin.ctypes.data, int(nthreads))
+    return ids.astype(np.int64), safe.astype(bool), margin
 
 
 # --------------------------------------------------------------------------------------------------
