@@ -369,42 +369,57 @@ static int launch_reset_winners(gg_context *ctx, int n, int flags, cudaStream_t 
 // host memory the rows are fetched over PCIe: first ALL of them, in parallel, into a device staging table (one thread
 // per element, so a warp's loads of one row share their sectors), then k_resolve_batch walks the views in order on
 // the staged copy.  The winners are re-pointed from pixel indices to staging rows in between.
+// The fetch is bound by the PCIe link's small-read rate (~0.3 G rows/s), not by the SMs: a few hundred rows in flight
+// keep the link busy.  So the kernel is a SMALL persistent grid (GG_STAGE_CTAS CTAs per SM, default 4, of 256 threads
+// and <= 32 registers: one CTA fits in the slot of one rasterizer CTA) that walks all (view, record) pairs of the
+// batch; launched on the high-priority resolve stream it slips into the first slots the rasterizer of the NEXT batch
+// frees and then runs beside it instead of time-slicing the machine with it.  A group of e_pad lanes fetches one
+// row, so the loads of a row share their sectors.  The lane that owns element 0 re-points the face's winner from the
+// pixel index to the staging row (nobody else reads this view's winner of this face before k_resolve_batch).
 template <typename T>
-__global__ void __launch_bounds__(256) k_stage_rows(const __grid_constant__ GGViewBatch views, int n_views, int64_t F,
-                                                    const __grid_constant__ GGPredBatch preds, int E, int flags,
-                                                    T *__restrict__ stage, int64_t rows_per_view) {
+__global__ void __launch_bounds__(256, 8) k_stage_rows(const __grid_constant__ GGViewBatch views, int n_views, int64_t F,
+                                                       const __grid_constant__ GGPredBatch preds, int E, int flags,
+                                                       T *__restrict__ stage, int64_t rows_per_view) {
     for (int v = 0; v < n_views; ++v)
         if (views.v[v].counters[3] != 0) return;
-    const int view = blockIdx.y;
-    const GGViewScratch &vs = views.v[view];
-    const int n_recs = vs.counters[1];
     const bool compat = (flags & GG_FLAG_COMPAT_NEG) != 0;
-    const int n = n_recs + ((compat && vs.counters[5] < 0) ? 1 : 0);
-    const T *__restrict__ pred = (const T *)preds.p[view];
-    T *__restrict__ out = stage + (int64_t)view * rows_per_view * E;
-    // block = (elements of a row padded to a power of two) x (rows): no index division, a row's loads sit in
-    // neighbouring lanes and share their sectors
-    for (int r = blockIdx.x * blockDim.y + threadIdx.y; r < n; r += gridDim.x * blockDim.y) {
-        if (r < n_recs && vs.recs[r].dup) continue;
-        const int64_t f = r < n_recs ? (int64_t)vs.recs[r].face : F - 1;
-        const int p = vs.winner[f];
-        if (p < 0) continue;
-        for (int e = threadIdx.x; e < E; e += blockDim.x) out[(int64_t)r * E + e] = pred[(int64_t)p * E + e];
-    }
-}
-
-__global__ void __launch_bounds__(256) k_stage_commit(const __grid_constant__ GGViewBatch views, int n_views, int64_t F,
-                                                      int flags) {
-    for (int v = 0; v < n_views; ++v)
-        if (views.v[v].counters[3] != 0) return;
-    const GGViewScratch &vs = views.v[blockIdx.y];
-    const int n_recs = vs.counters[1];
-    const bool compat = (flags & GG_FLAG_COMPAT_NEG) != 0;
-    const int n = n_recs + ((compat && vs.counters[5] < 0) ? 1 : 0);
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        if (r < n_recs && vs.recs[r].dup) continue;
-        const int64_t f = r < n_recs ? (int64_t)vs.recs[r].face : F - 1;
-        if (vs.winner[f] >= 0) vs.winner[f] = r;
+    const int rows_per_pass = gridDim.x * blockDim.y;
+    for (int view = 0; view < n_views; ++view) {
+        const GGViewScratch &vs = views.v[view];
+        const int n_recs = vs.counters[1];
+        const int n = n_recs + ((compat && vs.counters[5] < 0) ? 1 : 0);
+        const T *__restrict__ pred = (const T *)preds.p[view];
+        T *__restrict__ out = stage + (int64_t)view * rows_per_view * E;
+        // two rows per group and pass: their PCIe reads overlap
+        for (int r0 = blockIdx.x * blockDim.y + threadIdx.y; r0 < n; r0 += 2 * rows_per_pass) {
+            int rr[2] = {r0, r0 + rows_per_pass};
+            int pp[2] = {-1, -1};
+            int64_t ff[2] = {0, 0};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int r = rr[u];
+                if (r >= n) continue;
+                if (r < n_recs && vs.recs[r].dup) continue;
+                ff[u] = r < n_recs ? (int64_t)vs.recs[r].face : F - 1;
+                pp[u] = vs.winner[ff[u]];
+            }
+            T val[2][2];
+            const int e0 = threadIdx.x, e1 = threadIdx.x + blockDim.x;  // E <= 2 * blockDim.x (E <= 64)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (pp[u] < 0) continue;
+                if (e0 < E) val[u][0] = pred[(int64_t)pp[u] * E + e0];
+                if (e1 < E) val[u][1] = pred[(int64_t)pp[u] * E + e1];
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (pp[u] < 0) continue;
+                if (e0 < E) out[(int64_t)rr[u] * E + e0] = val[u][0];
+                if (e1 < E) out[(int64_t)rr[u] * E + e1] = val[u][1];
+                for (int e = e1 + blockDim.x; e < E; e += blockDim.x) out[(int64_t)rr[u] * E + e] = pred[(int64_t)pp[u] * E + e];
+                if (threadIdx.x == 0) vs.winner[ff[u]] = rr[u];
+            }
+        }
     }
 }
 
@@ -424,11 +439,9 @@ static int stage_host_rows(gg_context *ctx, int n, GGPredBatch &pb, int E, int f
     T *stage = (T *)ctx->d_stage;
     int e_pad = 1;
     while (e_pad < E && e_pad < 32) e_pad <<= 1;
-    const dim3 g((unsigned)(ctx->sm_count * 8), n), b(e_pad, 256 / e_pad);
-    GG_LAUNCH(ctx, GG_ST_RESOLVE, st,
+    const dim3 g((unsigned)(ctx->sm_count * ctx->stage_ctas)), b(e_pad, 256 / e_pad);
+    GG_LAUNCH(ctx, GG_ST_STAGE, st,
               k_stage_rows<T><<<g, b, 0, st>>>(ctx->vset[ctx->cur], n, ctx->F, pb, E, flags, stage, rows_per_view));
-    GG_LAUNCH(ctx, GG_ST_RESOLVE, st,
-              k_stage_commit<<<dim3((unsigned)(ctx->sm_count * 2), n), 256, 0, st>>>(ctx->vset[ctx->cur], n, ctx->F, flags));
     for (int i = 0; i < n; ++i) pb.p[i] = stage + (int64_t)i * rows_per_view * E;
     return GG_OK;
 }

@@ -210,6 +210,7 @@ int gg_create(int device, gg_context **out) {
     memset(ctx->vset, 0, sizeof(ctx->vset));
     if (const char *e = getenv("GG_DENSE_PREFETCH")) ctx->dense_prefetch = atoi(e) != 0;
     if (const char *e = getenv("GG_STAGE_HOST_ROWS")) ctx->stage_host_rows = atoi(e) != 0;
+    if (const char *e = getenv("GG_STAGE_CTAS")) ctx->stage_ctas = atoi(e) > 0 ? atoi(e) : 1;
     GG_CUDA(cudaMalloc(&ctx->d_sticky, 4 * sizeof(int32_t)));
     GG_CUDA(cudaMemset(ctx->d_sticky, 0, 4 * sizeof(int32_t)));
     // the short, latency-bound binning kernels get the higher priority so that they slip in between the CTAs of the
@@ -291,7 +292,7 @@ int gg_sync(gg_context *ctx, void *stream) {
 
 static const char *k_stage_names[GG_ST_COUNT] = {"mesh_setup", "project", "cull_blocks", "setup_faces", "scan_tiles",
                                                    "fill_bins", "raster_tiles", "last_pixel", "resolve", "pixel_sum",
-                                                   "finalize", "render_flat", "misc"};
+                                                   "finalize", "render_flat", "misc", "stage_host_rows"};
 
 int gg_stage_count(void) { return GG_ST_COUNT; }
 

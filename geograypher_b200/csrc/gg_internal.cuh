@@ -76,7 +76,7 @@ struct GGPredBatch {  // device pointers of the views' prediction images
 // ---- per-stage launch counting and (optional) CUDA-event timing ------------------------------------------
 enum GGStage {
     GG_ST_MESH = 0, GG_ST_PROJECT, GG_ST_CULL, GG_ST_SETUP, GG_ST_SCAN, GG_ST_FILL, GG_ST_RASTER, GG_ST_LAST_PIXEL,
-    GG_ST_RESOLVE, GG_ST_PIXEL_SUM, GG_ST_FINALIZE, GG_ST_RENDER_FLAT, GG_ST_MISC, GG_ST_COUNT
+    GG_ST_RESOLVE, GG_ST_PIXEL_SUM, GG_ST_FINALIZE, GG_ST_RENDER_FLAT, GG_ST_MISC, GG_ST_STAGE, GG_ST_COUNT
 };
 
 struct GGProfPending {
@@ -136,6 +136,7 @@ struct gg_context {
     char *d_stage = nullptr;      // rows fetched from prediction images that live in host memory
     size_t stage_bytes = 0;
     int stage_host_rows = 1;      // GG_STAGE_HOST_ROWS=0: resolve reads the host images directly
+    int stage_ctas = 4;           // CTAs per SM of the host-row fetch kernel (GG_STAGE_CTAS)
     int32_t *d_raster = nullptr;  // internal n x H x W raster when the caller does not want pix2face back
     int64_t raster_cap = 0;
     int32_t *d_sticky = nullptr;  // [4] since the last gg_sync: OR of the batches' overflow flags, most face records any
