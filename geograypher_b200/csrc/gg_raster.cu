@@ -667,13 +667,15 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
     const int ty = lane >> 2;
 
     // Per pixel: the winner's key (bits of its 1/z, which is positive -> ordered like the float; then ~face so that the
-    // lower ID wins a tie) compared as ONE 64-bit unsigned integer, and its position in the tile's list (-1 = none).
-    unsigned kw[8], kf[8];
+    // lower ID wins a tie) compared as ONE 64-bit quantity, and its position in the tile's list (-1 = none).
+    // The key lives in a register PAIR read as one float64: for these bit patterns (sign clear, exponent field below
+    // all-ones) the float64 order equals the unsigned 64-bit order, and DSETP -- one instruction on the FP64 pipe --
+    // replaces the two ISETPs of a 64-bit integer compare on the ALU pipe, which is the pipe that limits this kernel.
+    double key[8];
     int bp[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        kw[i] = 0u;
-        kf[i] = 0u;  // ~(-1)
+        key[i] = 0.0;  // 1/z = 0, ~face = 0 (face -1)
         bp[i] = -1;
     }
     if (WINNERS) s_win[lane] = -1;
@@ -728,11 +730,9 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {  // branch-free: selects cost less than the divergence bookkeeping
                     const float w = fmaf(gx, (float)i, wrow);
-                    const unsigned wb = __float_as_uint(w);
-                    const bool upd = ((e0 | e1 | e2) >= 0) &
-                                     ((((unsigned long long)wb << 32) | nface) > (((unsigned long long)kw[i] << 32) | kf[i]));
-                    kw[i] = upd ? wb : kw[i];
-                    kf[i] = upd ? nface : kf[i];
+                    const double cand = __hiloint2double(__float_as_int(w), (int)nface);
+                    const bool upd = ((e0 | e1 | e2) >= 0) & (cand > key[i]);  // w <= 0 (never inside a face) loses
+                    key[i] = upd ? cand : key[i];
                     bp[i] = upd ? pos : bp[i];
                     e0 += s0;
                     e1 += s1;
@@ -744,10 +744,9 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
                 for (int i = 0; i < 8; ++i) {  // unrolled so that bw / bf / br stay in registers
                     float w;
                     if (exact_cover(r, tile_x0 + tx0 + i, tile_y0 + ty, w) && w > 0.f) {
-                        const unsigned wb = __float_as_uint(w);
-                        if ((((unsigned long long)wb << 32) | nface) > (((unsigned long long)kw[i] << 32) | kf[i])) {
-                            kw[i] = wb;
-                            kf[i] = nface;
+                        const double cand = __hiloint2double(__float_as_int(w), (int)nface);
+                        if (cand > key[i]) {
+                            key[i] = cand;
                             bp[i] = pos;
                         }
                     }
@@ -761,8 +760,8 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
     int bf[8];  // 1/z and face ID of the winners, -1 = none
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        bw[i] = __uint_as_float(kw[i]);
-        bf[i] = (int)~kf[i];
+        bw[i] = __int_as_float(__double2hiint(key[i]));
+        bf[i] = ~__double2loint(key[i]);
     }
 
     // ---- write the 8 pixels of this lane ----

@@ -3,8 +3,8 @@
 Views are independent; the only coupling between them is the per-face accumulator pair
 ``(sum[F, C] float64, count[F] int32)``, a commutative sum over views (reference meshes.py:2057-2067; the
 reference's chunked variant already merges partial sums this way, derived_meshes.py:292-302).  So: one process per
-GPU, the mesh replicated, the cameras split into contiguous blocks, and ONE all-reduce of the accumulators at the
-end, followed by the mean / argmax epilogue.  ``render_flat`` has no coupling at all (replicas only).
+GPU, the mesh replicated, the cameras split into contiguous blocks, and ONE all-reduce of the accumulators (counts
+packed behind the sums) at the end, followed by the mean / argmax epilogue.  ``render_flat`` has no coupling at all (replicas only).
 
 The functions take an initialised ``torch.distributed`` process group (NCCL on GPUs; the host-side logic is
 exercised with gloo on CPU tensors in tests/test_distributed_gloo.py).
@@ -32,15 +32,22 @@ def shard_cameras(cameras, rank: int, world_size: int):
 
 
 def allreduce_accumulators(d_sum, d_count, group=None):
-    """In-place sum of the per-face accumulators over all ranks.  Counts (and one-hot / vote sums) are integers
-    and therefore identical for any number of ranks; float64 sums of real-valued scores differ from the single-GPU
-    result only by the association order of at most ``world_size`` partial sums (~1e-16 relative)."""
+    """In-place sum of the per-face accumulators over all ranks with ONE collective: the int32 counts ride behind the
+    float64 sums in a single float64 buffer (exact: counts are far below 2^53).  Counts (and one-hot / vote sums) are
+    integers and therefore identical for any number of ranks; float64 sums of real-valued scores differ from the
+    single-GPU result only by the association order of at most ``world_size`` partial sums (~1e-16 relative)."""
+    import torch
     import torch.distributed as dist
 
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return d_sum, d_count
-    dist.all_reduce(d_sum, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(d_count, op=dist.ReduceOp.SUM, group=group)
+    n_sum = d_sum.numel()
+    pack = torch.empty((n_sum + d_count.numel(),), dtype=torch.float64, device=d_sum.device)
+    pack[:n_sum].copy_(d_sum.reshape(-1))
+    pack[n_sum:].copy_(d_count.reshape(-1))
+    dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
+    d_sum.copy_(pack[:n_sum].view(d_sum.shape))
+    d_count.copy_(pack[n_sum:].view(d_count.shape))
     return d_sum, d_count
 
 

@@ -561,42 +561,18 @@ class TexturedPhotogrammetryMesh:
         return t.to(dev, non_blocking=True)
 
     def _to_host(self, *tensors):
-        """Device tensors -> fresh NumPy arrays owned by the caller.  The transfer goes through page-locked staging
-        buffers that the mesh keeps (full PCIe rate), followed by a multi-threaded host copy into new arrays."""
+        """Device tensors -> fresh NumPy arrays owned by the caller.  Every array is backed by its own page-locked
+        buffer, so the device-to-host copy runs at the full PCIe rate and is the ONLY copy (no second pass from a
+        staging buffer into pageable memory, which used to cost more than the transfer itself).  The buffers come
+        from torch's caching host allocator: they go back to its pool when the caller drops the arrays, and a later
+        call reuses them."""
         import torch
 
-        outs = []
-        stage = self.__dict__.setdefault("_pinned_stage", {})
-        for i, t in enumerate(tensors):
-            key = (i, t.dtype, tuple(t.shape))
-            if key not in stage:
-                for old in [k for k in stage if k[0] == i]:
-                    del stage[old]
-                stage[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            stage[key].copy_(t, non_blocking=True)
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+        for h, t in zip(host, tensors):
+            h.copy_(t, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        jobs = []
-        for i, t in enumerate(tensors):
-            src = stage[(i, t.dtype, tuple(t.shape))].numpy()
-            dst = np.empty(src.shape, dtype=src.dtype)
-            outs.append(dst)
-            s1, d1 = src.reshape(-1), dst.reshape(-1)
-            step = max(1 << 20, -(-s1.size // 32))
-            jobs += [(d1[a : a + step], s1[a : a + step]) for a in range(0, s1.size, step)]
-        # The copy into fresh (not yet touched) pages is page-fault bound: spread it over a few threads of our own
-        # (NumPy releases the GIL for these copies; OMP_NUM_THREADS, which torchrun sets to 1, does not matter).
-        n_threads = min(16, os.cpu_count() or 1, max(1, len(jobs)))
-        if n_threads > 1:
-            pool = self.__dict__.get("_copy_pool")
-            if pool is None:
-                from concurrent.futures import ThreadPoolExecutor
-
-                pool = self.__dict__["_copy_pool"] = ThreadPoolExecutor(max_workers=n_threads)
-            list(pool.map(lambda job: np.copyto(job[0], job[1]), jobs))
-        else:
-            for d, s_ in jobs:
-                np.copyto(d, s_)
-        return outs
+        return [h.numpy() for h in host]  # the array keeps its tensor (and thereby the buffer) alive
 
     # -- pageable host images: the GPU lists the pixels it needs, the host gathers them -----------------------------
     def _pinned(self, name, shape, dtype):
