@@ -30,7 +30,7 @@ EXPORTS = [
     "gg_project_aggregate", "gg_finalize", "gg_render_flat", "gg_stage_count", "gg_stage_name", "gg_profile",
     "gg_profile_read", "gg_drain", "gg_set_pipeline", "gg_build_warp_map", "gg_gather_i32",
     "gg_label_polygons", "gg_get_capacity", "gg_rasterize_render_flat", "gg_project_winners", "gg_accumulate_rows",
-    "gg_overflow_info",
+    "gg_overflow_info", "gg_resize_render", "gg_label_polygons_overlay",
 ]
 
 
@@ -111,7 +111,9 @@ def load():
     lib.gg_set_pipeline.argtypes = [vp, i32]
     lib.gg_build_warp_map.argtypes = [i32, ctypes.POINTER(GGDistortion), i32, i32, i32, vp, vp, vp]
     lib.gg_gather_i32.argtypes = [i32, vp, vp, i64, ctypes.c_int32, vp, vp]
+    lib.gg_resize_render.argtypes = [i32, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]
     lib.gg_label_polygons.argtypes = [i32, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.gg_label_polygons_overlay.argtypes = lib.gg_label_polygons.argtypes
     lib.gg_profile.argtypes = [vp, i32]
     lib.gg_profile_read.argtypes = [vp, vp, vp, i32]
     for name in EXPORTS:
@@ -185,21 +187,47 @@ def gather_i32(d_in, d_src_index, fill: int):
     return out
 
 
-def label_polygons_weights(xyz, xy, faces, labels, face_weight, rings, n_classes, device=0):
+def resize_render(d_in, h_out: int, w_out: int, order: int, out_dtype=OUT_F64):
+    """(h_in, w_in, D) float64 CUDA tensor -> (h_out, w_out, D) tensor: skimage.transform.resize(order = 0 | 1) as
+    save_renders uses it (reference meshes.py:2312-2321), optionally with the uint8 cast fused in."""
+    import torch
+
+    assert d_in.is_cuda and d_in.dtype == torch.float64 and d_in.dim() == 3
+    d_in = d_in.contiguous()
+    h_in, w_in, D = (int(x) for x in d_in.shape)
+    out = torch.empty((h_out, w_out, D), dtype=torch.float64 if out_dtype == OUT_F64 else torch.uint8, device=d_in.device)
+    _check(load().gg_resize_render(d_in.device.index or 0, d_in.data_ptr(), h_in, w_in, D, int(h_out), int(w_out),
+                                   int(order), out.data_ptr(), out_dtype, _stream_ptr(None)))
+    return out
+
+
+def _signed_area(ring):
+    x, y = ring[:, 0], ring[:, 1]
+    return 0.5 * float(np.dot(x, np.roll(y, -1)) - np.dot(np.roll(x, -1), y))
+
+
+def label_polygons_weights(xyz, xy, faces, labels, face_weight, rings, n_classes, device=0, overlay=False, holes=None):
     """(n_polys, n_classes) float64 NumPy array of summed face weights.  ``rings``: list (one entry per polygon) of
-    lists of (K, 2) float arrays (exterior rings and holes alike).  Host arrays in, host array out."""
+    lists of (K, 2) float arrays (exterior rings and holes alike).  ``overlay``: partially covered faces vote with the
+    area of their intersection (sjoin_overlay=False) instead of only faces within a polygon; it needs to know which
+    rings are holes (``holes``: per polygon a list of bools; default: only the first ring of a polygon is an
+    exterior).  Host arrays in, host array out."""
     import torch
 
     if not torch.cuda.is_available():
         raise GeograypherB200Error(-5, "no CUDA device: geograypher_b200 has no CPU fallback")
     dev = torch.device("cuda", device)
     flat, ring_off, poly_off, bbox = [], [0], [0], []
-    for poly in rings:
+    for pi, poly in enumerate(rings):
         pts = []
-        for ring in poly:
+        for ri, ring in enumerate(poly):
             ring = np.asarray(ring, dtype=np.float64).reshape(-1, 2)
             if len(ring) > 1 and np.array_equal(ring[0], ring[-1]):
                 ring = ring[:-1]  # closed rings repeat their first vertex
+            if overlay and len(ring) >= 3:  # exteriors counter-clockwise, holes clockwise
+                is_hole = holes[pi][ri] if holes is not None else ri > 0
+                if (_signed_area(ring) < 0) != bool(is_hole):
+                    ring = ring[::-1]
             flat.append(ring)
             pts.append(ring)
             ring_off.append(ring_off[-1] + len(ring))
@@ -214,10 +242,10 @@ def label_polygons_weights(xyz, xy, faces, labels, face_weight, rings, n_classes
     d_pxy = t(np.concatenate(flat) if flat else np.zeros((1, 2)), np.float64)
     d_ro, d_po, d_bb = t(ring_off, np.int32), t(poly_off, np.int32), t(bbox, np.float64)
     d_w = torch.zeros((n_polys, n_classes), dtype=torch.float64, device=dev)
-    _check(load().gg_label_polygons(device, d_xyz.data_ptr(), d_xy.data_ptr(), d_faces.data_ptr(), d_labels.data_ptr(),
-                                    d_fw.data_ptr() if d_fw is not None else None, int(len(faces)), d_pxy.data_ptr(),
-                                    d_ro.data_ptr(), d_po.data_ptr(), d_bb.data_ptr(), n_polys, int(n_classes),
-                                    d_w.data_ptr(), _stream_ptr(None)))
+    fn = load().gg_label_polygons_overlay if overlay else load().gg_label_polygons
+    _check(fn(device, d_xyz.data_ptr(), d_xy.data_ptr(), d_faces.data_ptr(), d_labels.data_ptr(),
+              d_fw.data_ptr() if d_fw is not None else None, int(len(faces)), d_pxy.data_ptr(), d_ro.data_ptr(),
+              d_po.data_ptr(), d_bb.data_ptr(), n_polys, int(n_classes), d_w.data_ptr(), _stream_ptr(None)))
     return d_w.cpu().numpy()
 
 

@@ -182,6 +182,12 @@ static int check_cams(const gg_camera *cams, int n) {
     return GG_OK;
 }
 
+static const char *k_stage_names[GG_ST_COUNT] = {"mesh_setup", "project", "cull_blocks", "setup_faces", "scan_tiles",
+                                                   "fill_bins", "raster_tiles", "last_pixel", "resolve", "pixel_sum",
+                                                   "finalize", "render_flat", "misc", "stage_host_rows"};
+
+const char *gg_stage_label(int stage) { return (stage >= 0 && stage < GG_ST_COUNT) ? k_stage_names[stage] : "?"; }
+
 extern "C" {
 
 int gg_abi_version(void) { return GG_ABI_VERSION; }
@@ -290,9 +296,7 @@ int gg_sync(gg_context *ctx, void *stream) {
     return GG_OK;
 }
 
-static const char *k_stage_names[GG_ST_COUNT] = {"mesh_setup", "project", "cull_blocks", "setup_faces", "scan_tiles",
-                                                   "fill_bins", "raster_tiles", "last_pixel", "resolve", "pixel_sum",
-                                                   "finalize", "render_flat", "misc", "stage_host_rows"};
+
 
 int gg_stage_count(void) { return GG_ST_COUNT; }
 

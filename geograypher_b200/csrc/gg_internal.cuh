@@ -1,6 +1,7 @@
 // Internal declarations shared by the translation units of libgeograypher_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges are no-ops unless a profiler injects itself
 #include <stdint.h>
 
 #include <string>
@@ -147,6 +148,7 @@ struct gg_context {
 };
 
 void gg_set_error(const std::string &msg);
+const char *gg_stage_label(int stage);  // gg_api.cu: the names gg_stage_name() returns
 int gg_cuda_fail(cudaError_t e, const char *what);
 
 // Launch a kernel (or any stream operation) under a stage label: counts it, and brackets it with events when
@@ -155,6 +157,7 @@ int gg_cuda_fail(cudaError_t e, const char *what);
     do {                                                                    \
         GGProfPending _p{stage, nullptr, nullptr};                          \
         if ((ctx)->prof.on) {                                               \
+            nvtxRangePushA(gg_stage_label(stage)); /* NVTX range per stage */ \
             _p.a = (ctx)->prof.get();                                       \
             _p.b = (ctx)->prof.get();                                       \
             cudaEventRecord(_p.a, st);                                      \
@@ -164,6 +167,7 @@ int gg_cuda_fail(cudaError_t e, const char *what);
         if ((ctx)->prof.on) {                                               \
             cudaEventRecord(_p.b, st);                                      \
             (ctx)->prof.pending.push_back(_p);                              \
+            nvtxRangePop();                                                 \
         }                                                                   \
         GG_CUDA(cudaGetLastError());                                        \
     } while (0)

@@ -101,6 +101,60 @@ __global__ void __launch_bounds__(256) k_gather_i32(const int32_t *__restrict__ 
     }
 }
 
+
+// ---- save_renders' up-sampling to the native resolution (meshes.py:2312-2321) ---------------------------------------
+// skimage.transform.resize(rendered, native_size, order = 0 | 1) is scipy.ndimage.zoom(..., grid_mode=True,
+// mode="mirror") (skimage >= 0.19; numpy-style "reflect" is ndimage's "mirror"): output pixel i samples the input at
+// x = (i + 0.5) * n_in / n_out - 0.5, nearest = floor(x + 0.5), linear between floor(x) and floor(x) + 1, coordinates
+// outside [0, n_in - 1] mirrored about the end pixels.  NaN (no face) propagates through the linear weights exactly
+// like it does there.  The uint8 rule of save_renders (meshes.py:2323-2334) can be applied on the way out.
+__device__ __forceinline__ double mirror_coord(double x, int n) {
+    if (n == 1) return 0.0;
+    if (x < 0.0) x = -x;
+    const double hi = (double)(n - 1);
+    if (x > hi) x = 2.0 * hi - x;
+    return x;
+}
+
+template <typename OUT>
+__device__ __forceinline__ OUT resize_out(double v);
+template <>
+__device__ __forceinline__ double resize_out<double>(double v) {
+    return v;
+}
+template <>
+__device__ __forceinline__ uint8_t resize_out<uint8_t>(double v) {
+    if (!(v >= 0.0) || v > 255.0 || !isfinite(v)) return 0;
+    return (uint8_t)v;
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(256) k_resize(const double *__restrict__ in, int h_in, int w_in, int D, int h_out,
+                                                int w_out, int order, OUT *__restrict__ out) {
+    const double sy = (double)h_in / (double)h_out, sx = (double)w_in / (double)w_out;
+    const int64_t n = (int64_t)h_out * w_out;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(p / w_out), j = (int)(p - (int64_t)i * w_out);
+        const double y = ((double)i + 0.5) * sy - 0.5, x = ((double)j + 0.5) * sx - 0.5;
+        if (order == 0) {
+            const int yi = min(max((int)floor(y + 0.5), 0), h_in - 1), xi = min(max((int)floor(x + 0.5), 0), w_in - 1);
+            for (int d = 0; d < D; ++d) out[p * D + d] = resize_out<OUT>(in[((int64_t)yi * w_in + xi) * D + d]);
+        } else {
+            const double ym = mirror_coord(y, h_in), xm = mirror_coord(x, w_in);
+            const int y0 = min((int)floor(ym), h_in - 1), x0 = min((int)floor(xm), w_in - 1);
+            const int y1 = min(y0 + 1, h_in - 1), x1 = min(x0 + 1, w_in - 1);
+            const double ty = ym - (double)y0, tx = xm - (double)x0;
+            for (int d = 0; d < D; ++d) {
+                const double a = in[((int64_t)y0 * w_in + x0) * D + d], b = in[((int64_t)y0 * w_in + x1) * D + d];
+                const double c = in[((int64_t)y1 * w_in + x0) * D + d], e = in[((int64_t)y1 * w_in + x1) * D + d];
+                // separable, rows first (ndimage.zoom filters axis by axis)
+                const double top = (1.0 - tx) * a + tx * b, bot = (1.0 - tx) * c + tx * e;
+                out[p * D + d] = resize_out<OUT>((1.0 - ty) * top + ty * bot);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -146,6 +200,24 @@ int gg_gather_i32(int device, const int32_t *d_in, const int32_t *d_src_index, i
     const int64_t want = (n_out + 255) / 256;
     k_gather_i32<<<(unsigned)(want < 148 * 32 ? want : 148 * 32), 256, 0, (cudaStream_t)stream>>>(d_in, d_src_index, n_out,
                                                                                                  fill, d_out);
+    GG_CUDA(cudaGetLastError());
+    return GG_OK;
+}
+
+int gg_resize_render(int device, const double *d_in, int h_in, int w_in, int D, int h_out, int w_out, int order,
+                     void *d_out, int out_dtype, void *stream) {
+    if (!d_in || !d_out || h_in < 1 || w_in < 1 || h_out < 1 || w_out < 1 || D < 1 || (order != 0 && order != 1) ||
+        (out_dtype != GG_OUT_F64 && out_dtype != GG_OUT_U8)) {
+        gg_set_error("gg_resize_render: bad arguments (order 0 | 1; out_dtype GG_OUT_F64 | GG_OUT_U8)");
+        return GG_ERR_INVALID;
+    }
+    GG_CUDA(cudaSetDevice(device));
+    const int64_t want = ((int64_t)h_out * w_out + 255) / 256;
+    const unsigned g = (unsigned)(want < 148 * 32 ? want : 148 * 32);
+    if (out_dtype == GG_OUT_F64)
+        k_resize<double><<<g, 256, 0, (cudaStream_t)stream>>>(d_in, h_in, w_in, D, h_out, w_out, order, (double *)d_out);
+    else
+        k_resize<uint8_t><<<g, 256, 0, (cudaStream_t)stream>>>(d_in, h_in, w_in, D, h_out, w_out, order, (uint8_t *)d_out);
     GG_CUDA(cudaGetLastError());
     return GG_OK;
 }

@@ -444,8 +444,11 @@ class TexturedPhotogrammetryMesh:
     # ------------------------------------------------------------------------------------------------
     # render_flat
     # ------------------------------------------------------------------------------------------------
-    def render_flat_device(self, cameras, batch_size: int = None, render_img_scale: float = 1, out_dtype="float64"):
-        """Generator of (n_batch, h, w, d) CUDA tensors: the face texture seen from every camera."""
+    def render_flat_device(self, cameras, batch_size: int = None, render_img_scale: float = 1, out_dtype="float64",
+                           check: bool = True):
+        """Generator of (n_batch, h, w, d) CUDA tensors: the face texture seen from every camera.  ``check=False``
+        leaves the launches asynchronous (the caller synchronises the context once at the end and handles a scratch
+        overflow there); the first batch is always checked, which sizes the scratch."""
         import torch
 
         mesh = self.get_mesh_in_cameras_coords(cameras)
@@ -457,7 +460,7 @@ class TexturedPhotogrammetryMesh:
         gg = self._gg_cameras(cam_list, mesh, render_img_scale)
         B = self.views_per_batch if batch_size is None else max(1, min(batch_size, _lib.MAX_VIEWS_PER_CALL))
         for s in range(0, len(gg), B):  # fused: the face-ID rasters are never written
-            yield mesh.context.rasterize_render_flat(gg[s : s + B], tex, out_dtype=code)
+            yield mesh.context.rasterize_render_flat(gg[s : s + B], tex, out_dtype=code, check=check or s == 0)
 
     def render_flat(self, cameras, batch_size: int = 1, render_img_scale: float = 1, return_camera: bool = False,
                     **pix2face_kwargs):
@@ -795,20 +798,58 @@ class TexturedPhotogrammetryMesh:
             json.dump({str(int(k)): (v if isinstance(v, str) else float(v)) for k, v in IDs_to_labels.items()}, f,
                       ensure_ascii=False, indent=4)
 
+    def _to_host_pipelined(self, device_batches):
+        """Device batches -> host arrays through TWO page-locked staging buffers and a copy stream: the device-to-host
+        copy of batch k runs while batch k+1 is rendered, and the consumer works on batch k-1.  Yields
+        ``(host_array_view, release)``: the view is only valid until ``release()`` is called, after which its buffer
+        receives a later batch."""
+        import threading
+
+        import torch
+
+        copy_stream = self.__dict__.get("_copy_stream")
+        if copy_stream is None:
+            copy_stream = self.__dict__["_copy_stream"] = torch.cuda.Stream(device=self.device)
+        slots = [None, None]          # pinned tensors
+        events = [None, None]
+        free = [threading.Semaphore(1), threading.Semaphore(1)]
+        pending = None
+        for k, batch in enumerate(device_batches):
+            slot = k % 2
+            free[slot].acquire()  # the consumer of the batch that used this buffer two rounds ago has let go of it
+            if slots[slot] is None or slots[slot].shape != batch.shape or slots[slot].dtype != batch.dtype:
+                slots[slot] = torch.empty(batch.shape, dtype=batch.dtype, pin_memory=True)
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):
+                slots[slot].copy_(batch, non_blocking=True)
+                events[slot] = torch.cuda.Event()
+                events[slot].record(copy_stream)
+            batch.record_stream(copy_stream)
+            if pending is not None:
+                events[pending].synchronize()
+                yield slots[pending].numpy(), free[pending].release
+            pending = slot
+        if pending is not None:
+            events[pending].synchronize()
+            yield slots[pending].numpy(), free[pending].release
+
     def save_renders(self, camera_set, render_image_scale=1.0, output_folder="renders", make_composites: bool = False,
                      save_native_resolution: bool = False, cast_to_uint8: bool = True, save_as_npy: bool = False,
                      uint8_value_for_null_texture=NULL_TEXTURE_INT_VALUE, n_writer_threads: int = 8, **render_kwargs):
         """Render the face texture from every camera and write one file per image (reference meshes.py:2248-2397).
 
         With ``cast_to_uint8`` the cast rule of the reference (< 0, > 255 or non-finite -> the null value, then
-        truncation, meshes.py:2323-2334) is applied on the GPU and only one byte per pixel and channel crosses PCIe;
-        files are written by a small thread pool so that the disk does not stall the GPU.  Outputs keep the image's
-        path relative to ``camera_set.image_folder`` (meshes.py:2349-2366) and are ``.npy`` arrays (``save_as_npy``) or
-        deflate-compressed TIFFs (needs Pillow).  Composites with the photographs and up-sampling to the native
-        resolution are visualisation features outside this build.
+        truncation, meshes.py:2323-2334) is applied on the GPU and only one byte per pixel and channel crosses PCIe.
+        ``save_native_resolution`` up-samples scaled renders to the camera's native size on the GPU like the reference
+        does on the host (nearest neighbour for discrete textures, bilinear otherwise, meshes.py:2312-2321).  The
+        device-to-host copies go through two page-locked buffers on a copy stream (the copy of one batch overlaps the
+        rendering of the next) and the files are written by a small thread pool, so neither PCIe nor the disk stalls
+        the GPU.  Outputs keep the image's path relative to ``camera_set.image_folder`` (meshes.py:2349-2366) and are
+        ``.npy`` arrays (``save_as_npy``) or deflate-compressed TIFFs (needs Pillow).  Composites with the photographs
+        are a visualisation feature outside this build.  Returns the number of bytes handed to the writers.
         """
-        if make_composites or (save_native_resolution and render_image_scale != 1):
-            raise NotImplementedError("composites / native-resolution up-sampling are visualisation steps outside this build")
+        if make_composites:
+            raise NotImplementedError("composites with the photographs are a visualisation step outside this build")
         if uint8_value_for_null_texture != 0 and cast_to_uint8:
             raise NotImplementedError("only NULL_TEXTURE_INT_VALUE = 0 is supported for the fused uint8 cast")
         from concurrent.futures import ThreadPoolExecutor
@@ -838,26 +879,61 @@ class TexturedPhotogrammetryMesh:
         apply_distortion = render_kwargs.pop("apply_distortion", True)
         if apply_distortion and not hasattr(camera_set, "warp_dewarp_device"):
             apply_distortion = False if render_kwargs.get("distortion_set") is None else apply_distortion
-        gen = (self._render_flat_distorted_device(camera_set, render_image_scale, cast_to_uint8)
-               if apply_distortion and hasattr(camera_set, "warp_dewarp_device")
-               else self.render_flat_device(camera_set, None, render_image_scale, "uint8" if cast_to_uint8 else "float64"))
-        k = 0
-        with ThreadPoolExecutor(max_workers=max(1, n_writer_threads)) as pool:
-            futures = []
+        upsample = bool(save_native_resolution) and render_image_scale != 1
+        distorted = apply_distortion and hasattr(camera_set, "warp_dewarp_device")
+        render_dtype = "uint8" if (cast_to_uint8 and not upsample) else "float64"
+
+        def device_batches():
+            gen = (self._render_flat_distorted_device(camera_set, render_image_scale, render_dtype == "uint8")
+                   if distorted else self.render_flat_device(camera_set, None, render_image_scale, render_dtype, check=False))
+            if not upsample:
+                yield from gen
+                return
+            import torch
+
+            order = 0 if self.is_discrete_texture() else 1  # meshes.py:2315-2320
+            code = _lib.OUT_U8 if cast_to_uint8 else _lib.OUT_F64
+            k = 0
             for batch in gen:
-                host = batch.cpu().numpy()
-                for img in host:
-                    cam = cam_list[k]
-                    try:
-                        rel = Path(cam.get_image_filename()).relative_to(camera_set.image_folder)
-                    except (ValueError, TypeError):
-                        raise ValueError(
-                            f"Tried to find the relative path of the camera path ({cam.get_image_filename()}) inside of "
-                            f"the camera set image folder ({camera_set.image_folder}), but failed.")
-                    futures.append(pool.submit(write, Path(output_folder, rel), img))
+                out = []
+                for img in batch:
+                    h_native, w_native = cam_list[k].get_image_size()
+                    out.append(_lib.resize_render(img, h_native, w_native, order, code))
                     k += 1
-            for f in futures:
-                f.result()
+                yield torch.stack(out)
+
+        ctx = self._get_context()
+        for attempt in range(4):
+            k, n_bytes = 0, 0
+            try:
+                with ThreadPoolExecutor(max_workers=max(1, n_writer_threads)) as pool:
+                    all_futures = []
+                    for host, release in self._to_host_pipelined(device_batches()):
+                        futures = []
+                        for img in host:
+                            cam = cam_list[k]
+                            try:
+                                rel = Path(cam.get_image_filename()).relative_to(camera_set.image_folder)
+                            except (ValueError, TypeError):
+                                raise ValueError(
+                                    f"Tried to find the relative path of the camera path ({cam.get_image_filename()}) "
+                                    f"inside of the camera set image folder ({camera_set.image_folder}), but failed.")
+                            futures.append(pool.submit(write, Path(output_folder, rel), img))
+                            n_bytes += img.nbytes
+                            k += 1
+                        # the staging buffer goes back to the pipeline once ITS files are written (the pool is FIFO:
+                        # the writes above start before this task does)
+                        pool.submit(lambda fs=futures, rel_=release: ([f.exception() for f in fs], rel_()))
+                        all_futures += futures
+                    pool.shutdown(wait=True)
+                    for f in all_futures:
+                        f.result()
+                ctx.sync()  # unchecked launches: a scratch overflow of any batch shows up here
+                return n_bytes
+            except _lib.GeograypherB200Error as e:
+                if e.code != _lib.ERR_OVERFLOW or attempt == 3:
+                    raise
+                ctx._grow_after_overflow()  # some renders were skipped: grow the scratch and write everything again
 
     def _render_flat_distorted_device(self, cameras, scale, cast_to_uint8):
         """render_flat through the lens model, on the device: rasterize, warp the face-ID raster, gather."""
@@ -872,47 +948,55 @@ class TexturedPhotogrammetryMesh:
             yield mesh.context.render_flat(p2f.contiguous(), tex, out_dtype=code)
 
     @staticmethod
-    def _polygon_rings(polygons):
+    def _polygon_rings(polygons, with_holes=False):
         """Normalise the accepted polygon containers to a list (per polygon) of lists of (K, 2) rings: arrays, dicts
-        {"exterior", "holes"}, shapely-like (Multi)Polygons, or anything with a ``.geometry`` column of those."""
+        {"exterior", "holes"}, shapely-like (Multi)Polygons, or anything with a ``.geometry`` column of those.  With
+        ``with_holes`` also returns, per polygon, which rings are holes."""
         geoms = getattr(polygons, "geometry", polygons)
-        out = []
+        out, holes = [], []
         for g in geoms:
             if hasattr(g, "geoms"):  # MultiPolygon: rings of all parts, even-odd rule
                 parts = list(g.geoms)
             else:
                 parts = [g]
-            rings = []
+            rings, is_hole = [], []
             for part in parts:
                 if hasattr(part, "exterior"):
                     rings.append(np.asarray(part.exterior.coords)[:, :2])
-                    rings.extend(np.asarray(i.coords)[:, :2] for i in part.interiors)
+                    inner = [np.asarray(i.coords)[:, :2] for i in part.interiors]
                 elif isinstance(part, dict):
                     rings.append(np.asarray(part["exterior"], dtype=float))
-                    rings.extend(np.asarray(h, dtype=float) for h in part.get("holes", []))
+                    inner = [np.asarray(h, dtype=float) for h in part.get("holes", [])]
                 else:
                     rings.append(np.asarray(part, dtype=float))
+                    inner = []
+                rings.extend(inner)
+                is_hole += [False] + [True] * len(inner)
             out.append(rings)
-        return out
+            holes.append(is_hole)
+        return (out, holes) if with_holes else out
 
     def label_polygons(self, face_labels, polygons, face_weighting=None, sjoin_overlay=True,
                        return_class_labels=True, unknown_class_label="unknown", buffer_dist_meters=2.0,
                        vertex_xy=None):
-        """Assign a class to every polygon from per-face labels (reference meshes.py:1141-1306, sjoin path).
+        """Assign a class to every polygon from per-face labels (reference meshes.py:1141-1306).
 
-        Every face with a finite label whose 2-D triangle lies within a polygon votes for its class with weight
-        ``area3D * face_weighting``; the polygon gets the class with the largest total (lowest class ID on ties),
-        NaN / ``unknown_class_label`` when no face voted.  The polygon tests and the weighted vote run on the GPU
-        (``gg_label_polygons``).
+        ``sjoin_overlay=True`` (default, :1259-1261): every face with a finite label whose 2-D triangle lies WITHIN a
+        polygon votes for its class with weight ``area3D * face_weighting``.  ``sjoin_overlay=False`` (:1263-1268,
+        ``polygons.overlay(faces, how="identity")``): faces are split along the polygon boundaries and every piece
+        votes with ``area2D(piece) * (area3D / area2D)(face) * face_weighting``, so partially covered faces count in
+        proportion.  The polygon gets the class with the largest total (lowest class ID on ties), NaN /
+        ``unknown_class_label`` when nothing voted.  Both run on the GPU (``gg_label_polygons[_overlay]``).
 
         ``polygons``: sequence of (K, 2) exterior rings, dicts ``{"exterior", "holes"}``, shapely-like polygons, or a
         GeoDataFrame-like object -- in the SAME planar coordinates as ``vertex_xy``.  ``vertex_xy`` (*new*, (V, 2)):
         planar coordinates of the mesh vertices; defaults to the x, y of the stored vertices, which is right for meshes
-        kept in a local metric frame (the reference reprojects the mesh to the polygons' CRS with pyproj, which is
-        outside this build).  ``sjoin_overlay=False`` (exact overlay of partially covered faces) is not provided.
+        kept in a local metric frame (the reference reprojects the mesh to the polygons' CRS with pyproj,
+        meshes.py:1194-1209, which is outside this build: pass the reprojected coordinates).  Not reproduced: the
+        1e-6 precision snapping of both layers (:1222-1227) and the pre-filter that drops faces reaching more than
+        ``buffer_dist_meters`` beyond the dissolved polygons (:1236-1253) -- faces of a survey mesh are far smaller
+        than that buffer.
         """
-        if not sjoin_overlay:
-            raise NotImplementedError("only the sjoin (faces entirely within a polygon) overlay is provided")
         del buffer_dist_meters
         face_labels = np.squeeze(np.asarray(face_labels, dtype=float))
         if face_labels.ndim != 1:
@@ -921,12 +1005,12 @@ class TexturedPhotogrammetryMesh:
             face_weighting = np.squeeze(np.asarray(face_weighting, dtype=float))
             if face_weighting.ndim != 1:
                 raise ValueError(f"Faces labels must be one-dimensional, but is {face_weighting.ndim}")
-        rings = self._polygon_rings(polygons)
+        rings, holes = self._polygon_rings(polygons, with_holes=True)
         xy = self.points[:, :2] if vertex_xy is None else np.asarray(vertex_xy, dtype=float)
         finite = face_labels[np.isfinite(face_labels)]
         n_classes = int(finite.max()) + 1 if len(finite) else 1
         weights = _lib.label_polygons_weights(self.points, xy, self.faces, face_labels, face_weighting, rings,
-                                              n_classes, self.device)
+                                              n_classes, self.device, overlay=not sjoin_overlay, holes=holes)
         best = weights.max(axis=1)
         predicted = np.where(best > 0, weights.argmax(axis=1).astype(float), np.nan).tolist()
         IDs_to_labels = self.get_IDs_to_labels()

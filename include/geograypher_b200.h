@@ -202,6 +202,12 @@ int gg_build_warp_map(int device, const gg_distortion *h_dist, int h, int w, int
    (utils/image.py:72-126 with interpolation_order = 0), integer-safe. */
 int gg_gather_i32(int device, const int32_t *d_in, const int32_t *d_src_index, int64_t n_out, int32_t fill,
                   int32_t *d_out, void *stream);
+/* save_renders' up-sampling of a render to the camera's native size (meshes.py:2312-2321:
+   skimage.transform.resize(rendered, native_size, order = 0 for discrete textures, 1 otherwise), i.e.
+   scipy.ndimage.zoom(grid_mode=True, mode="mirror")), optionally with the uint8 rule of meshes.py:2323-2334 fused in.
+   d_in: h_in x w_in x D float64 (NaN = no face); d_out: h_out x w_out x D of out_dtype (GG_OUT_F64 | GG_OUT_U8). */
+int gg_resize_render(int device, const double *d_in, int h_in, int w_in, int D, int h_out, int w_out, int order,
+                     void *d_out, int out_dtype, void *stream);
 
 /* ---- label_polygons (meshes.py:1141-1306 with sjoin_overlay=True): every face with a finite label whose
         2-D triangle lies within polygon p adds  area3D(face) * face_weight  to d_weights[p][class].
@@ -214,6 +220,13 @@ int gg_label_polygons(int device, const double *d_xyz, const double *d_xy, const
                       const double *d_labels, const double *d_face_weight, int64_t F, const double *d_poly_xy,
                       const int32_t *d_ring_offsets, const int32_t *d_poly_ring_offsets, const double *d_poly_bbox,
                       int n_polys, int n_classes, double *d_weights, void *stream);
+/* The same with sjoin_overlay=False (meshes.py:1263-1276: polygons.overlay(faces, how="identity")): every labelled face
+   adds  area2D(face n polygon) * (area3D / area2D)(face) * face_weight  to each polygon it overlaps.  Rings must be
+   oriented: exteriors counter-clockwise, holes clockwise (the areas of the pieces are signed sums over ring edges). */
+int gg_label_polygons_overlay(int device, const double *d_xyz, const double *d_xy, const int32_t *d_faces,
+                              const double *d_labels, const double *d_face_weight, int64_t F, const double *d_poly_xy,
+                              const int32_t *d_ring_offsets, const int32_t *d_poly_ring_offsets,
+                              const double *d_poly_bbox, int n_polys, int n_classes, double *d_weights, void *stream);
 
 #ifdef __cplusplus
 }

@@ -190,6 +190,17 @@ def rasterize(verts32, faces, cam: OraCamera, want_depth=False, want_margin=Fals
     return p2f
 
 
+def resize_render(image, output_shape, order):
+    """save_renders' up-sampling (meshes.py:2312-2321): skimage.transform.resize(image, output_shape, order=order) with
+    its defaults is scipy.ndimage.zoom(image, factors, order=order, mode="mirror", grid_mode=True) (skimage >= 0.19;
+    no anti-aliasing when up-sampling, preserve_range irrelevant for float input, clip leaves NaN alone)."""
+    from scipy import ndimage
+
+    image = np.asarray(image, dtype=float)
+    factors = [output_shape[0] / image.shape[0], output_shape[1] / image.shape[1]] + [1] * (image.ndim - 2)
+    return ndimage.zoom(image, factors, order=order, mode="mirror", grid_mode=True)
+
+
 _RAYCAST = None
 
 
@@ -503,6 +514,64 @@ def label_polygons(points, faces, face_labels, polygons_rings, face_weighting=No
             ok &= ~(((s[0] > 0) & (s[1] > 0) & (s[2] > 0)) | ((s[0] < 0) & (s[1] < 0) & (s[2] < 0)))
         sel = idx[ok]
         np.add.at(weights[p], face_labels[sel].astype(int), w[sel])
+    best = weights.max(axis=1)
+    labels = np.where(best > 0, weights.argmax(axis=1).astype(float), np.nan)
+    return labels.tolist(), weights
+
+
+def _clip_ring_by_triangle(ring, tri):
+    """Sutherland-Hodgman: the (possibly non-convex) ring clipped by the convex, counter-clockwise triangle."""
+    out = [tuple(p) for p in ring]
+    for e in range(3):
+        (x0, y0), (x1, y1) = tri[e], tri[(e + 1) % 3]
+        src, out = out, []
+        for i in range(len(src)):
+            p, q = src[i], src[(i + 1) % len(src)]
+            dp = (x1 - x0) * (p[1] - y0) - (y1 - y0) * (p[0] - x0)
+            dq = (x1 - x0) * (q[1] - y0) - (y1 - y0) * (q[0] - x0)
+            if dp >= 0:
+                out.append(p)
+            if (dp >= 0) != (dq >= 0):
+                t = dp / (dp - dq)
+                out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+        if len(out) < 3:
+            return []
+    return out
+
+
+def _ring_area(ring):
+    return 0.5 * abs(sum(ring[i][0] * ring[(i + 1) % len(ring)][1] - ring[(i + 1) % len(ring)][0] * ring[i][1]
+                         for i in range(len(ring))))
+
+
+def label_polygons_overlay(points, faces, face_labels, polygons, face_weighting=None, xy=None):
+    """label_polygons with sjoin_overlay=False (meshes.py:1263-1276), pure Python for small cases: every labelled face
+    votes in every polygon with  area2D(face n polygon) * (area3D / area2D) * weight.  ``polygons``: list of dicts
+    {"exterior": (K, 2), "holes": [(K, 2), ...]}.  The intersection area is computed by clipping the WHOLE exterior
+    ring (and each hole, subtracted) with the triangle -- a different decomposition from the CUDA kernel's signed fan
+    triangles.  Returns (labels list, weights (n_polys, n_classes))."""
+    points = np.asarray(points, dtype=float)
+    xy = points[:, :2] if xy is None else np.asarray(xy, dtype=float)
+    face_labels = np.asarray(face_labels, dtype=float)
+    finite = np.isfinite(face_labels)
+    n_classes = int(face_labels[finite].max()) + 1 if finite.any() else 1
+    weights = np.zeros((len(polygons), n_classes))
+    for f in np.nonzero(finite)[0]:
+        tri = [tuple(xy[v]) for v in faces[f]]
+        a2 = (tri[1][0] - tri[0][0]) * (tri[2][1] - tri[0][1]) - (tri[1][1] - tri[0][1]) * (tri[2][0] - tri[0][0])
+        if a2 == 0:
+            continue
+        if a2 < 0:
+            tri = [tri[0], tri[2], tri[1]]
+        p3 = points[faces[f]]
+        area3d = 0.5 * np.linalg.norm(np.cross(p3[1] - p3[0], p3[2] - p3[0]))
+        ratio = area3d / (0.5 * abs(a2)) * (1.0 if face_weighting is None else float(face_weighting[f]))
+        for p, poly in enumerate(polygons):
+            inter = _ring_area(_clip_ring_by_triangle(np.asarray(poly["exterior"], dtype=float), tri) or [(0, 0)] * 3)
+            for hole in poly.get("holes", []):
+                inter -= _ring_area(_clip_ring_by_triangle(np.asarray(hole, dtype=float), tri) or [(0, 0)] * 3)
+            if inter > 0:
+                weights[p, int(face_labels[f])] += inter * ratio
     best = weights.max(axis=1)
     labels = np.where(best > 0, weights.argmax(axis=1).astype(float), np.nan)
     return labels.tolist(), weights

@@ -192,3 +192,53 @@ def test_save_renders(scene, golden_render, tmp_path):
     mesh.save_renders(cams, output_folder=tmp_path / "tif", apply_distortion=False)
     img = np.asarray(Image.open(tmp_path / "tif" / "flight1" / "0001.tif"))
     np.testing.assert_array_equal(img, ora.cast_render_to_uint8(r["render1"][1]))
+
+
+@pytest.mark.parametrize("order,D", [(0, 1), (1, 1), (1, 3)])
+def test_resize_render_kernel_matches_skimage_semantics(order, D):
+    """gg_resize_render == skimage.transform.resize(order) as save_renders uses it (reference meshes.py:2312-2321),
+    i.e. scipy.ndimage.zoom(grid_mode=True, mode='mirror'): NaNs, non-integer factors, 1 and 3 channels."""
+    import torch
+
+    from geograypher_b200 import _lib
+
+    rng = np.random.default_rng(order * 10 + D)
+    img = rng.uniform(-20, 300, size=(37, 53, D))
+    img[rng.random((37, 53)) < 0.05] = np.nan
+    want = ora.resize_render(img, (111, 140), order)
+    got = _lib.resize_render(torch.from_numpy(img).cuda(), 111, 140, order).cpu().numpy()
+    if order == 0:
+        np.testing.assert_array_equal(got, want)
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12, equal_nan=True)
+    got8 = _lib.resize_render(torch.from_numpy(img).cuda(), 111, 140, order, _lib.OUT_U8).cpu().numpy()
+    np.testing.assert_array_equal(got8, ora.cast_render_to_uint8(got).reshape(got8.shape))
+
+
+def test_save_renders_native_resolution(scene, golden_render, tmp_path):
+    """Renders at half scale written at the camera's native size: nearest neighbour for a discrete (label) texture,
+    bilinear for a real-valued one, then the uint8 rule -- like the reference's host-side post-processing."""
+    g, cams0 = scene
+    r = golden_render
+    f, cx, cy, W, H = g["intrinsics"]
+    W, H = int(W), int(H)
+    cams = gg.PhotogrammetryCameraSet(
+        cameras=[gg.PhotogrammetryCamera(f"/data/imgs/{i:04d}.JPG", T, f, cx, cy, W, H) for i, T in enumerate(g["c2ws"])])
+    v32 = (g["verts"] - g["origin"]).astype(np.float32)
+    for discrete in (True, False):
+        tex = r["tex1"] if discrete else r["tex1"] * 0.37 + 1.5
+        mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), log_level="WARNING",
+                                             IDs_to_labels=({i: str(i) for i in range(10)} if discrete else None))
+        mesh.set_texture(tex, is_vertex_texture=False)
+        assert mesh.is_discrete_texture() == discrete
+        out = tmp_path / ("nn" if discrete else "lin")
+        n_bytes = mesh.save_renders(cams, render_image_scale=0.5, save_native_resolution=True, output_folder=out,
+                                    save_as_npy=True, apply_distortion=False)
+        assert n_bytes == len(cams) * H * W
+        for k, T in enumerate(g["c2ws"]):
+            cam = ora.make_camera(T, f, cx, cy, W, H, render_img_scale=0.5, origin=g["origin"])
+            small = ora.render_flat_gather(ora.rasterize(v32, g["faces"], cam), tex)
+            want = ora.cast_render_to_uint8(ora.resize_render(small, (H, W), 0 if discrete else 1))
+            arr = np.load(out / f"{k:04d}.npy")
+            assert arr.shape == (H, W) and arr.dtype == np.uint8
+            np.testing.assert_array_equal(arr, np.squeeze(want))

@@ -87,3 +87,58 @@ def test_label_polygons_known_answer_and_names():
     assert ids[:2] == [2.0, 0.0] and np.isnan(ids[2])
     # unweighted: the straddling square holds as many faces of each class; the tie goes to the lower class ID (0)
     assert mesh.label_polygons(labels, polys[1:2], return_class_labels=False) == [0.0]
+
+
+def test_label_polygons_overlay_known_areas():
+    """sjoin_overlay=False (reference meshes.py:1263-1276): partially covered faces vote with the area of their
+    intersection.  Flat unit grid (3D/2D ratio 1), a 2.5 x 2 rectangle placed off the grid lines: the weights are the
+    areas of the rectangle's parts over each class, to rounding."""
+    from geograypher_b200 import _lib
+
+    verts, faces = syn.terrain_mesh(8, 1.0, seed=0, crowns=False)
+    verts[:, 2] = 0.0
+    cen = verts[faces].mean(axis=1)
+    labels = np.where(cen[:, 0] < 4, 1.0, 0.0)
+    rect = np.array([[2.25, 1.5], [4.75, 1.5], [4.75, 3.5], [2.25, 3.5]])
+    w = _lib.label_polygons_weights(verts, verts[:, :2], faces, labels, None, [[rect]], 2, overlay=True)
+    np.testing.assert_allclose(w, [[0.75 * 2.0, 1.75 * 2.0]], rtol=1e-12)  # class 0: x in [4, 4.75]; class 1: [2.25, 4]
+    mesh = gg.TexturedPhotogrammetryMesh((verts, faces), log_level="WARNING")
+    assert mesh.label_polygons(labels, [rect], sjoin_overlay=False, return_class_labels=False) == [1.0]
+    # the sjoin path only counts faces entirely inside: x in [3, 4] x y in [2, 3] for class 1, nothing for class 0
+    w_in = _lib.label_polygons_weights(verts, verts[:, :2], faces, labels, None, [[rect]], 2)
+    np.testing.assert_allclose(w_in, [[0.0, 1.0]], rtol=1e-12)
+    # tilted mesh: the pieces carry the face's 3D / 2D area ratio
+    verts[:, 2] = verts[:, 0]  # 45 degrees: ratio sqrt(2)
+    w45 = _lib.label_polygons_weights(verts, verts[:, :2], faces, labels, None, [[rect]], 2, overlay=True)
+    np.testing.assert_allclose(w45, np.sqrt(2.0) * w, rtol=1e-12)
+
+
+def test_label_polygons_overlay_matches_restatement():
+    """Random polygons (convex and concave, with a hole, multi-part, clockwise and counter-clockwise rings) on a rough
+    terrain with per-face weights: the CUDA kernel (signed fan triangles) against a pure-Python clipper that cuts the
+    whole rings with each triangle."""
+    from geograypher_b200 import _lib
+
+    verts, faces = syn.terrain_mesh(24, 1.0, seed=3, crowns=True)
+    rng = np.random.default_rng(4)
+    labels = syn.voronoi_face_labels(verts, faces, n_sites=12, n_classes=5, nan_frac=0.2, seed=2)[:, 0]
+    weighting = rng.uniform(0.5, 2.0, len(faces))
+    star = _circle(12, 12, 6, 14)
+    star[::2] = 12 + (star[::2] - 12) * 0.45  # concave
+    polys = [{"exterior": _circle(7, 7, 4.3)}, {"exterior": _circle(16, 9, 3.1)[::-1]}, {"exterior": star},
+             {"exterior": _circle(15, 16, 6.2), "holes": [_circle(15, 16, 2.4)]},
+             {"exterior": np.array([[0.3, 20.2], [5.6, 19.7], [4.9, 23.8], [0.6, 23.1]])},
+             {"exterior": np.array([[30.0, 30.0], [31, 30], [31, 31.0]])}]  # outside the mesh
+    for w in (None, weighting):
+        want_labels, want = ora.label_polygons_overlay(verts, faces, labels, polys, face_weighting=w)
+        rings = [[p["exterior"]] + list(p.get("holes", [])) for p in polys]
+        got = _lib.label_polygons_weights(verts, verts[:, :2], faces, labels, w, rings, want.shape[1], overlay=True)
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-10)
+        mesh = gg.TexturedPhotogrammetryMesh((verts, faces), log_level="WARNING")
+        ids = mesh.label_polygons(labels, polys, face_weighting=w, sjoin_overlay=False, return_class_labels=False)
+        np.testing.assert_array_equal(np.asarray(ids, dtype=float), np.asarray(want_labels, dtype=float))
+    assert np.isnan(ids[-1]) and np.isfinite(ids[:5]).all()
+    # overlay weights of a polygon always reach at least its sjoin ("within") weights
+    inside = _lib.label_polygons_weights(verts, verts[:, :2], faces, labels, None, rings, want.shape[1])
+    over = _lib.label_polygons_weights(verts, verts[:, :2], faces, labels, None, rings, want.shape[1], overlay=True)
+    assert (over >= inside - 1e-9).all() and (over.sum() > inside.sum())

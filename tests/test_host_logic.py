@@ -130,7 +130,7 @@ def test_mesh_host_side():
     with pytest.raises(NotImplementedError):
         gg.TexturedPhotogrammetryMesh((verts, faces), downsample_target=0.5)
     with pytest.raises(NotImplementedError):
-        m.label_polygons(np.zeros(len(faces)), [], sjoin_overlay=False)
+        m.save_renders(None, make_composites=True)
     with pytest.raises(ValueError):  # reference meshes.py:1181-1185
         m.label_polygons(np.zeros((len(faces), 2)), [])
     rings = m._polygon_rings([np.array([[0, 0], [1, 0], [1, 1]]), {"exterior": [[0, 0], [4, 0], [4, 4]], "holes": [[[1, 1], [2, 1], [2, 2]]]}])
