@@ -370,7 +370,7 @@ static int launch_reset_winners(gg_context *ctx, int n, int flags, cudaStream_t 
 // per element, so a warp's loads of one row share their sectors), then k_resolve_batch walks the views in order on
 // the staged copy.  The winners are re-pointed from pixel indices to staging rows in between.
 // The fetch is bound by the PCIe link's small-read rate (~0.3 G rows/s), not by the SMs: a few hundred rows in flight
-// keep the link busy.  So the kernel is a SMALL persistent grid (GG_STAGE_CTAS CTAs per SM, default 4, of 256 threads
+// keep the link busy.  So the kernel is a SMALL persistent grid (GG_STAGE_CTAS CTAs per SM, default 8, of 256 threads
 // and <= 32 registers: one CTA fits in the slot of one rasterizer CTA) that walks all (view, record) pairs of the
 // batch; launched on the high-priority resolve stream it slips into the first slots the rasterizer of the NEXT batch
 // frees and then runs beside it instead of time-slicing the machine with it.  A group of e_pad lanes fetches one

@@ -135,14 +135,18 @@ __global__ void __launch_bounds__(256) k_resize(const double *__restrict__ in, i
     const int64_t n = (int64_t)h_out * w_out;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
         const int i = (int)(p / w_out), j = (int)(p - (int64_t)i * w_out);
-        const double y = ((double)i + 0.5) * sy - 0.5, x = ((double)j + 0.5) * sx - 0.5;
+        // no FMA contraction here: a coordinate that is an exact integer in ndimage's arithmetic must be one here
+        // too, or floor() picks another pair of neighbours (visible through NaN propagation)
+        const double y = __dadd_rn(__dmul_rn((double)i + 0.5, sy), -0.5), x = __dadd_rn(__dmul_rn((double)j + 0.5, sx), -0.5);
         if (order == 0) {
             const int yi = min(max((int)floor(y + 0.5), 0), h_in - 1), xi = min(max((int)floor(x + 0.5), 0), w_in - 1);
             for (int d = 0; d < D; ++d) out[p * D + d] = resize_out<OUT>(in[((int64_t)yi * w_in + xi) * D + d]);
         } else {
             const double ym = mirror_coord(y, h_in), xm = mirror_coord(x, w_in);
             const int y0 = min((int)floor(ym), h_in - 1), x0 = min((int)floor(xm), w_in - 1);
-            const int y1 = min(y0 + 1, h_in - 1), x1 = min(x0 + 1, w_in - 1);
+            // the upper neighbour of the last pixel is its mirror image (index n - 2), with weight 0: it only matters
+            // for NaN propagation, which ndimage does through zero weights too
+            const int y1 = y0 + 1 < h_in ? y0 + 1 : max(h_in - 2, 0), x1 = x0 + 1 < w_in ? x0 + 1 : max(w_in - 2, 0);
             const double ty = ym - (double)y0, tx = xm - (double)x0;
             for (int d = 0; d < D; ++d) {
                 const double a = in[((int64_t)y0 * w_in + x0) * D + d], b = in[((int64_t)y0 * w_in + x1) * D + d];

@@ -11,6 +11,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
+LAST = 50
 KEYS = {"k_raster_tiles<1, float, 0>": "c2:last_pixel:10", "k_raster_tiles<2, float, 10>": "c2:pixel_sum:10",
         "k_raster_tiles<3, unsigned char, 0>": "c4:render_flat:10"}
 
@@ -26,27 +27,27 @@ def main(src, dst, command):
         for k in KEYS:
             if k in name:
                 per[k][r[mi]].append(float(r[vi].replace(",", "")))
-    inst, traffic, lines = {}, {}, [f"# {command}", "# per launch of 10 views; median over the launches captured (the first launch of a kernel is "
-                                    "dropped: cold instruction cache / first touch)"]
+    inst, traffic, lines = {}, {}, [f"# {command}", f"# per launch of 10 views; mean over the last {LAST} launches of each kernel = one pass over the "
+                                    "500-view survey, the same launches bench.py times (warm-up launches come first and are dropped)"]
     for k, key in KEYS.items():
         if k not in per:
             continue
         m = per[k]
         n = len(m["smsp__inst_executed.sum"])
-        sl = slice(1, None) if n > 2 else slice(None)
-        i = statistics.median(m["smsp__inst_executed.sum"][sl])
-        rd, wr = statistics.median(m["dram__bytes_read.sum"][sl]), statistics.median(m["dram__bytes_write.sum"][sl])
-        t = statistics.median(m["gpu__time_duration.sum"][sl])
+        sl = slice(-LAST, None) if n > LAST else slice(None)  # the launches of the timed pass (warm-up launches come first)
+        i = statistics.mean(m["smsp__inst_executed.sum"][sl])
+        rd, wr = statistics.mean(m["dram__bytes_read.sum"][sl]), statistics.mean(m["dram__bytes_write.sum"][sl])
+        t = statistics.mean(m["gpu__time_duration.sum"][sl])
         # ncu prints bytes in the unit of the column; values here are already scaled by --csv to base units when
         # --print-units base is used
         inst[key], traffic[key] = int(i), int(rd + wr)
         lines.append(f"{k:42s} launches={n:3d} warp_inst={i:14.0f} dram_read_B={rd:14.0f} dram_write_B={wr:14.0f} "
                      f"time_ns={t:12.0f} -> {i / t:7.2f} Gwarp-inst/s, {(rd + wr) / t:7.1f} GB/s (serialised, cold cache)")
-    note = ("smsp__inst_executed.sum per launch of k_raster_tiles (10 views), median over the launches of one ncu pass of: "
+    note = ("smsp__inst_executed.sum per launch of k_raster_tiles (10 views), mean over the survey's 50 launches in one ncu pass of: "
             + command + ". Key = config:mode:views_per_launch.")
     (ROOT / "profiles" / "inst_counts.json").write_text(json.dumps({"_comment": note, **inst}, indent=1) + "\n")
     old = json.loads((ROOT / "profiles" / "traffic.json").read_text())
-    old["_comment"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch of k_raster_tiles, median over the launches of one "
+    old["_comment"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch of k_raster_tiles, mean over the survey's 50 launches in one "
                        "ncu pass of: " + command + ". Key = config:mode:views_per_launch.")
     old.update(traffic)
     (ROOT / "profiles" / "traffic.json").write_text(json.dumps(old, indent=1) + "\n")
