@@ -590,6 +590,12 @@ __device__ __noinline__ bool exact_cover(const GGFaceRec &r, int j, int i, float
     return true;
 }
 
+__device__ __forceinline__ int4 lds128(unsigned addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 // MODE 0: rasters only.  MODE 1: + last pixel of every face (fused last-pixel / vote aggregation).
 // MODE 2: + dense per-pixel score sums (GG_MODE_PIXEL_SUM), T = element type of the score images.
 #ifndef GG_DENSE_MIN_BLOCKS
@@ -600,6 +606,7 @@ __device__ __noinline__ bool exact_cover(const GGFaceRec &r, int j, int i, float
 #define GG_RM_DENSE 2
 #define GG_DENSE_ACC_FLOATS (GG_CHUNK * 32 + 64)  // per warp: slots of the list positions + one scratch row
 #define GG_RM_GATHER 3  // fused render_flat: out[p, :] = tex[face, :] (T = output element type)
+#define GG_RM_WINNERS_ONLY 4  // GG_RM_WINNERS without face-ID / depth rasters (the fused aggregation never asks for them)
 
 struct GGDenseArgs {
     GGPredBatch preds;
@@ -645,7 +652,8 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
                                                                        int n_tiles, int32_t *__restrict__ pix2face,
                                                                        float *__restrict__ depth, int compat_bg,
                                                                        const __grid_constant__ GGDenseArgs dense) {
-    constexpr bool WINNERS = (MODE == GG_RM_WINNERS);
+    constexpr bool WINNERS = (MODE == GG_RM_WINNERS || MODE == GG_RM_WINNERS_ONLY);
+    constexpr bool RASTER_OUT = (MODE != GG_RM_WINNERS_ONLY);  // pix2face / depth may be requested
     // grid: (groups of GG_RASTER_WARPS tiles along x, tile rows, views); one warp per tile
     const int view = blockIdx.z;
     const gg_camera &c = cams.cam[view];
@@ -665,6 +673,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
 
     const int tx0 = (lane & 3) * 8;  // this lane: pixels tx0..tx0+7 of row ty
     const int ty = lane >> 2;
+    const unsigned s_faces_addr = (unsigned)__cvta_generic_to_shared(s_faces);
 
     // Per pixel: the winner's key (bits of its 1/z, which is positive -> ordered like the float; then ~face so that the
     // lower ID wins a tie) compared as ONE 64-bit quantity, and its position in the tile's list (-1 = none).
@@ -698,29 +707,35 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
 
     for (int base = 0; base < len; base += GG_CHUNK) {
         const int n = min(GG_CHUNK, len - base);
-        {  // stream n ready-made 64-byte setups into shared memory: 16 B per lane, 4 x (up to) 512 B per warp
-            const int4 *src = reinterpret_cast<const int4 *>(vs.bins + beg + base) + lane;
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(s_faces) + lane * 16;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (q * 32 + lane < n * 4) {
-                    const int4 v = __ldg(src + q * 32);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + q * 512), "r"(v.x), "r"(v.y), "r"(v.z),
-                                 "r"(v.w)
+        {  // stream n ready-made 64-byte setups into shared memory, 16 B per lane and pass: the usual list of <= 8
+           // faces takes ONE pass (a four-way unrolled, predicated copy cost ~90 instructions per tile)
+            const int4 *src = reinterpret_cast<const int4 *>(vs.bins + beg + base);
+#pragma unroll 1
+            for (int idx = lane; idx < n * 4; idx += 64) {
+                const bool two = idx + 32 < n * 4;
+                const int4 v0 = __ldg(src + idx);
+                int4 v1 = v0;
+                if (two) v1 = __ldg(src + idx + 32);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_faces_addr + idx * 16), "r"(v0.x), "r"(v0.y),
+                             "r"(v0.z), "r"(v0.w)
+                             : "memory");
+                if (two)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_faces_addr + idx * 16 + 512), "r"(v1.x),
+                                 "r"(v1.y), "r"(v1.z), "r"(v1.w)
                                  : "memory");
-                }
             }
         }
         __syncwarp();
-        for (int k = 0; k < n; ++k) {
-            const int4 q3 = *reinterpret_cast<const int4 *>(&s_faces[k].lanemask);  // lanemask face rec fast
+        unsigned fa = s_faces_addr;  // shared-memory address of setup k: one register, bumped by 64 per face
+        for (int k = 0; k < n; ++k, fa += 64) {
+            const int4 q3 = lds128(fa + 48);  // lanemask face rec fast
             if (!((((unsigned)q3.x) >> lane) & 1u)) continue;
             const unsigned nface = ~(unsigned)q3.y;
             const int pos = base + k;
             if (q3.w) {
-                const int4 q0 = *reinterpret_cast<const int4 *>(&s_faces[k].e[0]);   // e0 e1 e2 sx0
-                const int4 q1 = *reinterpret_cast<const int4 *>(&s_faces[k].sx[1]);  // sx1 sx2 sy0 sy1
-                const int4 q2 = *reinterpret_cast<const int4 *>(&s_faces[k].sy[2]);  // sy2 w_org gx gy
+                const int4 q0 = lds128(fa);       // e0 e1 e2 sx0
+                const int4 q1 = lds128(fa + 16);  // sx1 sx2 sy0 sy1
+                const int4 q2 = lds128(fa + 32);  // sy2 w_org gx gy
                 const int s0 = q0.w, s1 = q1.x, s2 = q1.y;
                 int e0 = q0.x + s0 * tx0 + q1.z * ty;
                 int e1 = q0.y + s1 * tx0 + q1.w * ty;
@@ -767,7 +782,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
     // ---- write the 8 pixels of this lane ----
     const int row = tile_y0 + ty, col = tile_x0 + tx0;
     const bool row_ok = row < H;
-    if (row_ok && col < W) {
+    if (RASTER_OUT && row_ok && col < W) {
         const int64_t o = ((int64_t)view * H + row) * W + col;
         if (col + 7 < W && ((o & 3) == 0)) {
             if (pix2face) {
@@ -804,10 +819,15 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
             // tile entirely inside the image and every list position has a shared-memory slot (warp-uniform): one
             // predicated shared-memory atomic per run-end, nothing else
             const int after = has_next ? next_first : -2;
+            const unsigned s_win_addr = (unsigned)__cvta_generic_to_shared(s_win);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int nxt = (i < 7) ? bp[i < 7 ? i + 1 : 7] : after;
-                if ((bp[i] >= 0) & (bp[i] != nxt)) atomicMax(&s_win[bp[i]], pix0 + i);
+                // one PREDICATED reduction per run-end (no branch / reconvergence bookkeeping around it)
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, %1;\n\tsetp.ge.and.s32 p, %0, 0, p;\n\t"
+                             "@p red.shared.max.s32 [%2], %3;\n\t}" ::"r"(bp[i]), "r"(nxt),
+                             "r"(s_win_addr + (unsigned)bp[i] * 4u), "r"(pix0 + i)
+                             : "memory");
             }
             if (compat_bg) {
 #pragma unroll
@@ -1290,7 +1310,11 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
         }
         return GG_OK;
     }
-    if (want_winners)
+    if (want_winners && !d_pix2face && !d_depth)  // the fused aggregation: no raster leaves the SM
+        GG_LAUNCH(ctx, GG_ST_RASTER, st,
+                  (k_raster_tiles<GG_RM_WINNERS_ONLY, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
+                      cb, ctx->vset[ctx->cur], n_tiles, nullptr, nullptr, compat_bg ? (int)ctx->F : 0, da)));
+    else if (want_winners)
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
                   (k_raster_tiles<GG_RM_WINNERS, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
                       cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, d_depth, compat_bg ? (int)ctx->F : 0, da)));
