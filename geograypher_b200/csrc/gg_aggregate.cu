@@ -369,56 +369,61 @@ static int launch_reset_winners(gg_context *ctx, int n, int flags, cudaStream_t 
 // host memory the rows are fetched over PCIe: first ALL of them, in parallel, into a device staging table (one thread
 // per element, so a warp's loads of one row share their sectors), then k_resolve_batch walks the views in order on
 // the staged copy.  The winners are re-pointed from pixel indices to staging rows in between.
-// The fetch is bound by the PCIe link's small-read rate (~0.3 G rows/s), not by the SMs: a few hundred rows in flight
-// keep the link busy.  So the kernel is a SMALL persistent grid (GG_STAGE_CTAS CTAs per SM, default 8, of 256 threads
-// and <= 32 registers: one CTA fits in the slot of one rasterizer CTA) that walks all (view, record) pairs of the
-// batch; launched on the high-priority resolve stream it slips into the first slots the rasterizer of the NEXT batch
-// frees and then runs beside it instead of time-slicing the machine with it.  A group of e_pad lanes fetches one
-// row, so the loads of a row share their sectors.  The lane that owns element 0 re-points the face's winner from the
-// pixel index to the staging row (nobody else reads this view's winner of this face before k_resolve_batch).
-template <typename T>
-__global__ void __launch_bounds__(256, 8) k_stage_rows(const __grid_constant__ GGViewBatch views, int n_views, int64_t F,
-                                                       const __grid_constant__ GGPredBatch preds, int E, int flags,
-                                                       T *__restrict__ stage, int64_t rows_per_view) {
+// Two steps.  (1) k_compact_stage walks the view's face records (a chain of dependent L2 reads: record -> face ->
+// winner) and lists the winning pixel of every visible face densely, re-pointing the face's winner from the pixel to
+// its row in the staging table.  (2) k_fetch_rows is then nothing but the gather itself: one thread per ELEMENT of
+// the listed rows, flat indexing, so that consecutive lanes read consecutive bytes of a row and a warp covers 32 / E
+// rows -- the shape that reaches the link's scattered-read rate in scripts/pcie_rows_bench.cu (~0.26 G 40-byte
+// rows/s; the one-kernel version that did the record walk and the fetch together ran 3x below it).  The link needs
+// only a few hundred reads in flight, so the fetch is a SMALL grid (GG_STAGE_CTAS CTAs per SM): launched on the
+// high-priority resolve stream it slips into the first slots the rasterizer of the NEXT batch frees and runs beside
+// it instead of time-slicing the machine with it.
+__global__ void __launch_bounds__(256) k_compact_stage(const __grid_constant__ GGViewBatch views, int n_views, int64_t F,
+                                                       int flags, int32_t *__restrict__ row_pix, int64_t rows_per_view,
+                                                       int32_t *__restrict__ row_count) {
     for (int v = 0; v < n_views; ++v)
         if (views.v[v].counters[3] != 0) return;
+    const int view = blockIdx.y;
+    const GGViewScratch &vs = views.v[view];
+    const int n_recs = vs.counters[1];
     const bool compat = (flags & GG_FLAG_COMPAT_NEG) != 0;
-    const int rows_per_pass = gridDim.x * blockDim.y;
+    const int n = n_recs + ((compat && vs.counters[5] < 0) ? 1 : 0);
+    int32_t *__restrict__ pix = row_pix + (int64_t)view * rows_per_view;
+    for (int r0 = blockIdx.x * blockDim.x; r0 < n; r0 += gridDim.x * blockDim.x) {
+        const int r = r0 + threadIdx.x;
+        int64_t f = -1;
+        int p = -1;
+        if (r < n && !(r < n_recs && vs.recs[r].dup)) {
+            f = r < n_recs ? (int64_t)vs.recs[r].face : F - 1;
+            p = vs.winner[f];
+        }
+        const bool keep = p >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        int base = 0;
+        if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(&row_count[view], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) {
+            const int row = base + __popc(m & ((1u << (threadIdx.x & 31)) - 1));  // < rows_per_view: one row per record
+            pix[row] = p;
+            vs.winner[f] = row;  // nobody else reads this view's winner of this face before k_resolve_batch
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 8) k_fetch_rows(int n_views, const __grid_constant__ GGPredBatch preds, int E,
+                                                       unsigned div_magic, const int32_t *__restrict__ row_pix,
+                                                       int64_t rows_per_view, const int32_t *__restrict__ row_count,
+                                                       T *__restrict__ stage) {
     for (int view = 0; view < n_views; ++view) {
-        const GGViewScratch &vs = views.v[view];
-        const int n_recs = vs.counters[1];
-        const int n = n_recs + ((compat && vs.counters[5] < 0) ? 1 : 0);
         const T *__restrict__ pred = (const T *)preds.p[view];
+        const int32_t *__restrict__ pix = row_pix + (int64_t)view * rows_per_view;
         T *__restrict__ out = stage + (int64_t)view * rows_per_view * E;
-        // two rows per group and pass: their PCIe reads overlap
-        for (int r0 = blockIdx.x * blockDim.y + threadIdx.y; r0 < n; r0 += 2 * rows_per_pass) {
-            int rr[2] = {r0, r0 + rows_per_pass};
-            int pp[2] = {-1, -1};
-            int64_t ff[2] = {0, 0};
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int r = rr[u];
-                if (r >= n) continue;
-                if (r < n_recs && vs.recs[r].dup) continue;
-                ff[u] = r < n_recs ? (int64_t)vs.recs[r].face : F - 1;
-                pp[u] = vs.winner[ff[u]];
-            }
-            T val[2][2];
-            const int e0 = threadIdx.x, e1 = threadIdx.x + blockDim.x;  // E <= 2 * blockDim.x (E <= 64)
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (pp[u] < 0) continue;
-                if (e0 < E) val[u][0] = pred[(int64_t)pp[u] * E + e0];
-                if (e1 < E) val[u][1] = pred[(int64_t)pp[u] * E + e1];
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (pp[u] < 0) continue;
-                if (e0 < E) out[(int64_t)rr[u] * E + e0] = val[u][0];
-                if (e1 < E) out[(int64_t)rr[u] * E + e1] = val[u][1];
-                for (int e = e1 + blockDim.x; e < E; e += blockDim.x) out[(int64_t)rr[u] * E + e] = pred[(int64_t)pp[u] * E + e];
-                if (threadIdx.x == 0) vs.winner[ff[u]] = rr[u];
-            }
+        const unsigned total = (unsigned)row_count[view] * (unsigned)E;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+            const unsigned row = E == 1 ? i : __umulhi(i, div_magic);  // i / E (exact: i < 2^27, see the launch)
+            const unsigned e = i - row * (unsigned)E;
+            out[i] = pred[(int64_t)pix[row] * E + e];
         }
     }
 }
@@ -426,7 +431,14 @@ __global__ void __launch_bounds__(256, 8) k_stage_rows(const __grid_constant__ G
 template <typename T>
 static int stage_host_rows(gg_context *ctx, int n, GGPredBatch &pb, int E, int flags, cudaStream_t st) {
     const int64_t rows_per_view = ctx->cap_recs + 1;
-    const size_t need = (size_t)n * rows_per_view * E * sizeof(T);
+    if (rows_per_view * E >= (1LL << 27)) {
+        gg_set_error("gg_project_aggregate: too many face records x channels for the host-row staging table");
+        return GG_ERR_INVALID;
+    }
+    // [n][rows_per_view][E] staged rows, then [n][rows_per_view] winning pixels, then [32] row counts
+    const size_t b_rows = (size_t)n * rows_per_view * E * sizeof(T), b_rows_al = (b_rows + 255) / 256 * 256;
+    const size_t b_pix = (size_t)n * rows_per_view * sizeof(int32_t), b_pix_al = (b_pix + 255) / 256 * 256;
+    const size_t need = b_rows_al + b_pix_al + 256;
     if (ctx->stage_bytes < need) {
         if (ctx->d_stage) {
             GG_CUDA(cudaDeviceSynchronize());
@@ -437,11 +449,17 @@ static int stage_host_rows(gg_context *ctx, int n, GGPredBatch &pb, int E, int f
         ctx->stage_bytes = need;
     }
     T *stage = (T *)ctx->d_stage;
-    int e_pad = 1;
-    while (e_pad < E && e_pad < 32) e_pad <<= 1;
-    const dim3 g((unsigned)(ctx->sm_count * ctx->stage_ctas)), b(e_pad, 256 / e_pad);
+    int32_t *row_pix = (int32_t *)(ctx->d_stage + b_rows_al);
+    int32_t *row_count = (int32_t *)(ctx->d_stage + b_rows_al + b_pix_al);
+    GG_CUDA(cudaMemsetAsync(row_count, 0, GG_MAX_VIEWS_PER_CALL * sizeof(int32_t), st));
+    GG_LAUNCH(ctx, GG_ST_RESOLVE, st,
+              k_compact_stage<<<dim3((unsigned)(ctx->sm_count * 2), n), 256, 0, st>>>(ctx->vset[ctx->cur], n, ctx->F, flags,
+                                                                                    row_pix, rows_per_view, row_count));
+    // floor(i / E) == umulhi(i, ceil(2^32 / E)) for i * E < 2^32 -- far beyond the 2^27 elements checked above
+    const unsigned magic = E > 1 ? (unsigned)((0x100000000ULL + (unsigned)E - 1) / (unsigned)E) : 0u;
     GG_LAUNCH(ctx, GG_ST_STAGE, st,
-              k_stage_rows<T><<<g, b, 0, st>>>(ctx->vset[ctx->cur], n, ctx->F, pb, E, flags, stage, rows_per_view));
+              k_fetch_rows<T><<<(unsigned)(ctx->sm_count * ctx->stage_ctas), 256, 0, st>>>(n, pb, E, magic, row_pix,
+                                                                                        rows_per_view, row_count, stage));
     for (int i = 0; i < n; ++i) pb.p[i] = stage + (int64_t)i * rows_per_view * E;
     return GG_OK;
 }

@@ -6,6 +6,9 @@
 #include <vector>
 #include <algorithm>
 #include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <cstdint>
+#include <cstring>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
 // one thread per 4-byte word of a row (1-byte rows: one thread per row)
@@ -20,17 +23,30 @@ __global__ void k_rows(const unsigned char *__restrict__ src, const int *__restr
     }
 }
 
-int main() {
-    const long long P = 19961856;
+int main(int argc, char **argv) {
+    const int n_img = argc > 1 ? atoi(argv[1]) : 1;  // rows are spread over n_img x 19.96 M pixels of pinned memory
+    const long long P = 19961856LL * n_img;
     const int n = 250000;
     unsigned char *h = nullptr;
-    CK(cudaHostAlloc(&h, P * 64, cudaHostAllocDefault));
-    for (long long i = 0; i < P * 64; i += 4096) h[i] = (unsigned char)i;
+    const int thp = argc > 2 ? atoi(argv[2]) : 0;  // 1: transparent huge pages (mmap + MADV_HUGEPAGE) + cudaHostRegister
+    if (thp) {
+        const size_t bytes = ((size_t)P * 64 + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+        void *m = mmap(nullptr, bytes + (2u << 20), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m == MAP_FAILED) { printf("mmap failed\n"); return 1; }
+        h = (unsigned char *)(((uintptr_t)m + (2u << 20) - 1) / (2u << 20) * (2u << 20));
+        if (madvise(h, bytes, MADV_HUGEPAGE) != 0) printf("madvise(MADV_HUGEPAGE) failed\n");
+        for (size_t i = 0; i < bytes; i += 4096) h[i] = (unsigned char)i;  // fault the pages in (as huge pages)
+        CK(cudaHostRegister(h, bytes, cudaHostRegisterDefault));
+        printf("THP-backed, cudaHostRegister'ed buffer\n");
+    } else {
+        CK(cudaHostAlloc(&h, P * 64, cudaHostAllocDefault));
+        for (long long i = 0; i < P * 64; i += 4096) h[i] = (unsigned char)i;
+    }
     std::vector<int> pix(n);
     srand(1);
     for (int v = 0; v < 10; ++v) {
         std::vector<int> p(n / 10);
-        for (auto &x : p) x = (int)(((long long)rand() * 32768 + rand()) % P);
+        for (auto &x : p) x = (int)((((long long)rand() * 32768 + rand()) * 31 + rand()) % P);
         std::sort(p.begin(), p.end());
         std::copy(p.begin(), p.end(), pix.begin() + v * (n / 10));
     }
@@ -38,7 +54,8 @@ int main() {
     CK(cudaMalloc(&d_pix, n * 4)); CK(cudaMalloc(&d_dst, (size_t)n * 64));
     CK(cudaMemcpy(d_pix, pix.data(), n * 4, cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int row_bytes : {1, 20, 32, 40, 64}) {
+    printf("pinned buffer: %.2f GB (%d x 19.96 Mpx x 64 B)\n", P * 64 / 1e9, n_img);
+    for (int row_bytes : {1, 40}) {
         for (int blocks : {148, 148 * 4, 148 * 16}) {
             for (int rep = 0; rep < 2; ++rep) {
                 CK(cudaEventRecord(e0));
