@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../libgeograypher_b200.so
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -O2
-       --fmad=true -Xptxas -v -ccbin /usr/bin/g++)
+       --fmad=true -Xptxas -v -ccbin /usr/bin/g++ ${NVCC_EXTRA:-})
 mkdir -p build
 for f in gg_api gg_raster gg_aggregate gg_warp gg_polygons; do
   "$NVCC" "${FLAGS[@]}" -c $f.cu -o build/$f.o 2> build/$f.ptxas.log || { cat build/$f.ptxas.log; exit 1; }

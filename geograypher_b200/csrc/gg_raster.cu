@@ -30,6 +30,9 @@
 #ifndef GG_FILL_MIN_BLOCKS
 #define GG_FILL_MIN_BLOCKS 4
 #endif
+#ifndef GG_FILL_LANES
+#define GG_FILL_LANES 8  // lanes that share one face record in k_fill_bins and split its tiles (power of two)
+#endif
 
 namespace {
 
@@ -536,10 +539,10 @@ __global__ void __launch_bounds__(256, GG_FILL_MIN_BLOCKS) k_fill_bins(int64_t c
     if (vs.counters[3] != 0) return;
     const int n_recs = vs.counters[1];
     const int tiles_x = (cams.cam[view].W + GG_TILE_W - 1) / GG_TILE_W;
-    // 8 lanes share one record and split its tiles, so that the atomicAdd -> store chains of a face run in parallel
-    const int sub = threadIdx.x & 7;
-    const int groups = (gridDim.x * blockDim.x) >> 3;
-    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n_recs; r += groups) {
+    // GG_FILL_LANES lanes share one record and split its tiles, so that the atomicAdd -> store chains of a face run in parallel
+    const int sub = threadIdx.x & (GG_FILL_LANES - 1);
+    const int groups = (gridDim.x * blockDim.x) / GG_FILL_LANES;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) / GG_FILL_LANES; r < n_recs; r += groups) {
         const GGFaceRec rec = load_vec16(&vs.recs[r]);
         const int tx0 = rec.jmin / GG_TILE_W, tx1 = rec.jmax / GG_TILE_W;
         const int ty0 = rec.imin / GG_TILE_H, ty1 = rec.imax / GG_TILE_H;
@@ -549,7 +552,7 @@ __global__ void __launch_bounds__(256, GG_FILL_MIN_BLOCKS) k_fill_bins(int64_t c
             // lane `sub` looks at bits sub, sub + 8, ... of the mask (a box of up to 64 tiles): no bit counting, and the
             // 8 lanes of a record stay in step
             const float inv_ntx = 1.0f / (float)ntx;
-            for (int b = sub; b < 64 && (tmask >> b) != 0; b += 8) {
+            for (int b = sub; b < 64 && (tmask >> b) != 0; b += GG_FILL_LANES) {
                 if (!((tmask >> b) & 1ull)) continue;
                 const int by = (int)(((float)b + 0.5f) * inv_ntx);  // b / ntx, exact for these small integers
                 const int tx = tx0 + (b - by * ntx), ty = ty0 + by;
@@ -559,7 +562,7 @@ __global__ void __launch_bounds__(256, GG_FILL_MIN_BLOCKS) k_fill_bins(int64_t c
             }
         } else {
             const int total = ntx * (ty1 - ty0 + 1);
-            for (int i = sub; i < total; i += 8) {
+            for (int i = sub; i < total; i += GG_FILL_LANES) {
                 const int tx = tx0 + i % ntx, ty = ty0 + i / ntx;
                 if (!tile_may_touch(rec, tx, ty)) continue;
                 const int t = ty * tiles_x + tx;

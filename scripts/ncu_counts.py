@@ -12,7 +12,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 LAST = 50
-KEYS = {"k_raster_tiles<1, float, 0>": "c2:last_pixel:10", "k_raster_tiles<2, float, 10>": "c2:pixel_sum:10",
+KEYS = {"k_raster_tiles<4, float, 0>": "c2:last_pixel:10", "k_raster_tiles<2, float, 10>": "c2:pixel_sum:10",
         "k_raster_tiles<3, unsigned char, 0>": "c4:render_flat:10"}
 
 
