@@ -14,6 +14,7 @@
 #define GG_HALF 128
 #define GG_SUBPIX_LOG2 8
 #define GG_COORD_CLAMP 536870912.0f  // 2^29 sub-pixel units
+#define GG_GUARD_PX 1048576.0f       // contract C6: guard band of +-2^20 px (half of what the clamp can hold)
 
 // ---- tiling ------------------------------------------------------------------------------------------
 #define GG_TILE_W 32           // one warp rasterizes one 32 x 8 px tile; lane = 8 consecutive px of one row

@@ -44,6 +44,7 @@ struct Proj {
     int X, Y;
     float invz;
     bool ok;
+    bool far;  // the snapped coordinates would not even be finite (contract C6 clips such a triangle first)
 };
 
 struct Cam3 {  // camera-space point
@@ -76,6 +77,7 @@ __device__ __forceinline__ Proj to_screen(const Cam3 &q, const gg_camera &c) {
     p.X = 0;
     p.Y = 0;
     p.invz = 0.f;
+    p.far = false;
     if (p.ok) {
         const float sx = __fadd_rn(__fdiv_rn(__fmul_rn(c.f, q.x), q.z), c.px);
         const float sy = __fadd_rn(__fdiv_rn(__fmul_rn(c.f, q.y), q.z), c.py);
@@ -83,6 +85,7 @@ __device__ __forceinline__ Proj to_screen(const Cam3 &q, const gg_camera &c) {
         float fy = rintf(__fmul_rn(sy, (float)GG_SUBPIX));
         if (!isfinite(fx) || !isfinite(fy)) {
             p.ok = false;
+            p.far = true;
         } else {
             fx = fminf(fmaxf(fx, -GG_COORD_CLAMP), GG_COORD_CLAMP);
             fy = fminf(fmaxf(fy, -GG_COORD_CLAMP), GG_COORD_CLAMP);
@@ -281,23 +284,29 @@ __device__ __forceinline__ bool tile_may_touch(const GGFaceRec &r, int tx, int t
     return true;
 }
 
-// Screen-space record of one (sub-)triangle given in camera space; false when it cannot cover a pixel centre.
-__device__ __forceinline__ bool build_record(const Cam3 &qa, const Cam3 &qb, const Cam3 &qc, int face_id,
-                                             const gg_camera &c, GGFaceRec &r) {
+// Screen-space record of one (sub-)triangle given in camera space.  Returns 1 and the record, 0 when the triangle
+// cannot cover a pixel centre, 2 (only with check_guard) when a vertex projects beyond the guard band of contract C6:
+// the caller then clips the triangle against the band first.
+__device__ __forceinline__ int build_record(const Cam3 &qa, const Cam3 &qb, const Cam3 &qc, int face_id,
+                                            const gg_camera &c, GGFaceRec &r, bool check_guard) {
     const Proj p0 = to_screen(qa, c);
     Proj p1 = to_screen(qb, c);
     Proj p2 = to_screen(qc, c);
-    if (!(p0.ok && p1.ok && p2.ok)) return false;
+    if (!(p0.ok && p1.ok && p2.ok)) return (check_guard && (p0.far || p1.far || p2.far)) ? 2 : 0;
+    const int xmin = min(p0.X, min(p1.X, p2.X)), xmax = max(p0.X, max(p1.X, p2.X));
+    const int ymin = min(p0.Y, min(p1.Y, p2.Y)), ymax = max(p0.Y, max(p1.Y, p2.Y));
+    // contract C6: a vertex beyond the guard band of +-2^20 px.  Tested on the snapped integers: beyond 2^16 px the
+    // float32 coordinate times 256 is an integer already, so |X| > 2^28 <=> |sx| > 2^20 exactly (the oracle's test).
+    constexpr int kGuard = (int)GG_GUARD_PX * GG_SUBPIX;
+    if (check_guard && (xmin < -kGuard || xmax > kGuard || ymin < -kGuard || ymax > kGuard)) return 2;
     const long long area2 = (long long)(p1.X - p0.X) * (long long)(p2.Y - p0.Y) -
                             (long long)(p2.X - p0.X) * (long long)(p1.Y - p0.Y);
-    if (area2 == 0) return false;
+    if (area2 == 0) return 0;
     if (area2 < 0) {  // make the interior the positive side
         const Proj t = p1;
         p1 = p2;
         p2 = t;
     }
-    const int xmin = min(p0.X, min(p1.X, p2.X)), xmax = max(p0.X, max(p1.X, p2.X));
-    const int ymin = min(p0.Y, min(p1.Y, p2.Y)), ymax = max(p0.Y, max(p1.Y, p2.Y));
     // pixel centres 256*j+128 inside [xmin, xmax]; arithmetic shift == floor division
     int jmin = (xmin + (GG_SUBPIX - GG_HALF - 1)) >> GG_SUBPIX_LOG2;
     int jmax = (xmax - GG_HALF) >> GG_SUBPIX_LOG2;
@@ -307,7 +316,7 @@ __device__ __forceinline__ bool build_record(const Cam3 &qa, const Cam3 &qb, con
     imin = max(imin, 0);
     jmax = min(jmax, c.W - 1);
     imax = min(imax, c.H - 1);
-    if (jmin > jmax || imin > imax) return false;
+    if (jmin > jmax || imin > imax) return 0;
     const long long X[3] = {p0.X, p1.X, p2.X}, Y[3] = {p0.Y, p1.Y, p2.Y};
     long long Ak[3], Bk[3], E0[3];
 #pragma unroll
@@ -337,7 +346,156 @@ __device__ __forceinline__ bool build_record(const Cam3 &qa, const Cam3 &qb, con
     r.jmax = (uint16_t)jmax;
     r.imin = (uint16_t)imin;
     r.imax = (uint16_t)imax;
-    return true;
+    return 1;
+}
+
+// Count the tiles a record touches (one atomicAdd each), fill its tile mask and store it at recs[idx]; beyond the
+// capacity only the overflow flags are raised.
+__device__ __forceinline__ void emit_record(GGFaceRec &r, int idx, const GGViewScratch &vs, int64_t F, int64_t cap_recs,
+                                            int32_t *__restrict__ sticky, int tiles_x) {
+    if (idx < cap_recs) {
+        const int tx0 = r.jmin / GG_TILE_W, tx1 = r.jmax / GG_TILE_W;
+        const int ty0 = r.imin / GG_TILE_H, ty1 = r.imax / GG_TILE_H;
+        const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
+        unsigned long long tmask = 0;
+        const bool small = ntx * nty <= 64;
+        // tile_may_touch for every tile of the box, evaluated incrementally: the three edge functions at
+        // each tile's innermost corner differ from tile to tile by constants (same int64 values)
+        long long e_row[3], dex[3], dey[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int xc = tx0 * GG_TILE_W + (r.A[k] > 0 ? GG_TILE_W - 1 : 0);
+            const int yc = ty0 * GG_TILE_H + (r.B[k] > 0 ? GG_TILE_H - 1 : 0);
+            e_row[k] = r.C[k] + (long long)r.A[k] * GG_SUBPIX * xc + (long long)r.B[k] * GG_SUBPIX * yc;
+            dex[k] = (long long)r.A[k] * (GG_SUBPIX * GG_TILE_W);
+            dey[k] = (long long)r.B[k] * (GG_SUBPIX * GG_TILE_H);
+        }
+        int bit = 0;
+        for (int ty = ty0; ty <= ty1; ++ty) {
+            long long e0 = e_row[0], e1 = e_row[1], e2 = e_row[2];
+            int32_t *row_count = vs.tile_count + ty * tiles_x;
+            for (int tx = tx0; tx <= tx1; ++tx, ++bit) {
+                if ((e0 | e1 | e2) >= 0) {
+                    atomicAdd(&row_count[tx], 1);
+                    if (small) tmask |= 1ull << bit;
+                }
+                e0 += dex[0];
+                e1 += dex[1];
+                e2 += dex[2];
+            }
+            e_row[0] += dey[0];
+            e_row[1] += dey[1];
+            e_row[2] += dey[2];
+        }
+        r.tmask = small ? tmask : ~0ull;
+        store_vec16(&vs.recs[idx], r);
+        if (r.face == (int32_t)(F - 1)) vs.counters[5] = idx;
+    } else {
+        atomicOr(&vs.counters[3], 1);
+        atomicOr(sticky, 1);
+    }
+}
+
+// ---- contract C6: guard-band clipping (rare: faces cut by the near plane close to the camera, huge faces) ----------
+// Signed distance (>= 0: inside) of a camera-space point to guard plane k: 0 right, 1 left, 2 bottom, 3 top.
+__device__ __forceinline__ float guard_dist(const Cam3 &p, const gg_camera &c, int k) {
+    switch (k) {
+        case 0: return __fsub_rn(__fmul_rn(__fsub_rn(GG_GUARD_PX, c.px), p.z), __fmul_rn(c.f, p.x));
+        case 1: return __fadd_rn(__fmul_rn(__fadd_rn(GG_GUARD_PX, c.px), p.z), __fmul_rn(c.f, p.x));
+        case 2: return __fsub_rn(__fmul_rn(__fsub_rn(GG_GUARD_PX, c.py), p.z), __fmul_rn(c.f, p.y));
+        default: return __fadd_rn(__fmul_rn(__fadd_rn(GG_GUARD_PX, c.py), p.z), __fmul_rn(c.f, p.y));
+    }
+}
+
+// The (up to two) camera-space triangles of face fi after clipping against the near plane (contract C5).
+__device__ __forceinline__ int face_triangles(const float4 *__restrict__ verts, const int4 *__restrict__ faces, int64_t fi,
+                                              const gg_camera &c, Cam3 (&tri)[2][3], int &face_id) {
+    const int4 f = faces[fi];
+    face_id = f.w;
+    const float4 a = verts[f.x], b = verts[f.y], d = verts[f.z];
+    const Cam3 p[3] = {cam_space(a.x, a.y, a.z, c), cam_space(b.x, b.y, b.z, c), cam_space(d.x, d.y, d.z, c)};
+    bool finite = true;
+    int nfront = 0;
+    bool front[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        finite = finite && isfinite(p[k].x) && isfinite(p[k].y) && isfinite(p[k].z);
+        front[k] = p[k].z >= c.znear;
+        nfront += front[k] ? 1 : 0;
+    }
+    if (finite && nfront == 3) {
+        tri[0][0] = p[0];
+        tri[0][1] = p[1];
+        tri[0][2] = p[2];
+        return 1;
+    }
+    if (finite && nfront == 1) {  // rotate so that the vertex in front comes first: (A, B, C)
+        const int ia = front[0] ? 0 : (front[1] ? 1 : 2);
+        const Cam3 A = p[ia], B = p[(ia + 1) % 3], C = p[(ia + 2) % 3];
+        tri[0][0] = A;
+        tri[0][1] = clip_edge(A, B, c.znear);
+        tri[0][2] = clip_edge(A, C, c.znear);
+        return 1;
+    }
+    if (finite && nfront == 2) {  // rotate so that the vertex behind comes last: (A, B, C)
+        const int ic = !front[0] ? 0 : (!front[1] ? 1 : 2);
+        const Cam3 A = p[(ic + 1) % 3], B = p[(ic + 2) % 3], C = p[ic];
+        const Cam3 rbc = clip_edge(B, C, c.znear), rac = clip_edge(A, C, c.znear);
+        tri[0][0] = A;
+        tri[0][1] = B;
+        tri[0][2] = rbc;
+        tri[1][0] = A;
+        tri[1][1] = rbc;
+        tri[1][2] = rac;
+        return 2;
+    }
+    return 0;
+}
+
+// Sutherland-Hodgman against the four guard planes in float32 with a fixed operation order (the oracle does the
+// same arithmetic), fan triangulation, one record per fan triangle appended with its own atomicAdd.
+// The triangle is re-derived from the face, so that nothing but (fi, t) stays live across this call in the caller.
+__device__ __noinline__ bool setup_guarded(const float4 *__restrict__ verts, const int4 *__restrict__ faces, int64_t fi, int t,
+                                           const gg_camera &c, const GGViewScratch &vs, int64_t F, int64_t cap_recs,
+                                           int32_t *__restrict__ sticky, int tiles_x, bool kept_before) {
+    Cam3 tri[2][3];
+    int face_id;
+    if (face_triangles(verts, faces, fi, c, tri, face_id) <= t) return kept_before;
+    Cam3 buf[2][8];
+    int n = 3, cur = 0;
+    buf[0][0] = tri[t][0];
+    buf[0][1] = tri[t][1];
+    buf[0][2] = tri[t][2];
+    for (int k = 0; k < 4 && n >= 3; ++k) {
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const Cam3 P = buf[cur][i], Q = buf[cur][(i + 1) % n];
+            const float dP = guard_dist(P, c, k), dQ = guard_dist(Q, c, k);
+            const bool inP = dP >= 0.0f, inQ = dQ >= 0.0f;
+            if (inP && m < 8) buf[1 - cur][m++] = P;
+            if (inP != inQ && m < 8) {  // from the inside vertex towards the outside one
+                const Cam3 I = inP ? P : Q, O = inP ? Q : P;
+                const float dI = inP ? dP : dQ, dO = inP ? dQ : dP;
+                const float t = __fdiv_rn(dI, __fsub_rn(dI, dO));
+                Cam3 R;
+                R.x = __fadd_rn(I.x, __fmul_rn(t, __fsub_rn(O.x, I.x)));
+                R.y = __fadd_rn(I.y, __fmul_rn(t, __fsub_rn(O.y, I.y)));
+                R.z = __fadd_rn(I.z, __fmul_rn(t, __fsub_rn(O.z, I.z)));
+                buf[1 - cur][m++] = R;
+            }
+        }
+        n = m;
+        cur = 1 - cur;
+    }
+    for (int i = 1; i + 1 < n; ++i) {
+        GGFaceRec r;
+        if (build_record(buf[cur][0], buf[cur][i], buf[cur][i + 1], face_id, c, r, false) == 1) {
+            r.dup = kept_before ? 1 : 0;
+            kept_before = true;
+            emit_record(r, atomicAdd(&vs.counters[1], 1), vs, F, cap_recs, sticky, tiles_x);
+        }
+    }
+    return kept_before;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -358,97 +516,26 @@ __global__ void __launch_bounds__(GG_BLOCK_FACES, GG_SETUP_MIN_BLOCKS) k_setup_f
         // up to two triangles per face: faces crossing the near plane are clipped in camera space (contract C5)
         Cam3 tri[2][3];
         int n_tri = 0, face_id = -1;
-        if (fi < F) {
-            const int4 f = faces[fi];
-            face_id = f.w;
-            const float4 a = verts[f.x], b = verts[f.y], d = verts[f.z];
-            const Cam3 p[3] = {cam_space(a.x, a.y, a.z, c), cam_space(b.x, b.y, b.z, c), cam_space(d.x, d.y, d.z, c)};
-            bool finite = true;
-            int nfront = 0;
-            bool front[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                finite = finite && isfinite(p[k].x) && isfinite(p[k].y) && isfinite(p[k].z);
-                front[k] = p[k].z >= c.znear;
-                nfront += front[k] ? 1 : 0;
-            }
-            if (finite && nfront == 3) {
-                tri[0][0] = p[0];
-                tri[0][1] = p[1];
-                tri[0][2] = p[2];
-                n_tri = 1;
-            } else if (finite && nfront == 1) {  // rotate so that the vertex in front comes first: (A, B, C)
-                const int ia = front[0] ? 0 : (front[1] ? 1 : 2);
-                const Cam3 A = p[ia], B = p[(ia + 1) % 3], C = p[(ia + 2) % 3];
-                tri[0][0] = A;
-                tri[0][1] = clip_edge(A, B, c.znear);
-                tri[0][2] = clip_edge(A, C, c.znear);
-                n_tri = 1;
-            } else if (finite && nfront == 2) {  // rotate so that the vertex behind comes last: (A, B, C)
-                const int ic = !front[0] ? 0 : (!front[1] ? 1 : 2);
-                const Cam3 A = p[(ic + 1) % 3], B = p[(ic + 2) % 3], C = p[ic];
-                const Cam3 rbc = clip_edge(B, C, c.znear), rac = clip_edge(A, C, c.znear);
-                tri[0][0] = A;
-                tri[0][1] = B;
-                tri[0][2] = rbc;
-                tri[1][0] = A;
-                tri[1][1] = rbc;
-                tri[1][2] = rac;
-                n_tri = 2;
-            }
-        }
+        if (fi < F) n_tri = face_triangles(verts, faces, fi, c, tri, face_id);
         bool kept_before = false;
+        unsigned guarded = 0;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {  // every lane takes part in both rounds (warp-aggregated append)
-            bool keep = false;
+            int code = 0;
             GGFaceRec r;
-            if (t < n_tri) keep = build_record(tri[t][0], tri[t][1], tri[t][2], face_id, c, r);
+            if (t < n_tri) code = build_record(tri[t][0], tri[t][1], tri[t][2], face_id, c, r, true);
+            const bool keep = code == 1;
+            guarded |= code == 2 ? 1u << t : 0u;
             r.dup = kept_before ? 1 : 0;
             kept_before = kept_before || keep;
             const int idx = warp_append(&vs.counters[1], keep);
-            if (keep) {
-                if (idx < cap_recs) {
-                    const int tx0 = r.jmin / GG_TILE_W, tx1 = r.jmax / GG_TILE_W;
-                    const int ty0 = r.imin / GG_TILE_H, ty1 = r.imax / GG_TILE_H;
-                    const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
-                    unsigned long long tmask = 0;
-                    const bool small = ntx * nty <= 64;
-                    // tile_may_touch for every tile of the box, evaluated incrementally: the three edge functions at
-                    // each tile's innermost corner differ from tile to tile by constants (same int64 values)
-                    long long e_row[3], dex[3], dey[3];
+            if (keep) emit_record(r, idx, vs, F, cap_recs, sticky, tiles_x);
+        }
+        if (guarded) {  // contract C6 (rare, divergent): clip against the guard band, one record per fan triangle
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int xc = tx0 * GG_TILE_W + (r.A[k] > 0 ? GG_TILE_W - 1 : 0);
-                        const int yc = ty0 * GG_TILE_H + (r.B[k] > 0 ? GG_TILE_H - 1 : 0);
-                        e_row[k] = r.C[k] + (long long)r.A[k] * GG_SUBPIX * xc + (long long)r.B[k] * GG_SUBPIX * yc;
-                        dex[k] = (long long)r.A[k] * (GG_SUBPIX * GG_TILE_W);
-                        dey[k] = (long long)r.B[k] * (GG_SUBPIX * GG_TILE_H);
-                    }
-                    int bit = 0;
-                    for (int ty = ty0; ty <= ty1; ++ty) {
-                        long long e0 = e_row[0], e1 = e_row[1], e2 = e_row[2];
-                        int32_t *row_count = vs.tile_count + ty * tiles_x;
-                        for (int tx = tx0; tx <= tx1; ++tx, ++bit) {
-                            if ((e0 | e1 | e2) >= 0) {
-                                atomicAdd(&row_count[tx], 1);
-                                if (small) tmask |= 1ull << bit;
-                            }
-                            e0 += dex[0];
-                            e1 += dex[1];
-                            e2 += dex[2];
-                        }
-                        e_row[0] += dey[0];
-                        e_row[1] += dey[1];
-                        e_row[2] += dey[2];
-                    }
-                    r.tmask = small ? tmask : ~0ull;
-                    store_vec16(&vs.recs[idx], r);
-                    if (r.face == (int32_t)(F - 1)) vs.counters[5] = idx;
-                } else {
-                    atomicOr(&vs.counters[3], 1);
-                    atomicOr(sticky, 1);
-                }
-            }
+            for (int t = 0; t < 2; ++t)
+                if (guarded & (1u << t))
+                    kept_before = setup_guarded(verts, faces, fi, t, c, vs, F, cap_recs, sticky, tiles_x, kept_before);
         }
     }
 }

@@ -26,6 +26,10 @@
  *       exact ties -> lowest face ID
  *   C5  faces are clipped against the plane z_cam = znear in camera space (float32, fixed operation order); a face
  *       entirely behind it, or with a non-finite coordinate, is dropped
+ *   C6  guard band: a (sub-)triangle with a vertex that projects beyond +-2^20 px is clipped, in camera space and in
+ *       float32 with a fixed operation order, against the four planes  sx = +-2^20, sy = +-2^20  (Sutherland-Hodgman,
+ *       intersections always computed from the inside vertex towards the outside one) and fan-triangulated, so that
+ *       the snap of C2 never has to clamp a coordinate (clamping x and y independently would turn the edge)
  * It is pinned against the reference's own known-answer tests for this path
  * (tests/test_derived_meshes.py:23-76, tests/test_derived_cameras.py:339-415) in
  * tests/test_oracle_reference_pins.py.
@@ -204,6 +208,73 @@ static void raster_tri(const float *pa, const float *pb, const float *pc, int32_
     }
 }
 
+
+/* ---- contract C6: guard-band clipping ------------------------------------------------------------------- */
+#define ORA_GUARD 1048576.0f /* 2^20 px: half of what the snapped coordinates can hold */
+
+/* float32 screen coordinates of C1 (before the snap) beyond the guard band? */
+static inline int beyond_guard(const float *pc, const ora_camera *c) {
+    const float sx = (c->f * pc[0]) / pc[2] + c->px;
+    const float sy = (c->f * pc[1]) / pc[2] + c->py;
+    return !(fabsf(sx) <= ORA_GUARD) || !(fabsf(sy) <= ORA_GUARD);
+}
+
+/* signed distance (>= 0: inside) of a camera-space point to guard plane k: 0 right, 1 left, 2 bottom, 3 top */
+static inline float guard_dist(const float *p, const ora_camera *c, int k) {
+    float a, b;
+    switch (k) {
+        case 0: a = (ORA_GUARD - c->px) * p[2]; b = c->f * p[0]; return a - b;
+        case 1: a = (ORA_GUARD + c->px) * p[2]; b = c->f * p[0]; return a + b;
+        case 2: a = (ORA_GUARD - c->py) * p[2]; b = c->f * p[1]; return a - b;
+        default: a = (ORA_GUARD + c->py) * p[2]; b = c->f * p[1]; return a + b;
+    }
+}
+
+/* Clip the triangle (a, b, c) against the four guard planes; out receives at most 8 points; returns their number. */
+static int guard_clip(const float *pa, const float *pb, const float *pc, const ora_camera *cam, float out[8][3]) {
+    float buf[2][8][3];
+    int n = 3, cur = 0;
+    memcpy(buf[0][0], pa, 12);
+    memcpy(buf[0][1], pb, 12);
+    memcpy(buf[0][2], pc, 12);
+    for (int k = 0; k < 4 && n >= 3; ++k) {
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const float *P = buf[cur][i], *Q = buf[cur][(i + 1) % n];
+            const float dP = guard_dist(P, cam, k), dQ = guard_dist(Q, cam, k);
+            const int inP = dP >= 0.0f, inQ = dQ >= 0.0f;
+            if (inP && m < 8) memcpy(buf[1 - cur][m++], P, 12);
+            if (inP != inQ && m < 8) { /* from the inside vertex towards the outside one */
+                const float *I = inP ? P : Q, *O = inP ? Q : P;
+                const float dI = inP ? dP : dQ, dO = inP ? dQ : dP;
+                const float t = dI / (dI - dO);
+                float *R = buf[1 - cur][m++];
+                for (int d = 0; d < 3; ++d) {
+                    const float delta = O[d] - I[d];
+                    R[d] = I[d] + t * delta;
+                }
+            }
+        }
+        n = m;
+        cur = 1 - cur;
+    }
+    if (n < 3) return 0;
+    memcpy(out, buf[cur], sizeof(float) * 3 * (size_t)n);
+    return n;
+}
+
+/* raster_tri behind the guard band (C6) */
+static void raster_tri_guarded(const float *pa, const float *pb, const float *pc, int32_t face, const ora_camera *cam, int r0,
+                               int r1, int32_t *pix2face, double *wbest, double *wsecond) {
+    if (!beyond_guard(pa, cam) && !beyond_guard(pb, cam) && !beyond_guard(pc, cam)) {
+        raster_tri(pa, pb, pc, face, cam, r0, r1, pix2face, wbest, wsecond);
+        return;
+    }
+    float poly[8][3];
+    const int n = guard_clip(pa, pb, pc, cam, poly);
+    for (int i = 1; i + 1 < n; ++i) raster_tri(poly[0], poly[i], poly[i + 1], face, cam, r0, r1, pix2face, wbest, wsecond);
+}
+
 /* Up to two camera-space sub-triangles of face fi after clipping against z = znear (contract C5).  Returns their
  * number (0: dropped).  tri[t][k] points to 3 floats; clipped points live in buf. */
 static int face_subtris(const float *PC, const int32_t *faces, int64_t V, int64_t fi, float znear,
@@ -322,7 +393,10 @@ void ora_rasterize(const float *verts, int64_t V, const int32_t *faces, int64_t 
         int lo = H, hi = -1;
         for (int t = 0; t < nt; ++t) {
             int i0, i1;
-            if (subtri_rows(tri[t][0], tri[t][1], tri[t][2], cam, &i0, &i1)) {
+            if (beyond_guard(tri[t][0], cam) || beyond_guard(tri[t][1], cam) || beyond_guard(tri[t][2], cam)) {
+                lo = 0; /* clipped against the guard band while rasterizing: any row (rare, conservative) */
+                hi = H - 1;
+            } else if (subtri_rows(tri[t][0], tri[t][1], tri[t][2], cam, &i0, &i1)) {
                 if (i0 < lo) lo = i0;
                 if (i1 > hi) hi = i1;
             }
@@ -362,7 +436,7 @@ void ora_rasterize(const float *verts, int64_t V, const int32_t *faces, int64_t 
             float buf[4][3];
             const int nt = face_subtris(PC, faces, V, fi, znear, tri, buf);
             for (int t = 0; t < nt; ++t)
-                raster_tri(tri[t][0], tri[t][1], tri[t][2], (int32_t)fi, cam, r0, r1, pix2face, wbest, wsecond);
+                raster_tri_guarded(tri[t][0], tri[t][1], tri[t][2], (int32_t)fi, cam, r0, r1, pix2face, wbest, wsecond);
         }
     }
     if (depth_w) memcpy(depth_w, wbest, sizeof(double) * P);

@@ -353,3 +353,32 @@ def test_pageable_pointers_are_refused_by_the_fused_entry_point(torch, lib):
         ctx.project_aggregate([_gg(lib, cams[0])], [pageable], lib.PRED_F32, C, lib.MODE_LAST_PIXEL, 0, d_sum, d_count)
     ctx.sync()
     assert int(d_count.sum()) == 0
+
+
+def test_guard_band_clipping_matches_oracle_and_ray_caster(torch, lib):
+    """Contract C6 on the GPU: a 400 m face that reaches far behind the camera plane (its near-plane cut projects
+    millions of pixels away) plus the triangle soup at the default near plane -- the CUDA setup kernel clips against
+    the guard band with the oracle's float32 arithmetic (bit-identical rasters) and the result is what the
+    independent float64 ray caster sees."""
+    from test_oracle_raycast import EPS_EDGE
+    from test_oracle_reference_pins import downward_view, plane_mesh
+
+    ground, gfaces = plane_mesh()
+    ground = ground * 10.0
+    big = np.array([[-150.0, -200.0, 7.9], [150.0, -200.0, 7.9], [0.0, 200.0, 8.3]])
+    verts = np.concatenate([ground, big])
+    faces = np.concatenate([gfaces, [[len(ground), len(ground) + 1, len(ground) + 2]]]).astype(np.int32)
+    v32 = verts.astype(np.float32)
+    ctx = _ctx(torch, lib, v32, faces)
+    for zc, tilt in ((9.0, 70.0), (8.2, 60.0), (8.05, 50.0)):
+        T = downward_view(4, 100, 200)
+        T[:3, 3] = [1.0, -2.0, zc]
+        a = np.deg2rad(tilt)
+        T[:3, :3] = T[:3, :3] @ np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+        cam = ora.make_camera(T, 150.0, 0.0, 0.0, 240, 180)
+        gpu = ctx.rasterize([_gg(lib, cam)]).cpu().numpy()[0]
+        ref, _, margin = ora.rasterize(v32, faces, cam, want_depth=True, want_margin=True)
+        assert not ((gpu != ref) & (margin > 1e-5)).any()
+        rc, edge_safe, rc_margin = ora.raycast(v32, faces, cam, eps_edge=EPS_EDGE)
+        safe = edge_safe & (rc_margin > 1e-4)
+        assert safe.mean() > 0.9 and not (safe & (gpu != rc)).any()

@@ -83,13 +83,13 @@ def test_terrain_surveys(name, views):
         _compare(v32, faces, cam, f"{name} view {k}", min_safe=0.8)
 
 
+@pytest.mark.parametrize("znear", [1e-3, 0.5])
 @pytest.mark.parametrize("seed,n_faces,W,H", [(0, 300, 160, 120), (1, 800, 200, 150)])
-def test_triangle_soup(seed, n_faces, W, H):
+def test_triangle_soup(seed, n_faces, W, H, znear):
     """The soup of tests/test_gpu_parity.py: slivers, huge faces, faces through the near plane and behind the camera.
-    The near plane sits at 0.5 here: contract C2 clamps snapped coordinates to +-2^21 px, which is exact only while
-    |f x / z| stays below that on the near plane; with faces tens of metres wide cut at the default z = 1e-3 the
-    clipped vertices would be clamped (a documented limit of the contract, DESIGN.md section 9 -- it does not arise
-    for survey meshes, whose faces that straddle the camera plane lie far outside the field of view)."""
+    At the default near plane (1e-3) faces tens of metres wide are cut so close to the camera that their clipped
+    vertices project millions of pixels away: contract C6 (guard-band clipping) keeps the snapped coordinates exact
+    there -- before it existed the two oracles disagreed on a third of this scene's pixels."""
     rng = np.random.default_rng(seed)
     centers = rng.uniform([-30, -30, -5], [30, 30, 60], size=(n_faces, 1, 3))
     size = rng.choice([0.3, 3.0, 40.0], size=(n_faces, 1, 1), p=[0.4, 0.4, 0.2])
@@ -97,8 +97,28 @@ def test_triangle_soup(seed, n_faces, W, H):
     faces = np.arange(3 * n_faces, dtype=np.int32).reshape(-1, 3)
     c2w = np.eye(4)
     c2w[:3, 3] = [0.5, -0.25, -20.0]
-    cam = ora.make_camera(c2w, 0.8 * W, 3.0, -2.0, W, H, znear=0.5)
-    _compare(verts.astype(np.float32), faces, cam, f"soup {seed}", min_safe=0.6)
+    cam = ora.make_camera(c2w, 0.8 * W, 3.0, -2.0, W, H, znear=znear)
+    _compare(verts.astype(np.float32), faces, cam, f"soup {seed} znear {znear}", min_safe=0.6)
+
+
+def test_guard_band_one_huge_face_through_the_camera_plane():
+    """One 400 m face that passes a metre under the camera and reaches far behind it, over a small ground patch: its
+    near-plane cut projects beyond +-2^20 px, the guard band (C6) clips it, and it covers exactly the pixels the ray
+    caster says it covers."""
+    ground, gfaces = plane_mesh()
+    ground = ground * 10.0  # 40 m x 40 m at z = 0
+    big = np.array([[-150.0, -200.0, 7.9], [150.0, -200.0, 7.9], [0.0, 200.0, 8.3]])  # tilted sheet above the ground
+    verts = np.concatenate([ground, big])
+    faces = np.concatenate([gfaces, [[len(ground), len(ground) + 1, len(ground) + 2]]]).astype(np.int32)
+    T = downward_view(4, 100, 200)
+    T[:3, 3] = [1.0, -2.0, 9.0]  # just above the sheet, which reaches ~190 m in front of AND behind the camera plane
+    a = np.deg2rad(70.0)
+    T[:3, :3] = T[:3, :3] @ np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    cam = ora.make_camera(T, 150.0, 0.0, 0.0, 240, 180)
+    v32 = verts.astype(np.float32)
+    ids = ora.rasterize(v32, faces, cam)
+    assert 0.5 < (ids == len(faces) - 1).mean() < 0.98  # the sheet fills the view up to its horizon
+    _compare(v32, faces, cam, "huge face", min_safe=0.9, min_hit=0.5)
 
 
 # ---- the cube / cylinder / cone scene of the reference's concept figure --------------------------------------
