@@ -31,9 +31,11 @@ def shard_cameras(cameras, rank: int, world_size: int):
         return cameras.get_subset_cameras(inds)
 
 
-def allreduce_accumulators(d_sum, d_count, group=None):
+def allreduce_accumulators(d_sum, d_count, group=None, dst_rank=None):
     """In-place sum of the per-face accumulators over all ranks with ONE collective: the int32 counts ride behind the
-    float64 sums in a single float64 buffer (exact: counts are far below 2^53).  Counts (and one-hot / vote sums) are
+    float64 sums in a single float64 buffer (exact: counts are far below 2^53).  With ``dst_rank`` only that rank
+    needs the total and the collective is a reduce (half the traffic of an all-reduce); the other ranks' buffers are
+    then left with partial sums.  Counts (and one-hot / vote sums) are
     integers and therefore identical for any number of ranks; float64 sums of real-valued scores differ from the
     single-GPU result only by the association order of at most ``world_size`` partial sums (~1e-16 relative)."""
     import torch
@@ -45,7 +47,11 @@ def allreduce_accumulators(d_sum, d_count, group=None):
     pack = torch.empty((n_sum + d_count.numel(),), dtype=torch.float64, device=d_sum.device)
     pack[:n_sum].copy_(d_sum.reshape(-1))
     pack[n_sum:].copy_(d_count.reshape(-1))
-    dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
+    if dst_rank is None:
+        dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.reduce(pack, dst=dist.get_global_rank(group, dst_rank) if group is not None else dst_rank,
+                    op=dist.ReduceOp.SUM, group=group)
     d_sum.copy_(pack[:n_sum].view(d_sum.shape))
     d_count.copy_(pack[n_sum:].view(d_count.shape))
     return d_sum, d_count
@@ -104,7 +110,7 @@ def aggregate_projected_images_distributed(mesh, cameras, aggregate_img_scale: f
         d_count = torch.zeros((mesh.faces.shape[0],), dtype=torch.int32, device=dev)
     mesh._get_context().drain()  # accumulators are written on the library's internal streams
     t0 = mark("accumulate", t0)
-    allreduce_accumulators(d_sum, d_count, group)
+    allreduce_accumulators(d_sum, d_count, group, dst_rank=dst_rank)
     t0 = mark("allreduce", t0)
     if dst_rank is not None and rank != dst_rank:
         return None, {}

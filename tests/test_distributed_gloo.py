@@ -45,6 +45,7 @@ def _worker(rank, world, port, out):
             proj = ora.project_image(p2f[k], agg["soft"][k], F)
             summed += np.nan_to_num(proj, nan=0.0)
             counts += np.any(np.isfinite(proj), axis=1).astype(np.int32)
+        r_sum, r_count = torch.from_numpy(summed.copy()), torch.from_numpy(counts.copy())  # partials, for the reduce below
         d_sum, d_count = torch.from_numpy(summed), torch.from_numpy(counts)
         ggd.allreduce_accumulators(d_sum, d_count)
         avg, cnt, tot = ggd.finalize_host(d_sum.numpy(), d_count.numpy())
@@ -53,6 +54,11 @@ def _worker(rank, world, port, out):
         np.testing.assert_allclose(avg, agg["avg2"], rtol=1e-12, atol=0, equal_nan=True)
         amax = ora.find_argmax_nonzero_value(avg)
         np.testing.assert_array_equal(amax, agg["argmax2"][:, 0])
+        # result wanted on one rank only: a reduce instead of an all-reduce; the destination holds the same totals
+        ggd.allreduce_accumulators(r_sum, r_count, dst_rank=1)
+        if rank == 1:
+            np.testing.assert_array_equal(r_count.numpy(), d_count.numpy())
+            np.testing.assert_array_equal(r_sum.numpy(), d_sum.numpy())
         out[rank] = 1
     finally:
         dist.destroy_process_group()
