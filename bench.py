@@ -21,10 +21,11 @@ Rank 0 prints ONE JSON line:
               HBM fraction of the same kernel is kept under `roofline.hbm`.  The dense `pixel_sum` mode, which
               streams every score, carries an HBM roofline.
 `e2e`         the same metric through the reference-facing Python API (TexturedPhotogrammetryMesh.
-              aggregate_projected_images on a SegmentorPhotogrammetryCameraSet) with the score images in pinned HOST
-              memory; the rows the aggregation needs cross PCIe inside the timed region and the per-face results are
-              copied back.  `e2e_index_u8` (class-index images, the LookUpSegmentor contract) and `e2e_pageable`
-              (ordinary NumPy arrays) are the same call on other input kinds (N = 1 only).
+              aggregate_projected_images on a SegmentorPhotogrammetryCameraSet) with the score images in HOST memory
+              (geograypher_b200.host_array); the rows the aggregation needs cross PCIe inside the timed region and the
+              per-face results are copied back.  `e2e_pinned` (page-locked arrays), `e2e_index_u8` (class-index images,
+              the LookUpSegmentor contract) and `e2e_pageable` (ordinary NumPy arrays) are the same call on other
+              input kinds (N = 1 only).
 `pixel_sum`, `c3_strong`, `c4`, `c5`   sub-records: dense mode; the 500-view survey split over the N ranks (strong
               scaling, all-reduce + epilogue + device-to-host copy inside the timing, parity-checked against a
               single-GPU run); render_flat to uint8 label rasters; the 20M-face one-hot-vote survey.
@@ -240,12 +241,15 @@ def run_reference(args):
     total = float(sum(timed))
     value = len(timed) / total
     cores = host_threads()
-    sample = f"{len(timed)} views of {args.config} (1 view per step); " + CPU_NOTE.format(cores=cores)
+    sample = (f"{len(timed)} views of {args.config}: each CPU step is ONE view of the {args.views_per_step}-view step the "
+              f"GPU arm times; ") + CPU_NOTE.format(cores=cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, cfg, 1, 1),
+        # the SAME config record as the GPU arm (the workload is what is compared); how much of it one CPU step covers
+        # is a property of this arm and lives in cpu_baseline.sample
+        "config": workload_config(args, cfg, args.views_per_step, args.batch),
         "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample,
                          "raster_s_per_view": t_r / n, "aggregate_s_per_view": t_a / n},
         "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -344,16 +348,15 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
 
-    # The page-locked host images of the end-to-end legs are allocated first, while the host's memory is still
-    # unfragmented: the GPU reads scattered rows out of them over PCIe, and that runs measurably slower from pinned
-    # buffers that were allocated late in a process than from these.
+    # The host images of the end-to-end legs are allocated first, while the host's memory is still unfragmented: the
+    # GPU reads scattered rows out of them over PCIe.
     e2e_host = None
     if "e2e" not in skip:
         e2e_host = []
-        for i in range(min(8, args.e2e_views)):
-            t = torch.empty((H, W, C), dtype=torch.float32, pin_memory=True)
-            t.copy_(syn.softmax_predictions_device(my_cams[i % len(my_cams)], H, W, C, dev))
-            e2e_host.append(t.numpy())
+        for i in range(min(8, args.e2e_views)):  # gg.host_array: host memory that the GPU reads in place over PCIe
+            a = gg.host_array((H, W, C), np.float32, device=local_rank)
+            torch.from_numpy(a).copy_(syn.softmax_predictions_device(my_cams[i % len(my_cams)], H, W, C, dev))
+            e2e_host.append(a)
         torch.cuda.synchronize()
 
     ctx = _lib.Context(local_rank)
@@ -465,11 +468,12 @@ def run_ours(args):
     torch.cuda.empty_cache()
     c4 = run_c4(args, torch, dist, _lib, syn, ctx, world, rank, dev, verts, faces, all_cams, cfg, peak, peak_src) \
         if "c4" not in skip else None
-    e2e = e2e_idx = e2e_page = None
+    e2e = e2e_idx = e2e_page = e2e_pin = None
     if "e2e" not in skip:
-        e2e = run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, e2e_host, "pinned_f32")
+        e2e = run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, e2e_host, "host_array_f32")
         if world == 1 and "e2e_extra" not in skip:
             e2e_idx = run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, None, "pinned_index_u8")
+            e2e_pin = run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, e2e_host, "pinned_f32")
             e2e_page = run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, e2e_host, "pageable_f32")
     e2e_host = None
 
@@ -504,7 +508,7 @@ def run_ours(args):
                 "note": "same workload with every pixel adding its scores (GG_MODE_PIXEL_SUM, not the reference's "
                         "semantics): the fused rasterizer epilogue streams the (H,W,C) float32 scores from HBM"
                         if other_name == "pixel_sum" else "reference-parity mode"},
-            "c3_strong": c3, "c4": c4, "c5": c5, "e2e_index_u8": e2e_idx, "e2e_pageable": e2e_page,
+            "c3_strong": c3, "c4": c4, "c5": c5, "e2e_index_u8": e2e_idx, "e2e_pinned": e2e_pin, "e2e_pageable": e2e_page,
             "parity_check": (c3 or {}).get("parity_check"),
             "accumulators": "float64 sums + int32 counts" + ("; one NCCL all-reduce (counts packed behind the sums) at "
                                                               "the end" if world > 1 else ""),
@@ -682,8 +686,9 @@ def run_c5(args, torch, dist, _lib, syn, world, rank, local_rank, dev):
 
 def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, host, kind):
     """aggregate_projected_images through the reference-facing API, prediction images in host memory.
-    kind: pinned_f32 ((H,W,C) float32 in page-locked memory, read in place by the GPU), pinned_index_u8 ((H,W) uint8
-    class-index images, the LookUpSegmentor contract, expanded on the GPU), pageable_f32 (ordinary NumPy arrays)."""
+    kind: host_array_f32 ((H,W,C) float32 in gg.host_array memory -- host-resident, mapped into the GPU -- read in
+    place), pinned_f32 (the same in page-locked memory), pinned_index_u8 ((H,W) uint8 class-index images, the
+    LookUpSegmentor contract, expanded on the GPU), pageable_f32 (ordinary NumPy arrays)."""
     W, H = cfg.image_size
     C = cfg.n_classes
     from geograypher_b200 import distributed as ggd
@@ -704,6 +709,15 @@ def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, hos
             host.append(t.numpy())
         segmentor = gg.ArraySegmentor([host[i % len(host)] for i in range(len(all_ids))], num_classes=C, one_hot=True)
         elem_bytes, row_elems = 1, 1
+    elif kind == "pinned_f32":
+        src = host
+        host = []
+        for i in range(len(src)):  # the same images in page-locked (cudaHostAlloc) memory
+            t = torch.empty((H, W, C), dtype=torch.float32, pin_memory=True)
+            t.copy_(torch.from_numpy(src[i]))
+            host.append(t.numpy())
+        segmentor = gg.ArraySegmentor([host[i % len(host)] for i in range(len(all_ids))], num_classes=C)
+        elem_bytes, row_elems = 4, C
     elif kind == "pageable_f32":
         pinned = host
         host = [np.array(pinned[i % len(pinned)], copy=True) for i in range(16)]  # ordinary (pageable) arrays
@@ -744,11 +758,14 @@ def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, hos
     del mesh
     torch.cuda.empty_cache()
     notes = {
-        "pinned_f32": "float32 (H,W,C) score images stay in pinned HOST memory; last-pixel aggregation needs one row "
-                      "per visible face, which a small persistent kernel fetches over PCIe through unified addressing "
-                      "while the next batch is rasterized (h2d bytes = rows fetched, sector-granular); the per-face "
-                      "float64 averages, sums and counts are copied back at the end.  The link's scattered-read rate "
-                      "(profiles/r02_pcie_rows.txt: ~230 M 40-byte rows/s) bounds this leg at ~6 000 views/s",
+        "host_array_f32": "float32 (H,W,C) score images stay in HOST memory (geograypher_b200.host_array: managed memory "
+                          "whose preferred location is the host, mapped into the GPU); last-pixel aggregation needs one "
+                          "row per visible face, which a small kernel fetches over PCIe in place while the next batch is "
+                          "rasterized (h2d bytes = rows fetched, sector-granular); the per-face float64 averages, sums and "
+                          "counts are copied back at the end",
+        "pinned_f32": "the same images in page-locked (cudaHostAlloc) memory: on this host the scattered-read rate from "
+                      "page-locked memory falls with the pinned footprint (profiles/r02_pcie_rows_footprint.txt: 284 -> "
+                      "100 M 40-byte rows/s from 1.3 to 10 GB)",
         "pinned_index_u8": "(H,W) uint8 class-index images in pinned host memory (what LookUpSegmentor yields before "
                            "its one-hot expansion), expanded on the GPU exactly like Segmentor.inds_to_one_hot; one "
                            "byte per visible face crosses PCIe",

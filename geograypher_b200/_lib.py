@@ -30,7 +30,8 @@ EXPORTS = [
     "gg_project_aggregate", "gg_finalize", "gg_render_flat", "gg_stage_count", "gg_stage_name", "gg_profile",
     "gg_profile_read", "gg_drain", "gg_set_pipeline", "gg_build_warp_map", "gg_gather_i32",
     "gg_label_polygons", "gg_get_capacity", "gg_rasterize_render_flat", "gg_project_winners", "gg_accumulate_rows",
-    "gg_overflow_info", "gg_resize_render", "gg_label_polygons_overlay",
+    "gg_overflow_info", "gg_resize_render", "gg_label_polygons_overlay", "gg_host_alloc", "gg_host_free",
+    "gg_pointer_kind",
 ]
 
 
@@ -94,6 +95,9 @@ def load():
     lib.gg_reserve.argtypes = [vp, i64, i64]
     lib.gg_last_batch_stats.argtypes = [vp, i32, vp]
     lib.gg_overflow_info.argtypes = [vp, vp]
+    lib.gg_host_alloc.argtypes = [i32, ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.gg_host_free.argtypes = [vp]
+    lib.gg_pointer_kind.argtypes = [vp]
     lib.gg_get_capacity.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
     lib.gg_set_mesh.argtypes = [vp, vp, i64, vp, i64, vp]
     lib.gg_project.argtypes = [vp, camp, i32, vp, vp, vp, vp, vp]
@@ -126,6 +130,33 @@ def load():
 def _check(rc):
     if rc != 0:
         raise GeograypherB200Error(rc, load().gg_last_error().decode("utf-8", "replace"))
+
+
+POINTER_PAGEABLE, POINTER_PINNED, POINTER_DEVICE, POINTER_MANAGED = 0, 1, 2, 3
+
+
+def pointer_kind(array) -> int:
+    """Where a NumPy array's memory lives as far as the GPU is concerned (gg_pointer_kind): pageable host memory
+    (the GPU cannot read it), page-locked host memory, device memory or managed memory."""
+    return int(load().gg_pointer_kind(ctypes.c_void_p(int(array.ctypes.data))))
+
+
+def host_array(shape, dtype=np.float32, device: int = 0) -> np.ndarray:
+    """A NumPy array in host memory that the GPU can read in place (gg_host_alloc): the container to hand prediction
+    images to ``aggregate_projected_images`` in.  The aggregation fetches one row per visible face and view out of it
+    over PCIe; unlike page-locked buffers its scattered-read rate does not collapse when many large images are
+    resident.  Freed when the array (and every view of it) is garbage-collected."""
+    import weakref
+
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(s) for s in shape)
+    dtype = np.dtype(dtype)
+    n_bytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+    lib = load()
+    ptr = ctypes.c_void_p()
+    _check(lib.gg_host_alloc(int(device), n_bytes, ctypes.byref(ptr)))
+    buf = (ctypes.c_ubyte * n_bytes).from_address(ptr.value)
+    weakref.finalize(buf, lib.gg_host_free, ctypes.c_void_p(ptr.value))  # the array's base object keeps buf alive
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 def make_camera(world_to_cam, f, cx, cy, image_width, image_height, render_img_scale=1.0, origin=None,

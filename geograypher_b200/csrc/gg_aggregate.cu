@@ -561,7 +561,8 @@ static int resolve_batch_body(gg_context *ctx, int n, const void *const *h_pred,
     bool on_host = ctx->stage_host_rows != 0;
     for (int i = 0; i < n && on_host; ++i) {
         cudaPointerAttributes attr;
-        on_host = cudaPointerGetAttributes(&attr, h_pred[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        on_host = cudaPointerGetAttributes(&attr, h_pred[i]) == cudaSuccess &&
+                  (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);  // gg_host_alloc: host-resident
     }
     (void)cudaGetLastError();
     if (on_host) {

@@ -192,6 +192,46 @@ extern "C" {
 
 int gg_abi_version(void) { return GG_ABI_VERSION; }
 
+int gg_host_alloc(int device, size_t bytes, void **out) {
+    if (!out || bytes == 0) {
+        gg_set_error("gg_host_alloc: bad arguments");
+        return GG_ERR_INVALID;
+    }
+    *out = nullptr;
+    GG_CUDA(cudaSetDevice(device));
+    void *p = nullptr;
+    GG_CUDA(cudaMallocManaged(&p, bytes, cudaMemAttachGlobal));
+    // the pages live in HOST memory and are mapped into the GPU's address space: kernels read them over PCIe in
+    // place, nothing migrates
+    cudaError_t e = cudaMemAdvise(p, bytes, cudaMemAdviseSetPreferredLocation, cudaCpuDeviceId);
+    if (e == cudaSuccess) e = cudaMemAdvise(p, bytes, cudaMemAdviseSetAccessedBy, device);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return gg_cuda_fail(e, "cudaMemAdvise");
+    }
+    *out = p;
+    return GG_OK;
+}
+
+int gg_host_free(void *p) {
+    if (p) GG_CUDA(cudaFree(p));
+    return GG_OK;
+}
+
+int gg_pointer_kind(const void *p) {
+    cudaPointerAttributes attr;
+    if (!p || cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    switch (attr.type) {
+        case cudaMemoryTypeHost: return 1;
+        case cudaMemoryTypeDevice: return 2;
+        case cudaMemoryTypeManaged: return 3;
+        default: return 0;
+    }
+}
+
 const char *gg_last_error(void) { return g_last_error.c_str(); }
 
 int gg_create(int device, gg_context **out) {

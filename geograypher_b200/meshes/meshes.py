@@ -36,13 +36,13 @@ from geograypher_b200.utils.indexing import determine_IDs_to_labels
 
 
 class _HostMapped:
-    """A pinned host tensor handed to the kernels by address (zero-copy)."""
+    """A host array the GPU can read in place (page-locked or gg.host_array memory), handed to the kernels by address."""
 
-    def __init__(self, tensor):
-        self.tensor = tensor
+    def __init__(self, array):
+        self.array = array  # keeps the memory alive while batches that read it are in flight
 
     def data_ptr(self):
-        return self.tensor.data_ptr()
+        return int(self.array.ctypes.data)
 
 
 class LocalMesh:
@@ -558,10 +558,9 @@ class TexturedPhotogrammetryMesh:
         are uploaded."""
         import torch
 
-        t = torch.from_numpy(arr)
-        if zero_copy and t.is_pinned():
-            return _HostMapped(t)
-        return t.to(dev, non_blocking=True)
+        if zero_copy and _lib.pointer_kind(arr) in (_lib.POINTER_PINNED, _lib.POINTER_MANAGED):
+            return _HostMapped(arr)
+        return torch.from_numpy(arr).to(dev, non_blocking=True)
 
     def _to_host(self, *tensors):
         """Device tensors -> fresh NumPy arrays owned by the caller.  Every array is backed by its own page-locked
@@ -698,7 +697,7 @@ class TexturedPhotogrammetryMesh:
                         preds.append(arr)
                     sparse = (not apply_distortion and self.sparse_host_gather and mode != _lib.MODE_PIXEL_SUM
                               and len({a.dtype for a in preds}) == 1
-                              and not any(torch.from_numpy(a).is_pinned() for a in preds))
+                              and not any(_lib.pointer_kind(a) != _lib.POINTER_PAGEABLE for a in preds))
                     if sparse:
                         if in_flight:  # the fused calls queued so far use the library's own streams
                             ctx.sync()

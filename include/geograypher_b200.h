@@ -82,6 +82,15 @@ typedef enum { GG_OUT_F64 = 0, GG_OUT_F32 = 1, GG_OUT_U8 = 2 } gg_out_dtype;
 int gg_abi_version(void);
 const char *gg_last_error(void);
 int gg_create(int device, gg_context **out);
+/* Host memory for prediction images that the fused aggregation reads IN PLACE over PCIe (one row per visible face and
+   view): managed memory whose preferred location is the host and that is mapped into `device`.  On the benchmark host
+   scattered reads from such a buffer keep their rate as the buffers grow (0.23 G 40-byte rows/s at 10 GB) where
+   cudaHostAlloc'ed memory drops to 0.10 G rows/s (profiles/r02_pcie_rows_*.txt).  No counterpart in the reference
+   (its images are NumPy arrays); page-locked (cudaHostAlloc / torch pin_memory) buffers are accepted as well.
+   gg_pointer_kind: 0 pageable or unknown, 1 page-locked host, 2 device, 3 managed. */
+int gg_host_alloc(int device, size_t bytes, void **out);
+int gg_host_free(void *p);
+int gg_pointer_kind(const void *p);
 void gg_destroy(gg_context *ctx);
 /* Synchronise `stream` and the internal streams, and report a deferred failure of the work enqueued since the last
    gg_sync (GG_ERR_OVERFLOW: the batches that overflowed the scratch were skipped as a whole; CUDA errors). */

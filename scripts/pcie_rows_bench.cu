@@ -29,7 +29,13 @@ int main(int argc, char **argv) {
     const int n = 250000;
     unsigned char *h = nullptr;
     const int thp = argc > 2 ? atoi(argv[2]) : 0;  // 1: transparent huge pages (mmap + MADV_HUGEPAGE) + cudaHostRegister
-    if (thp) {
+    if (thp == 2) {  // managed memory that prefers the host and is mapped into the GPU: accessed over PCIe, not migrated
+        CK(cudaMallocManaged(&h, (size_t)P * 64));
+        CK(cudaMemAdvise(h, (size_t)P * 64, cudaMemAdviseSetPreferredLocation, cudaCpuDeviceId));
+        CK(cudaMemAdvise(h, (size_t)P * 64, cudaMemAdviseSetAccessedBy, 0));
+        for (long long i = 0; i < P * 64; i += 4096) h[i] = (unsigned char)i;
+        printf("managed memory, preferred location = host, accessed by GPU 0\n");
+    } else if (thp) {
         const size_t bytes = ((size_t)P * 64 + (2u << 20) - 1) / (2u << 20) * (2u << 20);
         void *m = mmap(nullptr, bytes + (2u << 20), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         if (m == MAP_FAILED) { printf("mmap failed\n"); return 1; }

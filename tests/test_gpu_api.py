@@ -242,3 +242,37 @@ def test_save_renders_native_resolution(scene, golden_render, tmp_path):
             arr = np.load(out / f"{k:04d}.npy")
             assert arr.shape == (H, W) and arr.dtype == np.uint8
             np.testing.assert_array_equal(arr, np.squeeze(want))
+
+
+def test_host_array_inputs_are_read_in_place(scene, golden_aggregate):
+    """geograypher_b200.host_array: host memory mapped into the GPU.  Prediction images held in it go through the fused
+    zero-copy route (pointer kind = managed, no upload) and give bit-identical results to every other route -- the
+    reference's own aggregate on the golden scene."""
+    from geograypher_b200 import _lib
+
+    g, cams = scene
+    a = golden_aggregate
+    C = a["avg2"].shape[1]
+    images = []
+    for img in a["soft"]:
+        h = gg.host_array(img.shape, img.dtype)
+        assert _lib.pointer_kind(h) == _lib.POINTER_MANAGED and _lib.pointer_kind(np.zeros(4)) == _lib.POINTER_PAGEABLE
+        h[...] = img
+        images.append(h)
+    seg = gg.SegmentorPhotogrammetryCameraSet(cams, gg.ArraySegmentor(images, num_classes=C))
+    mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), compat_negative_index=True, log_level="WARNING")
+    routes = []
+    orig = mesh._to_device_or_mapped
+
+    def spy(arr, dev, zero_copy=True):
+        out = orig(arr, dev, zero_copy)
+        routes.append(type(out).__name__)
+        return out
+
+    mesh._to_device_or_mapped = spy
+    avg, info = mesh.aggregate_projected_images(seg)
+    assert routes and set(routes) == {"_HostMapped"}
+    np.testing.assert_array_equal(avg, a["avg2"])
+    np.testing.assert_array_equal(info["projection_counts"], a["counts2"])
+    np.testing.assert_array_equal(info["summed_projections"], a["summed2"])
+    del images, seg  # the buffers are released with the arrays
