@@ -19,10 +19,12 @@
 // ---- tiling ------------------------------------------------------------------------------------------
 #define GG_TILE_W 32           // one warp rasterizes one 32 x 8 px tile; lane = 8 consecutive px of one row
 #define GG_TILE_H 8
+#ifndef GG_RASTER_WARPS
 #define GG_RASTER_WARPS 4      // independent warps (tiles) per CTA
+#endif
 #define GG_RASTER_THREADS (32 * GG_RASTER_WARPS)
 #ifndef GG_RASTER_MIN_BLOCKS
-#define GG_RASTER_MIN_BLOCKS 8
+#define GG_RASTER_MIN_BLOCKS (32 / GG_RASTER_WARPS)  // 64 registers per thread: 32 warps per SM
 #endif
 #define GG_CHUNK 32            // faces staged per warp per pass (one per lane)
 #define GG_BLOCK_FACES 128     // faces per cull block

@@ -744,6 +744,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
                                                                        const __grid_constant__ GGDenseArgs dense) {
     constexpr bool WINNERS = (MODE == GG_RM_WINNERS || MODE == GG_RM_WINNERS_ONLY);
     constexpr bool RASTER_OUT = (MODE != GG_RM_WINNERS_ONLY);  // pix2face / depth may be requested
+    constexpr bool NEED_POS = (MODE == GG_RM_DENSE);  // only the dense epilogue indexes by list position
     // grid: (groups of GG_RASTER_WARPS tiles along x, tile rows, views); one warp per tile
     const int view = blockIdx.z;
     const gg_camera &c = cams.cam[view];
@@ -757,9 +758,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
     const int tile_x0 = tile_x * GG_TILE_W, tile_y0 = blockIdx.y * GG_TILE_H;
 
     __shared__ GGTileFace s_all[GG_RASTER_WARPS][GG_CHUNK];
-    __shared__ int s_win_all[WINNERS ? GG_RASTER_WARPS : 1][GG_CHUNK];
     GGTileFace *s_faces = s_all[warp];
-    int *s_win = s_win_all[WINNERS ? warp : 0];  // last pixel won by the first GG_CHUNK list positions
 
     const int tx0 = (lane & 3) * 8;  // this lane: pixels tx0..tx0+7 of row ty
     const int ty = lane >> 2;
@@ -777,12 +776,14 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
         key[i] = 0.0;  // 1/z = 0, ~face = 0 (face -1)
         bp[i] = -1;
     }
-    if (WINNERS) s_win[lane] = -1;
     const float fty = (float)ty, ftx0 = (float)tx0;
 
     const bool overflow = vs.counters[3] != 0;
     const int beg = vs.tile_offset[tile];
-    const int len = overflow ? 0 : vs.tile_count[tile] - beg;  // the fill cursor ends at the end of the list
+    int end;  // the fill cursor ends at the end of the list; loaded unconditionally, beside the overflow flag (the
+              // compiler would predicate it on the flag and chain two memory round trips)
+    asm volatile("ld.global.s32 %0, [%1];" : "=r"(end) : "l"(vs.tile_count + tile));
+    const int len = overflow ? 0 : end - beg;
 
     if (MODE == GG_RM_DENSE) {
         // The epilogue will stream this tile's scores: ask for them now (one bulk L2 prefetch per tile row, issued by
@@ -836,9 +837,18 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
                 for (int i = 0; i < 8; ++i) {  // branch-free: selects cost less than the divergence bookkeeping
                     const float w = fmaf(gx, (float)i, wrow);
                     const double cand = __hiloint2double(__float_as_int(w), (int)nface);
-                    const bool upd = ((e0 | e1 | e2) >= 0) & (cand > key[i]);  // w <= 0 (never inside a face) loses
-                    key[i] = upd ? cand : key[i];
-                    bp[i] = upd ? pos : bp[i];
+                    if (NEED_POS) {
+                        const bool upd = ((e0 | e1 | e2) >= 0) & (cand > key[i]);  // w <= 0 (never inside a face) loses
+                        key[i] = upd ? cand : key[i];
+                        bp[i] = upd ? pos : bp[i];
+                    } else {
+                        // the same update with the two conditions folded into ONE predicate by hand (left to itself the
+                        // compiler nests two selects per key half when the predicate has a single consumer)
+                        asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %0;\n\tsetp.ge.and.s32 p, %2, 0, p;\n\t"
+                            "selp.f64 %0, %1, %0, p;\n\t}"
+                            : "+d"(key[i])
+                            : "d"(cand), "r"(e0 | e1 | e2));
+                    }
                     e0 += s0;
                     e1 += s1;
                     e2 += s2;
@@ -852,7 +862,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
                         const double cand = __hiloint2double(__float_as_int(w), (int)nface);
                         if (cand > key[i]) {
                             key[i] = cand;
-                            bp[i] = pos;
+                            if (NEED_POS) bp[i] = pos;
                         }
                     }
                 }
@@ -897,56 +907,50 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
     }
 
     if (WINNERS) {
-        // Last pixel (row-major) won by every face record.  Only the end of a run of equal winners inside this lane's
-        // 8 pixels can be the face's last pixel of the row; a run continued by the next strip is left to that strip.
-        // Run-ends are max-reduced per list position in shared memory, then one atomicMax per (tile, face) goes to
-        // the view's winner array.
-        const int next_first = __shfl_down_sync(0xffffffffu, bp[0], 1);
+        // Last pixel (row-major) won by every face.  Only the end of a run of equal winners inside this lane's 8
+        // pixels can be the face's last pixel of the row; a run continued by the next strip is left to that strip.
+        // Every run-end is ONE predicated max-reduction straight into the view's winner array (fire and forget, L2
+        // resident): the per-pixel state carries no list position, and no shared-memory pre-reduction or flush.
+        // nf = the key's low word = ~face (0 = no winner; 1 = a face ID no mesh has, the "nothing follows" mark).
+        unsigned nf[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nf[i] = (unsigned)__double2loint(key[i]);
+        const unsigned next_first = __shfl_down_sync(0xffffffffu, nf[0], 1);
         const bool has_next = (lane & 3) != 3;
         int bgmax = -1;
         const int pix0 = row * W + col;
-        if (tile_x0 + GG_TILE_W <= W && tile_y0 + GG_TILE_H <= H && len <= GG_CHUNK) {
-            // tile entirely inside the image and every list position has a shared-memory slot (warp-uniform): one
-            // predicated shared-memory atomic per run-end, nothing else
-            const int after = has_next ? next_first : -2;
-            const unsigned s_win_addr = (unsigned)__cvta_generic_to_shared(s_win);
+        int *const winner = vs.winner;
+        const char *const wbase = reinterpret_cast<const char *>(winner) - 4;  // &winner[~nf] = wbase - 4 * (int)nf
+        if (tile_x0 + GG_TILE_W <= W && tile_y0 + GG_TILE_H <= H) {  // tile entirely inside the image (warp-uniform)
+            const unsigned after = has_next ? next_first : 1u;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int nxt = (i < 7) ? bp[i < 7 ? i + 1 : 7] : after;
-                // one PREDICATED reduction per run-end (no branch / reconvergence bookkeeping around it)
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, %1;\n\tsetp.ge.and.s32 p, %0, 0, p;\n\t"
-                             "@p red.shared.max.s32 [%2], %3;\n\t}" ::"r"(bp[i]), "r"(nxt),
-                             "r"(s_win_addr + (unsigned)bp[i] * 4u), "r"(pix0 + i)
+                const unsigned nxt = (i < 7) ? nf[i < 7 ? i + 1 : 7] : after;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, %1;\n\tsetp.ne.and.u32 p, %0, 0, p;\n\t"
+                             "@p red.global.max.s32 [%2], %3;\n\t}" ::"r"(nf[i]), "r"(nxt), "l"(wbase - (int64_t)(int)nf[i] * 4),
+                             "r"(pix0 + i)
                              : "memory");
             }
             if (compat_bg) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) bgmax = bp[i] < 0 ? pix0 + i : bgmax;  // pixel index grows with i
+                for (int i = 0; i < 8; ++i) bgmax = nf[i] == 0u ? pix0 + i : bgmax;  // pixel index grows with i
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const bool in_img = row_ok && (col + i < W);
                 const int pix = pix0 + i;
-                const int nxt = (i < 7) ? ((col + i + 1 < W) ? bp[i + 1] : -2) : ((has_next && col + 8 < W) ? next_first : -2);
+                const unsigned nxt =
+                    (i < 7) ? ((col + i + 1 < W) ? nf[i < 7 ? i + 1 : 7] : 1u) : ((has_next && col + 8 < W) ? next_first : 1u);
                 if (in_img) {
-                    if (bp[i] < 0) {
-                        bgmax = pix;  // pixel index grows with i
-                    } else if (bp[i] != nxt) {
-                        if (bp[i] < GG_CHUNK) atomicMax(&s_win[bp[i]], pix);
-                        else atomicMax(&vs.winner[bf[i]], pix);
-                    }
+                    if (nf[i] == 0u) bgmax = pix;  // pixel index grows with i
+                    else if (nf[i] != nxt) atomicMax(&winner[(int)~nf[i]], pix);
                 }
             }
         }
-        __syncwarp();
-        if (lane < len) {  // len > GG_CHUNK: the first chunk's setups were overwritten, fetch the face ID again
-            const int p = s_win[lane];
-            if (p >= 0) atomicMax(&vs.winner[len <= GG_CHUNK ? s_faces[lane].face : vs.bins[beg + lane].face], p);
-        }
         if (compat_bg) {  // meshes.py:2000: background pixels index the last face
             bgmax = __reduce_max_sync(0xffffffffu, bgmax);
-            if (lane == 0 && bgmax >= 0) atomicMax(&vs.winner[compat_bg - 1], bgmax);
+            if (lane == 0 && bgmax >= 0) atomicMax(&winner[compat_bg - 1], bgmax);
         }
     }
 
