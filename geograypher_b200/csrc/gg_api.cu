@@ -267,7 +267,7 @@ int gg_create(int device, gg_context **out) {
     GG_CUDA(cudaStreamCreateWithPriority(&ctx->sB, cudaStreamNonBlocking, prio_lo));
     GG_CUDA(cudaStreamCreateWithPriority(&ctx->sC, cudaStreamNonBlocking, prio_hi));
     GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_user, cudaEventDisableTiming));
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < GG_NSETS; ++s) {
         GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_bin[s], cudaEventDisableTiming));
         GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_ras[s], cudaEventDisableTiming));
         GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_mid[s], cudaEventDisableTiming));
@@ -299,7 +299,7 @@ void gg_destroy(gg_context *ctx) {
     if (ctx->sB) cudaStreamDestroy(ctx->sB);
     if (ctx->sC) cudaStreamDestroy(ctx->sC);
     if (ctx->ev_user) cudaEventDestroy(ctx->ev_user);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < GG_NSETS; ++s) {
         if (ctx->ev_bin[s]) cudaEventDestroy(ctx->ev_bin[s]);
         if (ctx->ev_ras[s]) cudaEventDestroy(ctx->ev_ras[s]);
         if (ctx->ev_mid[s]) cudaEventDestroy(ctx->ev_mid[s]);
@@ -313,7 +313,7 @@ int gg_sync(gg_context *ctx, void *stream) {
     GG_CUDA(cudaStreamSynchronize(ctx->sA));
     GG_CUDA(cudaStreamSynchronize(ctx->sB));
     GG_CUDA(cudaStreamSynchronize(ctx->sC));
-    ctx->ras_pending[0] = ctx->ras_pending[1] = false;
+    for (int s = 0; s < GG_NSETS; ++s) ctx->ras_pending[s] = false;
     GG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     GG_CUDA(cudaGetLastError());
     int32_t st4[4] = {0, 0, 0, 0};
@@ -381,7 +381,7 @@ int gg_set_pipeline(gg_context *ctx, int enable) {
     int rc = check_ctx(ctx, false);
     if (rc != GG_OK) return rc;
     GG_CUDA(cudaDeviceSynchronize());
-    ctx->ras_pending[0] = ctx->ras_pending[1] = false;
+    for (int s = 0; s < GG_NSETS; ++s) ctx->ras_pending[s] = false;
     ctx->pipeline = enable != 0;
     return GG_OK;
 }
@@ -454,7 +454,7 @@ int gg_set_mesh(gg_context *ctx, const float *d_verts, int64_t V, const int32_t 
     ctx->n_slots = 0;
     ctx->slot_tiles = 0;
     ctx->cap_recs = ctx->cap_bins = 0;
-    ctx->ras_pending[0] = ctx->ras_pending[1] = false;
+    for (int s = 0; s < GG_NSETS; ++s) ctx->ras_pending[s] = false;
     ctx->d_wdense = nullptr;
     ctx->wdense_cap = 0;
     ctx->d_verts = nullptr;
@@ -587,14 +587,14 @@ int gg_project_aggregate(gg_context *ctx, const gg_camera *h_cams, int n, const 
         // leaves every face's last pixel in scratch and k_resolve_batch applies the views in order (bit-identical
         // to the reference's loop, meshes.py:2056-2062).  Pixel-sum: the rasterizer's dense epilogue streams the
         // scores.  Software pipeline: this batch is binned on stream A while the previous batch is still being
-        // rasterized on stream B; the two alternate between two sets of scratch slots.  The accumulators are
+        // rasterized on stream B; the batches rotate through GG_NSETS sets of scratch slots.  The accumulators are
         // complete once gg_finalize / gg_sync (or any other entry point) has been called on the caller's stream.
         cudaStream_t sb = st, sr = st;
         if (ctx->pipeline) {
             sb = ctx->sA;
             sr = ctx->sB;
             ctx->cur = ctx->parity;
-            ctx->parity ^= 1;
+            ctx->parity = (ctx->parity + 1) % GG_NSETS;
             GG_CUDA(cudaEventRecord(ctx->ev_user, st));
             GG_CUDA(cudaStreamWaitEvent(sb, ctx->ev_user, 0));  // after whatever the caller enqueued before
             GG_CUDA(cudaStreamWaitEvent(sr, ctx->ev_user, 0));

@@ -26,6 +26,9 @@
 #ifndef GG_RASTER_MIN_BLOCKS
 #define GG_RASTER_MIN_BLOCKS (32 / GG_RASTER_WARPS)  // 64 registers per thread: 32 warps per SM
 #endif
+#ifndef GG_NSETS
+#define GG_NSETS 3             // scratch-slot sets the software pipeline rotates through
+#endif
 #define GG_CHUNK 32            // faces staged per warp per pass (one per lane)
 #define GG_BLOCK_FACES 128     // faces per cull block
 
@@ -124,13 +127,15 @@ struct gg_context {
     int64_t slot_tiles = 0;
     char *d_scratch = nullptr;
     size_t scratch_bytes = 0;
-    GGViewBatch vset[2];          // two sets of batch slots: batch k+1 is binned while batch k is rasterized
+    GGViewBatch vset[GG_NSETS];   // sets of batch slots: batch k+1 is binned while batch k is rasterized and batch
+                                  // k-1 resolved (the third set keeps a slow resolve -- rows fetched over PCIe -- from
+                                  // holding back the binning of batch k+2)
     int cur = 0;                  // set used by the work being enqueued / most recently enqueued
     // software pipeline of the fused aggregation (gg_project_aggregate): binning on sA, raster + resolve on sB
     cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr;  // binning / rasterizer / resolve
-    cudaEvent_t ev_mid[2] = {nullptr, nullptr};             // rasterizer of a set done (resolve may start)
-    cudaEvent_t ev_user = nullptr, ev_bin[2] = {nullptr, nullptr}, ev_ras[2] = {nullptr, nullptr};
-    bool ras_pending[2] = {false, false};
+    cudaEvent_t ev_mid[GG_NSETS] = {};            // rasterizer of a set done (resolve may start)
+    cudaEvent_t ev_user = nullptr, ev_bin[GG_NSETS] = {}, ev_ras[GG_NSETS] = {};
+    bool ras_pending[GG_NSETS] = {};
     int parity = 0;
     bool pipeline = true;
     int32_t *d_winner = nullptr;  // [F] last-pixel winner per face (dense, unfused aggregation)

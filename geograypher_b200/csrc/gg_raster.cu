@@ -1223,7 +1223,7 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
         GG_CUDA(cudaFree(ctx->d_scratch));
         ctx->d_scratch = nullptr;
     }
-    const int slots = n_views > ctx->n_slots ? n_views : ctx->n_slots;  // per set; two sets are allocated
+    const int slots = n_views > ctx->n_slots ? n_views : ctx->n_slots;  // per set; GG_NSETS sets are allocated
     const int64_t slot_tiles = tiles > ctx->slot_tiles ? tiles : ctx->slot_tiles;
     const size_t b_vis = align_up((size_t)ctx->n_blocks * 4, 256);
     const size_t b_rec = align_up((size_t)cap_recs * sizeof(GGFaceRec), 256);
@@ -1232,9 +1232,9 @@ int gg_ensure_scratch(gg_context *ctx, int n_views, int W, int H) {
     const size_t b_bin = align_up((size_t)cap_bins * sizeof(GGTileFace), 256);
     const size_t b_ctr = 256;
     const size_t per_slot = b_vis + b_rec + b_cnt + b_off + b_bin + b_ctr;
-    GG_CUDA(cudaMalloc(&ctx->d_scratch, per_slot * slots * 2));
-    ctx->scratch_bytes = per_slot * slots * 2;
-    for (int s = 0; s < 2 * slots; ++s) {
+    GG_CUDA(cudaMalloc(&ctx->d_scratch, per_slot * slots * GG_NSETS));
+    ctx->scratch_bytes = per_slot * slots * GG_NSETS;
+    for (int s = 0; s < GG_NSETS * slots; ++s) {
         char *p = ctx->d_scratch + per_slot * s;
         GGViewScratch &v = ctx->vset[s / slots].v[s % slots];
         v.vis_blocks = (int32_t *)p;
@@ -1300,7 +1300,7 @@ static int launch_dense(gg_context *ctx, const GGCamBatch &cb, dim3 rgrid, int n
 }
 
 int gg_pipeline_drain(gg_context *ctx, cudaStream_t st) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < GG_NSETS; ++s) {
         if (ctx->ras_pending[s]) {
             GG_CUDA(cudaStreamWaitEvent(st, ctx->ev_ras[s], 0));
             ctx->ras_pending[s] = false;
@@ -1330,10 +1330,10 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
                 GG_CUDA(cudaFree(ctx->d_wdense));
                 ctx->d_wdense = nullptr;
             }
-            GG_CUDA(cudaMalloc(&ctx->d_wdense, (size_t)2 * n * ctx->F * 4));
+            GG_CUDA(cudaMalloc(&ctx->d_wdense, (size_t)GG_NSETS * n * ctx->F * 4));
             // -1 = "not seen".  Set once: every consumer of a batch's winners (gg_launch_resolve_batch,
             // gg_launch_compact_winners) puts back the entries the batch touched, which is ~1 % of a full clear.
-            GG_CUDA(cudaMemset(ctx->d_wdense, 0xFF, (size_t)2 * n * ctx->F * 4));
+            GG_CUDA(cudaMemset(ctx->d_wdense, 0xFF, (size_t)GG_NSETS * n * ctx->F * 4));
             ctx->wdense_cap = (int64_t)n * ctx->F;
         }
         for (int i = 0; i < n; ++i)
