@@ -21,7 +21,7 @@ MAX_VIEWS_PER_CALL = 32
 PRED_F32, PRED_F64, PRED_U8, PRED_INDEX_U8 = 0, 1, 2, 3
 MODE_LAST_PIXEL, MODE_PIXEL_SUM, MODE_VOTE = 0, 1, 2
 OUT_F64, OUT_F32, OUT_U8 = 0, 1, 2
-FLAG_COMPAT_NEGATIVE_INDEX, FLAG_KEEP_NAN, FLAG_ASSIGN = 1, 2, 4
+FLAG_COMPAT_NEGATIVE_INDEX, FLAG_KEEP_NAN, FLAG_ASSIGN, FLAG_TRUNCATE = 1, 2, 4, 8
 ERR_OVERFLOW = -4
 
 EXPORTS = [
@@ -31,7 +31,7 @@ EXPORTS = [
     "gg_profile_read", "gg_drain", "gg_set_pipeline", "gg_build_warp_map", "gg_gather_i32",
     "gg_label_polygons", "gg_get_capacity", "gg_rasterize_render_flat", "gg_project_winners", "gg_accumulate_rows",
     "gg_overflow_info", "gg_resize_render", "gg_label_polygons_overlay", "gg_host_alloc", "gg_host_free",
-    "gg_pointer_kind",
+    "gg_pointer_kind", "gg_gather_rows_host",
 ]
 
 
@@ -98,6 +98,7 @@ def load():
     lib.gg_host_alloc.argtypes = [i32, ctypes.c_size_t, ctypes.POINTER(vp)]
     lib.gg_host_free.argtypes = [vp]
     lib.gg_pointer_kind.argtypes = [vp]
+    lib.gg_gather_rows_host.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp, i32]
     lib.gg_get_capacity.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
     lib.gg_set_mesh.argtypes = [vp, vp, i64, vp, i64, vp]
     lib.gg_project.argtypes = [vp, camp, i32, vp, vp, vp, vp, vp]
@@ -139,6 +140,32 @@ def pointer_kind(array) -> int:
     """Where a NumPy array's memory lives as far as the GPU is concerned (gg_pointer_kind): pageable host memory
     (the GPU cannot read it), page-locked host memory, device memory or managed memory."""
     return int(load().gg_pointer_kind(ctypes.c_void_p(int(array.ctypes.data))))
+
+
+def gather_rows_host(images, pairs, offsets, out, n_threads: int = 0, pair_starts=None):
+    """out[i] = images[v].reshape(-1, E)[pairs[s, 1]] for every i in offsets[v] .. offsets[v+1], with
+    s = pair_starts[v] + i - offsets[v] (``pair_starts`` None: s = i, packed lists) -- gg_gather_rows_host: the host half
+    of the pageable-image route, on several cores and without the GIL.  ``images``: C-contiguous arrays of one dtype
+    whose last axis has E elements (or (H, W) arrays, E = 1); ``pairs`` (N, 2) int32 (face, pixel); ``out`` (M, E)."""
+    n = len(images)
+    E = int(out.shape[1]) if out.ndim == 2 else 1
+    row_bytes = E * out.dtype.itemsize
+    for a in images:
+        if not a.flags["C_CONTIGUOUS"] or a.dtype != out.dtype or a.size % E:
+            raise ValueError("gather_rows_host: images must be C-contiguous, of the output's dtype, with E-element rows")
+    if not (pairs.flags["C_CONTIGUOUS"] and pairs.dtype == np.int32 and out.flags["C_CONTIGUOUS"]):
+        raise ValueError("gather_rows_host: pairs must be contiguous int32, out contiguous")
+    ptrs = (ctypes.c_void_p * n)(*[int(a.ctypes.data) for a in images])
+    npix = np.asarray([a.size // E for a in images], dtype=np.int64)
+    offs = np.ascontiguousarray(offsets, dtype=np.int64)
+    if offs.shape[0] != n + 1 or int(offs[-1]) > out.shape[0]:
+        raise ValueError("gather_rows_host: offsets do not match images / out")
+    starts = offs if pair_starts is None else np.ascontiguousarray(pair_starts, dtype=np.int64)
+    if starts.shape[0] < n or any(int(starts[v]) + int(offs[v + 1] - offs[v]) > pairs.shape[0] for v in range(n)):
+        raise ValueError("gather_rows_host: pair lists run past the end of pairs")
+    _check(load().gg_gather_rows_host(ptrs, npix.ctypes.data, pairs.ctypes.data,
+                                      None if pair_starts is None else starts.ctypes.data, offs.ctypes.data, n,
+                                      row_bytes, out.ctypes.data, int(n_threads)))
 
 
 def host_array(shape, dtype=np.float32, device: int = 0) -> np.ndarray:
@@ -459,12 +486,15 @@ class Context:
                     raise
                 self._grow_after_overflow(n)
 
-    def project_winners(self, cams, flags=0, stream=None):
+    def project_winners(self, cams, flags=0, stream=None, cap=None):
         """Rasterize up to 32 same-size views and list, per view, every visible face with its last pixel (row-major):
         returns (pairs (n, cap, 2) int32 CUDA tensor of (face, pixel), counts (n,) int32 CUDA tensor).  Asynchronous;
-        an overflow of the scratch shows up at the next sync() (grow with _grow_after_overflow and call again)."""
+        an overflow of the scratch shows up at the next sync() (grow with _grow_after_overflow and call again).
+        ``cap`` (default: what the scratch can produce) bounds the list of a view; a view with more visible faces
+        reports its full count and lists only the first ``cap``."""
         t, n = self.torch, len(cams)
-        cap = self.capacity_hint(cams[0].W, cams[0].H)
+        full = self.capacity_hint(cams[0].W, cams[0].H)
+        cap = full if cap is None else max(1, min(int(cap), full))
         pairs = t.empty((n, cap, 2), dtype=t.int32, device=self._dev())
         counts = t.empty((n,), dtype=t.int32, device=self._dev())
         _check(self.lib.gg_project_winners(self.handle, self._cam_array(cams), n, flags, pairs.data_ptr(), cap,

@@ -10,5 +10,5 @@ mkdir -p build
 for f in gg_api gg_raster gg_aggregate gg_warp gg_polygons; do
   "$NVCC" "${FLAGS[@]}" -c $f.cu -o build/$f.o 2> build/$f.ptxas.log || { cat build/$f.ptxas.log; exit 1; }
 done
-"$NVCC" -shared -o "$OUT" build/gg_api.o build/gg_raster.o build/gg_aggregate.o build/gg_warp.o build/gg_polygons.o -lcudart -ccbin /usr/bin/g++
+"$NVCC" -shared -o "$OUT" build/gg_api.o build/gg_raster.o build/gg_aggregate.o build/gg_warp.o build/gg_polygons.o -lcudart -lpthread -ccbin /usr/bin/g++
 echo "built $OUT"

@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(256) k_compact_winners(const __grid_constant__
             if (idx < cap) {
                 pairs[2 * ((int64_t)view * cap + idx)] = f;
                 pairs[2 * ((int64_t)view * cap + idx) + 1] = p;
-            } else {
+            } else if (!(flags & GG_FLAG_TRUNCATE)) {
                 atomicOr(sticky, 1);
             }
         }

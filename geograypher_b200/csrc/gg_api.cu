@@ -3,6 +3,13 @@
 #include <cstring>
 
 #include <cstdlib>
+#include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <unistd.h>
+#include <vector>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 
@@ -230,6 +237,120 @@ int gg_pointer_kind(const void *p) {
         case cudaMemoryTypeManaged: return 3;
         default: return 0;
     }
+}
+
+namespace {
+// Persistent host threads for gg_gather_rows_host: starting 15 threads per call costs as much as the gather itself.
+struct HostPool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable wake, done;
+    const std::function<void(int)> *job = nullptr;
+    int n_active = 0;   // workers taking part in the current job (worker t runs slice t + 1)
+    int generation = 0, pending = 0;
+    bool stop = false;
+
+    void worker(int t) {
+        int seen = 0;
+        for (;;) {
+            const std::function<void(int)> *f;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                wake.wait(lk, [&] { return stop || (generation != seen && t < n_active); });
+                if (stop) return;
+                seen = generation;
+                f = job;
+            }
+            (*f)(t + 1);
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (--pending == 0) done.notify_one();
+            }
+        }
+    }
+    void run(int T, const std::function<void(int)> &f) {  // slices 0 .. T-1; slice 0 on the calling thread
+        {
+            std::lock_guard<std::mutex> lk(m);
+            while ((int)threads.size() < T - 1) {
+                const int t = (int)threads.size();
+                threads.emplace_back([this, t] { worker(t); });
+            }
+            job = &f;
+            n_active = T - 1;
+            pending = T - 1;
+            ++generation;
+        }
+        wake.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(m);
+        done.wait(lk, [&] { return pending == 0; });
+        n_active = 0;
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        wake.notify_all();
+        for (auto &t : threads) t.join();
+    }
+};
+HostPool &host_pool() {
+    // never destroyed (worker threads must not be joined from atexit handlers); a forked child starts its own, since
+    // threads do not survive fork()
+    static HostPool *pool = nullptr;
+    static pid_t owner = 0;
+    if (!pool || owner != getpid()) {
+        pool = new HostPool();
+        owner = getpid();
+    }
+    return *pool;
+}
+std::mutex g_gather_mutex;
+}  // namespace
+
+int gg_gather_rows_host(const void *const *h_images, const int64_t *h_pixels_per_image, const int32_t *h_pairs,
+                        const int64_t *h_pair_starts, const int64_t *h_offsets, int n_views, int64_t row_bytes,
+                        void *h_out, int n_threads) {
+    if (!h_images || !h_pixels_per_image || !h_pairs || !h_offsets || !h_out || n_views < 1 || row_bytes < 1) {
+        gg_set_error("gg_gather_rows_host: bad arguments");
+        return GG_ERR_INVALID;
+    }
+    const int64_t total = h_offsets[n_views];
+    if (total <= 0) return GG_OK;
+    // default: up to 16 threads (more only add wake-up latency to a gather that lasts a fraction of a millisecond)
+    int T = n_threads > 0 ? n_threads : std::min(16, (int)std::thread::hardware_concurrency());
+    T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(T, 64), total / 4096 + 1));
+    // pair i of view v sits at h_pairs[2 * (start[v] + i - h_offsets[v])]: packed lists by default
+    const int64_t *start = h_pair_starts ? h_pair_starts : h_offsets;
+    const std::function<void(int)> work = [&](int t) {
+        const int64_t lo = total * t / T, hi = total * (t + 1) / T;
+        int v = 0;
+        while (h_offsets[v + 1] <= lo) ++v;
+        int va = v;
+        constexpr int kAhead = 16;  // rows are cache (and TLB) misses: keep some in flight per thread
+        for (int64_t i = lo; i < hi; ++i) {
+            while (h_offsets[v + 1] <= i) ++v;
+            if (i + kAhead < hi) {
+                while (h_offsets[va + 1] <= i + kAhead) ++va;
+                int64_t pa = h_pairs[2 * (start[va] + (i + kAhead - h_offsets[va])) + 1];
+                pa = pa < 0 ? 0 : (pa >= h_pixels_per_image[va] ? h_pixels_per_image[va] - 1 : pa);
+                const char *a = (const char *)h_images[va] + pa * row_bytes;
+                __builtin_prefetch(a);
+                __builtin_prefetch(a + row_bytes - 1);
+            }
+            int64_t p = h_pairs[2 * (start[v] + (i - h_offsets[v])) + 1];
+            p = p < 0 ? 0 : (p >= h_pixels_per_image[v] ? h_pixels_per_image[v] - 1 : p);  // np.take(mode="clip")
+            memcpy((char *)h_out + i * row_bytes, (const char *)h_images[v] + p * row_bytes, (size_t)row_bytes);
+        }
+    };
+    if (T == 1) {
+        work(0);
+        return GG_OK;
+    }
+    std::lock_guard<std::mutex> one_at_a_time(g_gather_mutex);
+    host_pool().run(T, work);
+    return GG_OK;
 }
 
 const char *gg_last_error(void) { return g_last_error.c_str(); }

@@ -585,62 +585,82 @@ class TexturedPhotogrammetryMesh:
         need = int(np.prod(shape))
         buf = stage.get(name)
         if buf is None or buf.dtype != dtype or buf.numel() < need:
-            buf = stage[name] = torch.empty((max(need, 1),), dtype=dtype, pin_memory=True)
+            # page-locking is slow (~1 GB/s): grow geometrically so that slowly growing batches do not re-pin each time
+            grown = need if buf is None or buf.dtype != dtype else max(need, buf.numel() * 3 // 2)
+            buf = stage[name] = torch.empty((max(grown, 1),), dtype=dtype, pin_memory=True)
         return buf[:need].view(*shape)
 
-    def _accumulate_sparse(self, ctx, gg, arrays, kind, C, mode, flags, d_sum, d_count):
-        """One batch whose prediction images sit in ordinary (pageable) NumPy arrays.  Uploading a 20-Mpx score image
-        costs ~100x the path itself, and the aggregation only needs the row of each visible face's last pixel, so:
-        rasterize and list (face, pixel) per view on the GPU (gg_project_winners), copy that short list to the host,
-        pick the rows out of the arrays with a few threads, send them back and apply them view by view
-        (gg_accumulate_rows) -- the same arithmetic, in the same order, as the fused path."""
+    def _sparse_begin(self, ctx, gg, flags, serial, full=False):
+        """First half of a batch whose prediction images sit in ordinary (pageable) NumPy arrays.  Uploading a 20-Mpx
+        score image costs ~100x the path itself, and the aggregation only needs the row of each visible face's last
+        pixel, so: rasterize and list (face, pixel) per view on the GPU (gg_project_winners) and start copying the
+        lists to the host on a side stream.  The lists are short and about as long as the previous batch's, so they are
+        given that much room (a view that needs more makes ``_sparse_finish`` redo the batch with full-size lists) and
+        lists and counts come back in ONE transfer.  Returns the state ``_sparse_finish`` completes; the caller begins
+        batch k+1 BEFORE finishing batch k, so the host picks rows while the GPU rasterizes."""
         import torch
 
+        sides = self.__dict__.get("_sparse_streams")
+        if sides is None:
+            sides = self.__dict__["_sparse_streams"] = [torch.cuda.Stream(device=self.device) for _ in range(2)]
         n = len(gg)
+        guess = int(self.__dict__.get("_sparse_guess", 0))
+        full = full or guess <= 0
+        pairs, counts = ctx.project_winners(gg, flags | (0 if full else _lib.FLAG_TRUNCATE), cap=None if full else guess)
+        listed = torch.cuda.Event()
+        listed.record()
+        slot = serial % 2
+        side = sides[slot]  # one copy stream per slot: the lists of batch k must not queue behind "batch k+1 listed"
+        # (the host finished reading this slot's list buffers two batches ago, in _sparse_finish)
+        h_counts = self._pinned(f"counts{slot}", (n,), torch.int32)
+        h_lists = self._pinned(f"lists{slot}", tuple(pairs.shape), torch.int32)
+        with torch.cuda.stream(side):
+            side.wait_event(listed)
+            h_counts.copy_(counts, non_blocking=True)
+            h_lists.copy_(pairs, non_blocking=True)
+            arrived = torch.cuda.Event()
+            arrived.record(side)
+        return dict(n=n, gg=gg, pairs=pairs, counts=counts, h_counts=h_counts, h_lists=h_lists, arrived=arrived,
+                    slot=slot, serial=serial, full=full)
+
+    def _sparse_finish(self, ctx, st, arrays, kind, C, mode, flags, d_sum, d_count):
+        """Second half: pick the listed rows out of the arrays on the host's cores (gg_gather_rows_host), send them
+        back and apply them view by view (gg_accumulate_rows) -- the same arithmetic, in the same order, as the fused
+        path."""
+        import torch
+
+        n, pairs, slot = st["n"], st["pairs"], st["slot"]
         E = 1 if (mode == _lib.MODE_VOTE or kind == _lib.PRED_INDEX_U8) else C  # elements per pixel
-        pairs, counts = ctx.project_winners(gg, flags)
-        h_counts = self._pinned("counts", (n,), torch.int32)
-        h_counts.copy_(counts, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        m = [int(x) for x in h_counts.tolist()]
+        st["arrived"].synchronize()
+        m = [int(x) for x in st["h_counts"].tolist()]
         cap = pairs.shape[1]
-        if max(m, default=0) > cap:  # the list did not fit: reported as an overflow by the next sync, then replayed
-            return
+        # room for the next batches' lists: a quarter more than the longest seen, never shrinking (stable buffer sizes)
+        self.__dict__["_sparse_guess"] = max(int(self.__dict__.get("_sparse_guess", 0)),
+                                             -(-(int(max(m, default=0) * 1.25) + 1024) // 8192) * 8192)
+        if max(m, default=0) > cap:
+            if st["full"]:  # the scratch itself overflowed: reported by the next sync, then replayed
+                return
+            redo = self._sparse_begin(ctx, st["gg"], flags, st["serial"], full=True)
+            return self._sparse_finish(ctx, redo, arrays, kind, C, mode, flags, d_sum, d_count)
         offs = np.concatenate([[0], np.cumsum(m)]).astype(np.int64)
         total = int(offs[-1])
         if total == 0:
             return
-        h_pairs = self._pinned("pairs", (total, 2), torch.int32)
-        for v in range(n):
-            if m[v]:
-                h_pairs[offs[v] : offs[v + 1]].copy_(pairs[v, : m[v]], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
         np_dtype = arrays[0].dtype
         t_dtype = torch.from_numpy(np.empty(0, dtype=np_dtype)).dtype
-        h_rows = self._pinned("rows_" + str(np_dtype), (total, E), t_dtype)
-        rows_np, pairs_np = h_rows.numpy(), h_pairs.numpy()
-
-        def gather(job):
-            v, a, b = job
-            flat = arrays[v].reshape(-1, E)
-            np.take(flat, pairs_np[a:b, 1], axis=0, out=rows_np[a:b], mode="clip")
-
-        jobs = []
-        for v in range(n):  # split every view into a few chunks so that all threads have work
-            step = max(2048, -(-m[v] // 4))
-            jobs += [(v, int(offs[v]) + a, int(offs[v]) + min(a + step, m[v])) for a in range(0, m[v], step)]
-        pool = self.__dict__.get("_copy_pool")
-        if pool is None:
-            from concurrent.futures import ThreadPoolExecutor
-
-            pool = self.__dict__["_copy_pool"] = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
-        list(pool.map(gather, jobs))
+        busy = self.__dict__.setdefault("_sparse_busy", [None, None])
+        if busy[slot] is not None:  # the upload that last read this slot's row buffer (two batches ago)
+            busy[slot].synchronize()
+        h_rows = self._pinned(f"rows{slot}_" + str(np_dtype), (total, E), t_dtype)
+        # every core picks rows (native threads with software prefetch: np.take holds the GIL)
+        _lib.gather_rows_host([np.ascontiguousarray(a) for a in arrays], st["h_lists"].numpy().reshape(-1, 2), offs,
+                              h_rows.numpy(), pair_starts=np.arange(n, dtype=np.int64) * cap)
         d_rows = h_rows.to(d_sum.device, non_blocking=True)
+        busy[slot] = torch.cuda.Event()
+        busy[slot].record()
         for v in range(n):  # view order = the reference's summation order
             if m[v]:
                 ctx.accumulate_rows(pairs[v], m[v], d_rows[offs[v] : offs[v + 1]], kind, C, mode, flags, d_sum, d_count)
-        # the staging buffers are reused by the next batch: the copies out of them must have finished
-        torch.cuda.current_stream().synchronize()
 
     def _fetch_prediction(self, cameras, k, scale, image_getter, index_getter):
         """(array, pred_kind, C) of view k: a caller-supplied getter, else the segmentor's class-index image when
@@ -676,6 +696,7 @@ class TexturedPhotogrammetryMesh:
         for attempt in range(4):
             d_sum = d_count = None
             in_flight = []
+            pending = None  # a batch of pageable images whose rows the host has yet to pick
             try:
                 for bi, s in enumerate(range(0, n, B)):
                     batch = cam_list[s : s + B]
@@ -702,9 +723,15 @@ class TexturedPhotogrammetryMesh:
                         if in_flight:  # the fused calls queued so far use the library's own streams
                             ctx.sync()
                             in_flight.clear()
-                        self._accumulate_sparse(ctx, self._gg_cameras(batch, mesh, aggregate_img_scale), preds, kind, C,
-                                                mode, flags, d_sum, d_count)
+                        # two-deep: this batch is rasterized while the host picks the rows of the previous one
+                        began = self._sparse_begin(ctx, self._gg_cameras(batch, mesh, aggregate_img_scale), flags, bi)
+                        if pending is not None:
+                            self._sparse_finish(ctx, *pending, mode, flags, d_sum, d_count)
+                        pending = (began, preds, kind, C)
                         continue
+                    if pending is not None:
+                        self._sparse_finish(ctx, *pending, mode, flags, d_sum, d_count)
+                        pending = None
                     preds = [self._to_device_or_mapped(a, dev, zero_copy=not apply_distortion) for a in preds]
                     if apply_distortion:
                         p2f = self._pix2face_for_aggregation(batch[0], mesh, aggregate_img_scale, pix2face_kwargs)
@@ -722,6 +749,9 @@ class TexturedPhotogrammetryMesh:
                     if uploaded >= window * B or len(in_flight) >= 8 * window:
                         ctx.sync()
                         in_flight.clear()
+                if pending is not None:
+                    self._sparse_finish(ctx, *pending, mode, flags, d_sum, d_count)
+                    pending = None
                 ctx.sync()  # raises GG_ERR_OVERFLOW if any batch since the last sync outgrew the scratch
                 break
             except _lib.GeograypherB200Error as e:

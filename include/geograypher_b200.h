@@ -91,6 +91,15 @@ int gg_create(int device, gg_context **out);
 int gg_host_alloc(int device, size_t bytes, void **out);
 int gg_host_free(void *p);
 int gg_pointer_kind(const void *p);
+/* Host-side helper of the pageable-image route (gg_project_winners -> this -> gg_accumulate_rows): copy, for every
+   listed (face, pixel) pair of every view, the `row_bytes` bytes of that pixel out of the view's image into one packed
+   table, on `n_threads` persistent host threads (0 = up to 16) with software prefetch.  View v owns output rows
+   h_offsets[v] .. h_offsets[v+1]; its pairs start at pair index h_pair_starts[v] (NULL: packed like the output, i.e.
+   h_offsets).  Pixel indices are clamped to the image like np.take(mode="clip").  Replaces the reference's NumPy fancy
+   indexing `img[pix2face-ordered rows]` (meshes.py:1991-2001), which holds the GIL.  No GPU work; no context needed. */
+int gg_gather_rows_host(const void *const *h_images, const int64_t *h_pixels_per_image, const int32_t *h_pairs,
+                        const int64_t *h_pair_starts, const int64_t *h_offsets, int n_views, int64_t row_bytes,
+                        void *h_out, int n_threads);
 void gg_destroy(gg_context *ctx);
 /* Synchronise `stream` and the internal streams, and report a deferred failure of the work enqueued since the last
    gg_sync (GG_ERR_OVERFLOW: the batches that overflowed the scratch were skipped as a whole; CUDA errors). */
@@ -150,6 +159,9 @@ int gg_rasterize(gg_context *ctx, const gg_camera *h_cams, int n, int32_t *d_pix
 #define GG_FLAG_COMPAT_NEG 1
 #define GG_FLAG_KEEP_NAN 2
 #define GG_FLAG_ASSIGN 4
+#define GG_FLAG_TRUNCATE 8 /* gg_project_winners: a view with more than cap_pairs_per_view visible faces lists the first
+                              cap and reports its full count in d_counts -- not an overflow; the caller calls again
+                              with room for it (lists are usually ~1 % of what the scratch could produce) */
 int gg_aggregate(gg_context *ctx, const int32_t *d_pix2face, int H, int W, const void *d_pred, int pred_kind,
                  int C, int mode, int flags, double *d_sum, int32_t *d_count, void *stream);
 

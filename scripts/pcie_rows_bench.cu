@@ -29,7 +29,23 @@ int main(int argc, char **argv) {
     const int n = 250000;
     unsigned char *h = nullptr;
     const int thp = argc > 2 ? atoi(argv[2]) : 0;  // 1: transparent huge pages (mmap + MADV_HUGEPAGE) + cudaHostRegister
-    if (thp == 2) {  // managed memory that prefers the host and is mapped into the GPU: accessed over PCIe, not migrated
+    if (thp == 3 || thp == 4) {  // ordinary malloc'ed memory: only readable by the GPU where the driver offers HMM / ATS
+        int pma = 0, hpt = 0;
+        CK(cudaDeviceGetAttribute(&pma, cudaDevAttrPageableMemoryAccess, 0));
+        CK(cudaDeviceGetAttribute(&hpt, cudaDevAttrPageableMemoryAccessUsesHostPageTables, 0));
+        printf("pageableMemoryAccess = %d, usesHostPageTables = %d\n", pma, hpt);
+        if (!pma) return 0;
+        h = (unsigned char *)malloc((size_t)P * 64);
+        for (long long i = 0; i < P * 64; i += 4096) h[i] = (unsigned char)i;
+        if (thp == 4) {
+            cudaError_t e1 = cudaMemAdvise(h, (size_t)P * 64, cudaMemAdviseSetPreferredLocation, cudaCpuDeviceId);
+            cudaError_t e2 = cudaMemAdvise(h, (size_t)P * 64, cudaMemAdviseSetAccessedBy, 0);
+            printf("malloc + advise: preferred location %s, accessed by %s\n", cudaGetErrorString(e1), cudaGetErrorString(e2));
+            (void)cudaGetLastError();
+        } else {
+            printf("malloc, no advice\n");
+        }
+    } else if (thp == 2) {  // managed memory that prefers the host and is mapped into the GPU: accessed over PCIe, not migrated
         CK(cudaMallocManaged(&h, (size_t)P * 64));
         CK(cudaMemAdvise(h, (size_t)P * 64, cudaMemAdviseSetPreferredLocation, cudaCpuDeviceId));
         CK(cudaMemAdvise(h, (size_t)P * 64, cudaMemAdviseSetAccessedBy, 0));

@@ -110,6 +110,24 @@ def test_aggregate_matches_reference_outputs(scene, golden_aggregate, sparse):
     _eq(avg[:-1], a["avg2"][:-1]); _eq(info["projection_counts"][:-1], a["counts2"][:-1])
 
 
+def test_pageable_route_redoes_a_batch_whose_lists_were_cut(scene, golden_aggregate):
+    """The pageable-image route sizes the (face, pixel) lists after the previous batch (GG_FLAG_TRUNCATE): a batch
+    that needs more room is listed again at full size -- same numbers, and no overflow is reported."""
+    g, cams = scene
+    a = golden_aggregate
+    C = a["avg1"].shape[1]
+    mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), compat_negative_index=True, views_per_batch=2)
+    seg2 = gg.SegmentorPhotogrammetryCameraSet(cams, gg.ArraySegmentor(list(a["soft"]), num_classes=C))
+    mesh.__dict__["_sparse_guess"] = 3  # far fewer than the faces any view sees
+    began = []
+    orig = mesh._sparse_begin
+    mesh._sparse_begin = lambda *args, **kw: (began.append(kw.get("full", False)), orig(*args, **kw))[1]
+    avg, info = mesh.aggregate_projected_images(seg2)
+    assert True in began and False in began  # the first batch was cut and redone
+    _eq(avg, a["avg2"]); _eq(info["projection_counts"], a["counts2"]); _eq(info["summed_projections"], a["summed2"])
+    assert mesh.__dict__["_sparse_guess"] >= 8192
+
+
 @pytest.mark.parametrize("sparse", [True, False])
 def test_votes_match_reference_outputs(scene, golden_aggregate, sparse):
     g, cams = scene

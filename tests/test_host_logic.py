@@ -166,3 +166,36 @@ def test_product_never_imports_the_oracle():
     for path in (ROOT / "geograypher_b200").rglob("*.py"):
         text = path.read_text()
         assert "import oracle" not in text and "from oracle" not in text, path
+
+
+def test_gather_rows_host_matches_numpy_indexing():
+    """gg_gather_rows_host (the host half of the pageable-image route; no GPU involved) == NumPy fancy indexing, for
+    packed and padded pair lists, float32 rows and uint8 class indices, empty views and out-of-range pixels (clipped)."""
+    from geograypher_b200 import _lib
+
+    rng = np.random.default_rng(3)
+    imgs = [rng.random((40, 50, 7)).astype(np.float32) for _ in range(5)]
+    m = [300, 0, 9000, 1, 4500]
+    offs = np.concatenate([[0], np.cumsum(m)])
+    pix = [rng.integers(0, 2000, k).astype(np.int32) for k in m]
+    pix[2][:3] = [-5, 2000, 10**6]  # np.take(mode="clip") semantics
+    ref = np.concatenate([imgs[v].reshape(-1, 7)[np.clip(pix[v], 0, 1999)] for v in range(5)])
+    packed = np.zeros((offs[-1], 2), np.int32)
+    packed[:, 1] = np.concatenate(pix)
+    for threads in (1, 3, 0):
+        out = np.zeros((offs[-1], 7), np.float32)
+        _lib.gather_rows_host(imgs, packed, offs, out, n_threads=threads)
+        np.testing.assert_array_equal(out, ref)
+    cap = 9100
+    padded = np.full((5, cap, 2), -7, np.int32)
+    for v in range(5):
+        padded[v, : m[v], 1] = pix[v]
+    out = np.zeros((offs[-1], 7), np.float32)
+    _lib.gather_rows_host(imgs, padded.reshape(-1, 2), offs, out, pair_starts=np.arange(5) * cap)
+    np.testing.assert_array_equal(out, ref)
+    idx = [rng.integers(0, 10, (40, 50)).astype(np.uint8) for _ in range(5)]
+    out8 = np.zeros((offs[-1], 1), np.uint8)
+    _lib.gather_rows_host(idx, packed, offs, out8)
+    np.testing.assert_array_equal(out8[:, 0], np.concatenate([idx[v].reshape(-1)[np.clip(pix[v], 0, 1999)] for v in range(5)]))
+    with pytest.raises(ValueError):
+        _lib.gather_rows_host(imgs, packed, offs[:-1], out)
