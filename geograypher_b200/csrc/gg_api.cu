@@ -377,6 +377,8 @@ int gg_create(int device, gg_context **out) {
     memset(ctx->vset, 0, sizeof(ctx->vset));
     if (const char *e = getenv("GG_DENSE_PREFETCH")) ctx->dense_prefetch = atoi(e) != 0;
     if (const char *e = getenv("GG_STAGE_HOST_ROWS")) ctx->stage_host_rows = atoi(e) != 0;
+    if (const char *e = getenv("GG_SETUP_CTAS")) ctx->setup_ctas = atoi(e);
+    if (const char *e = getenv("GG_FILL_CTAS")) ctx->fill_ctas = atoi(e);
     if (const char *e = getenv("GG_STAGE_CTAS")) ctx->stage_ctas = atoi(e) > 0 ? atoi(e) : 1;
     GG_CUDA(cudaMalloc(&ctx->d_sticky, 4 * sizeof(int32_t)));
     GG_CUDA(cudaMemset(ctx->d_sticky, 0, 4 * sizeof(int32_t)));

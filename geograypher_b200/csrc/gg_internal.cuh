@@ -142,6 +142,7 @@ struct gg_context {
     int64_t winner_cap = 0;
     int32_t *d_wdense = nullptr;  // [n_slots * F] per-view per-face winners of the fused aggregation
     int64_t wdense_cap = 0;
+    int setup_ctas = 0, fill_ctas = 0;  // > 0: CTAs per SM, summed over the views of a batch, of k_setup_faces / k_fill_bins
     char *d_stage = nullptr;      // rows fetched from prediction images that live in host memory
     size_t stage_bytes = 0;
     int stage_host_rows = 1;      // GG_STAGE_HOST_ROWS=0: resolve reads the host images directly
