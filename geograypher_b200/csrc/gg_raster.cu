@@ -1346,12 +1346,11 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
     const int nb = (int)ctx->n_blocks;
     GG_LAUNCH(ctx, GG_ST_CULL, st,
               k_cull_blocks<<<dim3((nb + 255) / 256, n), 256, 0, st>>>(ctx->d_block_lo, ctx->d_block_hi, nb, cb, ctx->vset[ctx->cur]));
-    // Grid sizes of the two binning kernels.  Alone they want the whole GPU (8 / 4 CTAs per SM and view).  In the
-    // software pipeline they run beside the previous batch's rasterizer, which is issue bound while they are latency
-    // bound: a SMALL resident set (2 CTAs per SM over the whole batch) that stays for the length of the rasterizer
-    // takes its idle issue slots instead of displacing its CTAs (measured: +2.6 % on c2; GG_SETUP_CTAS / GG_FILL_CTAS).
-    const int setup_ctas = ctx->setup_ctas > 0 ? ctx->setup_ctas : (piped ? 2 : 0);
-    const int fill_ctas = ctx->fill_ctas > 0 ? ctx->fill_ctas : (piped ? 2 : 0);
+    // Grid sizes of the two binning kernels: 8 / 4 CTAs per SM and view.  GG_SETUP_CTAS / GG_FILL_CTAS (CTAs per SM
+    // over the whole batch) shrink them to a small resident set that runs beside the previous batch's rasterizer
+    // instead of displacing its CTAs: +2.6 % on c2 at 2 / 2, but -5 % on c5, whose binning then becomes the critical
+    // path -- hence not the default.
+    const int setup_ctas = ctx->setup_ctas, fill_ctas = ctx->fill_ctas;
     int gsetup = nb < ctx->sm_count * 8 ? nb : ctx->sm_count * 8;
     if (setup_ctas > 0) gsetup = std::max(1, std::min(gsetup, ctx->sm_count * setup_ctas / n));
     const int gfill = fill_ctas > 0 ? std::max(1, ctx->sm_count * fill_ctas / n) : ctx->sm_count * 4;
