@@ -444,10 +444,13 @@ def run_ours(args):
                         "warp_instructions_per_launch": inst, "avg_launch_ms": avg_ms,
                         "peak_source": f"{sm_count} SMs x 4 schedulers x {clock_mhz:.0f} MHz (SM clock sampled under load)",
                         "traffic": hbm["traffic"], "hbm": hbm,
-                        "note": "reference-parity (last_pixel) aggregation needs ~0.1 GB of HBM traffic per 20-Mpx view: "
+                        "note": "reference-parity (last_pixel) aggregation needs ~0.02 GB of HBM traffic per 20-Mpx view: "
                                 "the rasterizer is bound by instruction issue, not by HBM (DESIGN.md section 5); "
-                                "instruction count per launch from the committed ncu capture "
-                                "(profiles/inst_counts.json), time measured live"}
+                                "instruction count per launch from the committed ncu capture of THIS kernel "
+                                "(profiles/inst_counts.json), time measured live with the binning and resolve kernels "
+                                "of the neighbouring batches sharing the SMs (0.70 under ncu, kernel alone); the "
+                                "numerator is the kernel's own instruction count, so a leaner kernel lowers this "
+                                "fraction while raising views/s"}
         return {"value": views / elapsed_s, "elapsed_s": elapsed_s, "roofline": roofline, "clocks": clocks,
                 "stage_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1] > 0},
                 "launches": int(sum(v[1] for v in prof.values())), "faces_per_view": f_v,

@@ -294,3 +294,49 @@ def test_host_array_inputs_are_read_in_place(scene, golden_aggregate):
     np.testing.assert_array_equal(info["projection_counts"], a["counts2"])
     np.testing.assert_array_equal(info["summed_projections"], a["summed2"])
     del images, seg  # the buffers are released with the arrays
+
+
+def test_many_batches_through_every_host_route_equal_the_upload_route():
+    """14 batches of one or two views (the software pipeline rotates through its three scratch sets several times; the
+    pageable route runs two-deep): prediction images in host_array memory, page-locked memory and ordinary NumPy arrays
+    give the same bits as whole images uploaded to the device, float32 scores and uint8 class indices alike."""
+    import torch
+
+    from geograypher_b200 import synthetic as syn
+
+    verts, faces, c2ws, cfg = syn.make_survey("c1")
+    W, H = cfg.image_size
+    C = cfg.n_classes
+    n = min(len(c2ws), 27)
+    intr = {0: dict(f=cfg.f, cx=cfg.cx, cy=cfg.cy, image_width=W, image_height=H, distortion_params={})}
+    cams = gg.PhotogrammetryCameraSet(cam_to_world_transforms=c2ws[:n], intrinsic_params_per_sensor_type=intr)
+    soft = [syn.softmax_predictions(k, H, W, C, grid=(5, 7)) for k in range(n)]
+    for img in soft[::5]:
+        img[::7, ::3, :] = np.nan  # nulls
+    idx = [np.argmax(np.nan_to_num(img), axis=2).astype(np.uint8) for img in soft]
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t.numpy()
+
+    def hosted(a):
+        h = gg.host_array(a.shape, a.dtype)
+        h[...] = a
+        return h
+
+    results = {}
+    for route, wrap in (("device", lambda a: a.copy()), ("host_array", hosted), ("pinned", pinned),
+                        ("pageable", lambda a: a.copy())):
+        mesh = gg.TexturedPhotogrammetryMesh((verts, faces), views_per_batch=2, log_level="WARNING",
+                                             sparse_host_gather=(route != "device"))
+        seg = gg.SegmentorPhotogrammetryCameraSet(cams, gg.ArraySegmentor([wrap(a) for a in soft], num_classes=C))
+        avg, info = mesh.aggregate_projected_images(seg, return_argmax=True)
+        segi = gg.SegmentorPhotogrammetryCameraSet(cams, gg.ArraySegmentor([wrap(a) for a in idx], num_classes=C, one_hot=True))
+        avgi, infoi = mesh.aggregate_projected_images(segi)
+        results[route] = (avg, info["projection_counts"], info["summed_projections"], info["argmax"], avgi,
+                          infoi["projection_counts"])
+    assert (results["device"][1] > 0).sum() > 100
+    for route in ("host_array", "pinned", "pageable"):
+        for got, want in zip(results[route], results["device"]):
+            np.testing.assert_array_equal(got, want, err_msg=route)
