@@ -754,7 +754,7 @@ def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, hos
     F = len(faces)
     seen_per_view = float(seen.item()) / max(n_views * world, 1)
     row_bytes = -(-row_elems * elem_bytes // 32) * 32  # PCIe reads are sector-granular
-    if kind == "pageable_f32":
+    if kind in ("pageable_f32", "pinned_f32"):  # (6.4 GB of page-locked images take the host-gather route too)
         h2d = seen_per_view * (row_elems * elem_bytes) * n_views / steps  # the host gathers the rows, then uploads them
     else:
         h2d = seen_per_view * row_bytes * n_views / steps
@@ -766,15 +766,18 @@ def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, hos
                           "row per visible face, which a small kernel fetches over PCIe in place while the next batch is "
                           "rasterized (h2d bytes = rows fetched, sector-granular); the per-face float64 averages, sums and "
                           "counts are copied back at the end",
-        "pinned_f32": "the same images in page-locked (cudaHostAlloc) memory: on this host the scattered-read rate from "
-                      "page-locked memory falls with the pinned footprint (profiles/r02_pcie_rows_footprint.txt: 284 -> "
-                      "100 M 40-byte rows/s from 1.3 to 10 GB)",
+        "pinned_f32": "the same images in page-locked (cudaHostAlloc) memory, 6.4 GB of them: on this host the "
+                      "scattered-read rate from page-locked memory falls with the pinned footprint "
+                      "(profiles/r02_pcie_rows_footprint.txt: 284 -> 100 M 40-byte rows/s from 1.3 to 10 GB; read in "
+                      "place this leg measured ~2 600 views/s), so above 4 GiB of distinct page-locked images the API "
+                      "takes the host-gather route of the pageable leg instead "
+                      "(TexturedPhotogrammetryMesh.pinned_direct_limit_bytes)",
         "pinned_index_u8": "(H,W) uint8 class-index images in pinned host memory (what LookUpSegmentor yields before "
                            "its one-hot expansion), expanded on the GPU exactly like Segmentor.inds_to_one_hot; one "
                            "byte per visible face crosses PCIe",
         "pageable_f32": "float32 (H,W,C) score images in ordinary NumPy arrays (16 distinct images): the GPU lists (face, "
-                        "last pixel) per view, the host gathers those rows and uploads them (gg_project_winners + "
-                        "gg_accumulate_rows)"}
+                        "last pixel) per view for batch k+1 while the host's cores pick the rows of batch k "
+                        "(gg_project_winners || gg_gather_rows_host -> gg_accumulate_rows)"}
     return {"value": n_views * world / dt, "unit": "views/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int((F * C * 8 * 2 + F * 8) / steps), "views": n_views * world, "seconds": dt,
             "input": kind, "distinct_host_images": len(host),

@@ -120,7 +120,11 @@ class TexturedPhotogrammetryMesh:
                 reproduces the base class, whose pyvista camera has no principal point (cameras.py:446-477).
             sparse_host_gather (*new*): prediction images in ordinary (pageable) NumPy arrays are not uploaded; the
                 GPU lists the one pixel per visible face that the aggregation needs and the host gathers those rows.
-                False uploads whole images.  Page-locked arrays are read in place by the GPU either way.
+                False uploads whole images.  Page-locked arrays are read in place by the GPU -- until the distinct
+                page-locked images of a call add up to more than ``pinned_direct_limit_bytes`` (an attribute, 4 GiB):
+                scattered PCIe reads from page-locked memory slow down with its footprint on some hosts (2.5x on
+                the benchmark host at 6 GB), where the host-gather route is then the faster one.
+                ``host_array`` memory keeps its rate and is always read in place.
         """
         if downsample_target != 1.0 or ROI is not None:
             raise NotImplementedError(
@@ -137,6 +141,7 @@ class TexturedPhotogrammetryMesh:
         self.views_per_batch = int(max(1, min(views_per_batch, _lib.MAX_VIEWS_PER_CALL)))
         self.use_principal_point = bool(use_principal_point)
         self.sparse_host_gather = bool(sparse_host_gather)
+        self.pinned_direct_limit_bytes = 4 << 30
         self._context = None
         self._local_cache = None
 
@@ -697,6 +702,7 @@ class TexturedPhotogrammetryMesh:
             d_sum = d_count = None
             in_flight = []
             pending = None  # a batch of pageable images whose rows the host has yet to pick
+            pinned_seen = {}
             try:
                 for bi, s in enumerate(range(0, n, B)):
                     batch = cam_list[s : s + B]
@@ -716,9 +722,15 @@ class TexturedPhotogrammetryMesh:
                         elif kind != this_kind:
                             raise ValueError("all prediction images of a batch must share one dtype / layout")
                         preds.append(arr)
+                    kinds = [_lib.pointer_kind(a) for a in preds]
+                    for a, pk in zip(preds, kinds):  # footprint of the distinct page-locked images seen so far
+                        if pk == _lib.POINTER_PINNED and a.ctypes.data not in pinned_seen:
+                            pinned_seen[a.ctypes.data] = a.nbytes
+                    pinned_large = sum(pinned_seen.values()) > self.pinned_direct_limit_bytes
+                    host_gatherable = all(pk == _lib.POINTER_PAGEABLE or (pk == _lib.POINTER_PINNED and pinned_large)
+                                          for pk in kinds)
                     sparse = (not apply_distortion and self.sparse_host_gather and mode != _lib.MODE_PIXEL_SUM
-                              and len({a.dtype for a in preds}) == 1
-                              and not any(_lib.pointer_kind(a) != _lib.POINTER_PAGEABLE for a in preds))
+                              and len({a.dtype for a in preds}) == 1 and host_gatherable)
                     if sparse:
                         if in_flight:  # the fused calls queued so far use the library's own streams
                             ctx.sync()
