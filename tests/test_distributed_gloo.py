@@ -54,6 +54,16 @@ def _worker(rank, world, port, out):
         np.testing.assert_allclose(avg, agg["avg2"], rtol=1e-12, atol=0, equal_nan=True)
         amax = ora.find_argmax_nonzero_value(avg)
         np.testing.assert_array_equal(amax, agg["argmax2"][:, 0])
+        # sharded epilogue: a reduce-scatter hands every rank the totals of ITS slice of the faces (even and ragged
+        # splits); gloo has no reduce-scatter, so the same packing runs through an all-reduce here
+        for n_faces in (F, F - 1, 1):
+            s_sum, s_cnt = ggd.reduce_scatter_accumulators(torch.from_numpy(r_sum.numpy()[:n_faces].copy()),
+                                                           torch.from_numpy(r_count.numpy()[:n_faces].copy()))
+            lo, hi = ggd.face_slice(n_faces, rank, world)
+            assert s_sum.shape == (-(-n_faces // world), C) and s_cnt.dtype == torch.int32
+            np.testing.assert_array_equal(s_cnt.numpy()[: hi - lo], d_count.numpy()[lo:hi])
+            np.testing.assert_array_equal(s_sum.numpy()[: hi - lo], d_sum.numpy()[lo:hi])
+            assert not s_sum.numpy()[hi - lo :].any() and not s_cnt.numpy()[hi - lo :].any()
         # result wanted on one rank only: a reduce instead of an all-reduce; the destination holds the same totals
         ggd.allreduce_accumulators(r_sum, r_count, dst_rank=1)
         if rank == 1:

@@ -58,6 +58,18 @@ def _worker(rank, world, port, out):
             np.testing.assert_array_equal(info0["projection_counts"], a["counts2"])
         else:
             assert avg0 is None and info0 == {}
+        # sharded epilogue: reduce-scatter, every rank finishes its slice of the faces and copies it into the node's
+        # shared host block; rank 0 hands out views of that block (twice: the block is cached and reused)
+        for rep in range(2):
+            avg1, info1 = ggd.aggregate_projected_images_distributed(mesh, seg, dst_rank=0, shared_host=True,
+                                                                     return_argmax=True)
+            if rank == 0:
+                np.testing.assert_allclose(avg1, a["avg2"], rtol=1e-12, atol=0, equal_nan=True)
+                np.testing.assert_allclose(info1["summed_projections"], a["summed2"], rtol=1e-12, atol=0, equal_nan=True)
+                np.testing.assert_array_equal(info1["projection_counts"], a["counts2"])
+                np.testing.assert_array_equal(info1["argmax"], a["argmax2"][:, 0])
+            else:
+                assert avg1 is None and info1 == {}
         out[rank] = 1
     finally:
         dist.destroy_process_group()
