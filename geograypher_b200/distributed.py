@@ -145,8 +145,11 @@ class SharedHostResult:
         self.sums = buf[n : 2 * n].reshape(self.F, self.C)
         self.counts = buf[2 * n : 2 * n + self.F]
         self.argmax = buf[2 * n + self.F :]
-        if rank == dst_rank:
-            buf[:] = 0.0  # touch the pages before they are page-locked
+        # touch the pages before they are page-locked -- every rank ITS slice, so that (under the default first-touch
+        # policy) the pages a GPU writes sit on the NUMA node of the process that drives it
+        lo, hi = face_slice(self.F, rank, dist.get_world_size(group))
+        for a in (self.avg, self.sums, self.counts, self.argmax):
+            a[lo:hi] = 0.0
         dist.barrier(group=group)
         rc = torch.cuda.cudart().cudaHostRegister(buf.ctypes.data, self.n_bytes, 0)
         if int(rc) != 0:
