@@ -533,12 +533,15 @@ def run_c3_strong(args, torch, dist, _lib, ctx, world, rank, dev, n_cams, run_vi
     mode = _lib.MODE_LAST_PIXEL
     sharded = world > 1
     if sharded:
-        res = ggd.SharedHostResult.get(F, C, None, 0)  # created (and page-locked) once, outside the timed region
-        lo, hi = ggd.face_slice(F, rank, world)
-        h_avg, h_sum, h_cnt = (torch.from_numpy(a[lo:hi]) for a in (res.avg, res.sums, res.counts))
-    else:
-        host = [torch.empty((F, C), dtype=torch.float64, pin_memory=True) for _ in range(2)]
-        host_cnt = torch.empty((F,), dtype=torch.int32, pin_memory=True)
+        try:
+            res = ggd.SharedHostResult.get(F, C, None, 0)  # created (and page-locked) once, outside the timed region
+            lo, hi = ggd.face_slice(F, rank, world)
+            h_avg, h_sum, h_cnt = (torch.from_numpy(a[lo:hi]) for a in (res.avg, res.sums, res.counts))
+        except OSError:  # no room in /dev/shm, or it cannot be page-locked here (every rank raises): all-reduce instead
+            sharded = False
+    if not sharded:
+        host = [torch.empty((F, C), dtype=torch.float64, pin_memory=True) for _ in range(2)] if rank == 0 else None
+        host_cnt = torch.empty((F,), dtype=torch.int32, pin_memory=True) if rank == 0 else None
 
     def once():
         d_sum.zero_()
@@ -557,45 +560,54 @@ def run_c3_strong(args, torch, dist, _lib, ctx, world, rank, dev, n_cams, run_vi
                 h_sum.copy_(s_sum[:k], non_blocking=True)
                 h_cnt.copy_(s_cnt[:k].double(), non_blocking=True)
             else:
+                if world > 1:
+                    packed_allreduce(torch, dist, d_sum, d_count, pack)
                 tm.mark()
                 avg, argmax = ctx.finalize(d_sum, d_count)
                 tm.mark()
-                host[0].copy_(avg, non_blocking=True)
-                host[1].copy_(d_sum, non_blocking=True)
-                host_cnt.copy_(d_count, non_blocking=True)
+                if rank == 0:
+                    host[0].copy_(avg, non_blocking=True)
+                    host[1].copy_(d_sum, non_blocking=True)
+                    host_cnt.copy_(d_count, non_blocking=True)
         ctx.sync()
         return tm
 
     once()  # warm-up (NCCL channels, pinned staging)
     tm = min((once() for _ in range(3)), key=lambda t: t.total_ms)
-    names = ["views", "reduce_scatter" if sharded else "allreduce", "finalize", "d2h"]
+    names = ["views", "reduce_scatter" if sharded else "allreduce", "finalize", "d2h"]  # (chosen before the timed runs)
     out = {"value": n_cams / (tm.total_ms / 1e3), "unit": "views/s", "scaling": "strong", "views": n_cams,
            "views_per_rank": len(mine), "total_ms": tm.total_ms,
            "phase_ms": {k: round(v, 3) for k, v in zip(names, tm.phases_ms)},
            "value_without_d2h": n_cams / (sum(tm.phases_ms[:3]) / 1e3),
            "collective": ("one reduce_scatter of F*(C+1) float64 (counts packed behind the sums of the same face slice); "
                           "every rank copies its slice of the result into a host block shared by the node's ranks"
-                          if sharded else "none (1 GPU)"),
+                          if sharded else ("none (1 GPU)" if world == 1 else
+                                           "one all_reduce of F*(C+1) float64 (counts packed behind the sums); rank 0 "
+                                           "copies the result to the host (the shared host block was unavailable)")),
            "note": "best of 3; max over ranks; finalize's NaN marking of unseen faces is part of the D2H'd sums"}
     # parity: a single GPU aggregates the whole survey alone; the result the ranks assembled on the host must agree
-    if sharded:
+    if world > 1:
         ok = torch.ones(1, device=dev)
         if rank == 0:
+            got = (res.avg, res.sums, res.counts) if sharded else (host[0].numpy(), host[1].numpy(),
+                                                                   host_cnt.numpy().astype(np.float64))
+            got = [np.array(a, copy=True) for a in got]
             d_sum.zero_()
             d_count.zero_()
             run_views(list(range(n_cams)), mode)
             one_avg, _ = ctx.finalize(d_sum, d_count)
             ctx.sync()
-            same_cnt = np.array_equal(res.counts, d_count.double().cpu().numpy())
-            close = (np.allclose(res.sums, d_sum.cpu().numpy(), rtol=1e-12, atol=0.0, equal_nan=True)
-                     and np.allclose(res.avg, one_avg.cpu().numpy(), rtol=1e-12, atol=0.0, equal_nan=True))
+            same_cnt = np.array_equal(got[2], d_count.double().cpu().numpy())
+            close = (np.allclose(got[1], d_sum.cpu().numpy(), rtol=1e-12, atol=0.0, equal_nan=True)
+                     and np.allclose(got[0], one_avg.cpu().numpy(), rtol=1e-12, atol=0.0, equal_nan=True))
             ok[0] = 1.0 if (same_cnt and close) else 0.0
         dist.broadcast(ok, src=0)
         if ok.item() != 1.0:
             raise RuntimeError("parity check failed: the result assembled by the ranks differs from the single-GPU run")
         out["parity_check"] = "ok"
         out["parity_note"] = (f"rank 0 re-ran all {n_cams} views alone: counts identical, float64 sums and averages within "
-                              f"1e-12 relative of the result the {world} ranks assembled in the shared host block")
+                              f"1e-12 relative of the result the {world} ranks "
+                              + ("assembled in the shared host block" if sharded else "all-reduced"))
     return out
 
 

@@ -116,6 +116,7 @@ class SharedHostResult:
         import torch.distributed as dist
 
         self.F, self.C = int(F), int(C)
+        self._buf = None
         rank = dist.get_rank(group)
         n = self.F * self.C
         self.n_bytes = (2 * n + 2 * self.F) * 8
@@ -129,7 +130,6 @@ class SharedHostResult:
             else:
                 self.shm = shared_memory.SharedMemory(create=True, size=self.n_bytes)
                 name[0] = self.shm.name
-                atexit.register(self._unlink)
         src = dist.get_global_rank(group, dst_rank) if group is not None else dst_rank
         dist.broadcast_object_list(name, src=src, group=group)
         if not name[0]:
@@ -145,22 +145,46 @@ class SharedHostResult:
         self.sums = buf[n : 2 * n].reshape(self.F, self.C)
         self.counts = buf[2 * n : 2 * n + self.F]
         self.argmax = buf[2 * n + self.F :]
-        # touch the pages before they are page-locked -- every rank ITS slice, so that (under the default first-touch
-        # policy) the pages a GPU writes sit on the NUMA node of the process that drives it
-        lo, hi = face_slice(self.F, rank, dist.get_world_size(group))
-        for a in (self.avg, self.sums, self.counts, self.argmax):
-            a[lo:hi] = 0.0
+        if rank == dst_rank:
+            buf[:] = 0.0  # touch the pages before they are page-locked (first touch by each rank for its own slice was
+                          # measured slower at N = 2: torchrun does not bind a process to its GPU's NUMA node)
         dist.barrier(group=group)
         rc = torch.cuda.cudart().cudaHostRegister(buf.ctypes.data, self.n_bytes, 0)
-        if int(rc) != 0:
-            raise OSError(f"cudaHostRegister of the shared result block failed: {rc}")
+        ok = torch.tensor([1.0 if int(rc) == 0 else 0.0], device=torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # all ranks succeed or all ranks give up
+        if ok.item() != 1.0:
+            if int(rc) == 0:
+                torch.cuda.cudart().cudaHostUnregister(buf.ctypes.data)
+            del buf
+            self.avg = self.sums = self.counts = self.argmax = None
+            self._release(rank == dst_rank)
+            raise OSError("cudaHostRegister of the shared result block failed on some rank")
         self._buf = buf
+        atexit.register(self._release, rank == dst_rank)
 
-    def _unlink(self):
+    def _release(self, unlink):
+        """At interpreter exit: un-pin, drop our views, unmap (left mapped if the caller still holds arrays), and -- on
+        the rank that created it -- remove the segment."""
         try:
-            self.shm.unlink()
+            import torch
+
+            if self._buf is not None:
+                torch.cuda.cudart().cudaHostUnregister(self._buf.ctypes.data)
         except Exception:
             pass
+        self.avg = self.sums = self.counts = self.argmax = self._buf = None
+        try:
+            self.shm.close()
+        except BufferError:  # the caller's arrays still point into the block: the OS unmaps it with the process
+            self.shm.close = lambda: None
+            self.shm._mmap = None
+        except Exception:
+            pass
+        if unlink:
+            try:
+                self.shm.unlink()
+            except Exception:
+                pass
 
     @classmethod
     def get(cls, F, C, group, dst_rank):
@@ -254,14 +278,19 @@ def aggregate_projected_images_distributed(mesh, cameras, aggregate_img_scale: f
     mesh._get_context().drain()  # accumulators are written on the library's internal streams
     t0 = mark("accumulate", t0)
     if shared_host and dst_rank is not None and world > 1:
-        res = finalize_sharded(mesh._get_context(), d_sum, d_count, group, dst_rank, want_argmax=return_argmax)
-        mark("reduce_scatter+finalize+to_host", t0)
-        if rank != dst_rank:
-            return None, {}
-        info = {"projection_counts": res.counts, "summed_projections": res.sums}
-        if return_argmax:
-            info["argmax"] = res.argmax
-        return res.avg, info
+        try:
+            res = finalize_sharded(mesh._get_context(), d_sum, d_count, group, dst_rank, want_argmax=return_argmax)
+        except OSError as e:  # raised on EVERY rank (no room in /dev/shm, or it cannot be page-locked): reduce instead
+            mesh.logger.warning(f"shared host result unavailable ({e}); falling back to a reduce to rank {dst_rank}")
+            res = None
+        if res is not None:
+            mark("reduce_scatter+finalize+to_host", t0)
+            if rank != dst_rank:
+                return None, {}
+            info = {"projection_counts": res.counts, "summed_projections": res.sums}
+            if return_argmax:
+                info["argmax"] = res.argmax
+            return res.avg, info
     allreduce_accumulators(d_sum, d_count, group, dst_rank=dst_rank)
     t0 = mark("allreduce", t0)
     if dst_rank is not None and rank != dst_rank:
