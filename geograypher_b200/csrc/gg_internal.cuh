@@ -23,6 +23,9 @@
 #define GG_RASTER_WARPS 4      // independent warps (tiles) per CTA
 #endif
 #define GG_RASTER_THREADS (32 * GG_RASTER_WARPS)
+#ifndef GG_TILES_PER_WARP
+#define GG_TILES_PER_WARP 2    // consecutive tiles of a row per warp (not in the dense mode); see k_raster_tiles
+#endif
 #ifndef GG_RASTER_MIN_BLOCKS
 #define GG_RASTER_MIN_BLOCKS (32 / GG_RASTER_WARPS)  // 64 registers per thread: 32 warps per SM
 #endif

@@ -746,24 +746,69 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
     constexpr bool WINNERS = (MODE == GG_RM_WINNERS || MODE == GG_RM_WINNERS_ONLY);
     constexpr bool RASTER_OUT = (MODE != GG_RM_WINNERS_ONLY);  // pix2face / depth may be requested
     constexpr bool NEED_POS = (MODE == GG_RM_DENSE);  // only the dense epilogue indexes by list position
-    // grid: (groups of GG_RASTER_WARPS tiles along x, tile rows, views); one warp per tile
+    // grid: (groups of GG_RASTER_WARPS * TPW tiles along x, tile rows, views); a warp rasterizes TPW consecutive
+    // tiles of a row, one after the other.  TPW > 1: the list bounds of all its tiles come back in ONE memory round
+    // trip (lane j loads tile j's), and the setups of tile j+1 travel into the second shared-memory buffer (cp.async)
+    // while tile j is rasterized, so that only a warp's first tile waits for memory.
+    constexpr int TPW = (MODE == GG_RM_DENSE) ? 1 : GG_TILES_PER_WARP;
     const int view = blockIdx.z;
     const gg_camera &c = cams.cam[view];
     const GGViewScratch &vs = views.v[view];
     const int W = c.W, H = c.H;
     const int tiles_x = (W + GG_TILE_W - 1) / GG_TILE_W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_x = blockIdx.x * GG_RASTER_WARPS + warp;
-    if (tile_x >= tiles_x) return;  // whole warp leaves; no block-level barriers below
-    const int tile = blockIdx.y * tiles_x + tile_x;
-    const int tile_x0 = tile_x * GG_TILE_W, tile_y0 = blockIdx.y * GG_TILE_H;
+    const int tile_xb = (blockIdx.x * GG_RASTER_WARPS + warp) * TPW;
+    if (tile_xb >= tiles_x) return;  // whole warp leaves; no block-level barriers below
+    const int tile_y0 = blockIdx.y * GG_TILE_H;
 
-    __shared__ GGTileFace s_all[GG_RASTER_WARPS][GG_CHUNK];
-    GGTileFace *s_faces = s_all[warp];
+    __shared__ GGTileFace s_all[GG_RASTER_WARPS][TPW > 1 ? 2 : 1][GG_CHUNK];
+    const unsigned s_base = (unsigned)__cvta_generic_to_shared(&s_all[warp][0][0]);
 
     const int tx0 = (lane & 3) * 8;  // this lane: pixels tx0..tx0+7 of row ty
     const int ty = lane >> 2;
-    const unsigned s_faces_addr = (unsigned)__cvta_generic_to_shared(s_faces);
+    const float fty = (float)ty, ftx0 = (float)tx0;
+
+    const bool overflow = vs.counters[3] != 0;
+    int my_beg = 0, my_end = 0;  // lane j < TPW: bounds of the warp's j-th tile (the fill cursor ends at the list's end)
+    if (lane < TPW && tile_xb + lane < tiles_x) {
+        const int t = blockIdx.y * tiles_x + tile_xb + lane;
+        my_beg = vs.tile_offset[t];
+        // loaded unconditionally, beside the overflow flag (the compiler would predicate it on the flag and chain two
+        // memory round trips)
+        asm volatile("ld.global.s32 %0, [%1];" : "=r"(my_end) : "l"(vs.tile_count + t));
+    }
+    if (overflow) my_end = my_beg;
+    auto stage_async = [&](int buf, int beg, int n) {  // n <= GG_CHUNK setups -> buffer buf, one commit group
+        const char *src = reinterpret_cast<const char *>(vs.bins + beg);
+        const unsigned dst = s_base + (unsigned)buf * (unsigned)(GG_CHUNK * sizeof(GGTileFace));
+        for (int idx = lane; idx < n * 4; idx += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + idx * 16), "l"(src + idx * 16) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (TPW > 1) {
+        const int b0 = __shfl_sync(0xffffffffu, my_beg, 0), e0 = __shfl_sync(0xffffffffu, my_end, 0);
+        stage_async(0, b0, min(GG_CHUNK, e0 - b0));
+    }
+
+#pragma unroll 1
+  for (int j = 0; j < TPW; ++j) {
+    const int tile_x = tile_xb + j;
+    if (tile_x >= tiles_x) break;
+    const int tile_x0 = tile_x * GG_TILE_W;
+    const int beg = __shfl_sync(0xffffffffu, my_beg, j);
+    const int len = __shfl_sync(0xffffffffu, my_end, j) - beg;
+    const unsigned s_faces_addr = s_base + (TPW > 1 ? (unsigned)(j & 1) * (unsigned)(GG_CHUNK * sizeof(GGTileFace)) : 0u);
+    GGTileFace *s_faces = &s_all[warp][TPW > 1 ? (j & 1) : 0][0];
+    if (TPW > 1) {
+        if (j + 1 < TPW && tile_x + 1 < tiles_x) {  // next tile's setups into the other buffer, then wait for this tile's
+            const int nb = __shfl_sync(0xffffffffu, my_beg, j + 1), ne = __shfl_sync(0xffffffffu, my_end, j + 1);
+            stage_async((j + 1) & 1, nb, min(GG_CHUNK, ne - nb));
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+    }
 
     // Per pixel: the winner's key (bits of its 1/z, which is positive -> ordered like the float; then ~face so that the
     // lower ID wins a tie) compared as ONE 64-bit quantity, and its position in the tile's list (-1 = none).
@@ -777,14 +822,6 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
         key[i] = 0.0;  // 1/z = 0, ~face = 0 (face -1)
         bp[i] = -1;
     }
-    const float fty = (float)ty, ftx0 = (float)tx0;
-
-    const bool overflow = vs.counters[3] != 0;
-    const int beg = vs.tile_offset[tile];
-    int end;  // the fill cursor ends at the end of the list; loaded unconditionally, beside the overflow flag (the
-              // compiler would predicate it on the flag and chain two memory round trips)
-    asm volatile("ld.global.s32 %0, [%1];" : "=r"(end) : "l"(vs.tile_count + tile));
-    const int len = overflow ? 0 : end - beg;
 
     if (MODE == GG_RM_DENSE) {
         // The epilogue will stream this tile's scores: ask for them now (one bulk L2 prefetch per tile row, issued by
@@ -799,8 +836,10 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
 
     for (int base = 0; base < len; base += GG_CHUNK) {
         const int n = min(GG_CHUNK, len - base);
-        {  // stream n ready-made 64-byte setups into shared memory, 16 B per lane and pass: the usual list of <= 8
+        if (TPW == 1 || base > 0) {  // (TPW > 1: the first chunk was prefetched)
+           // stream n ready-made 64-byte setups into shared memory, 16 B per lane and pass: the usual list of <= 8
            // faces takes ONE pass (a four-way unrolled, predicated copy cost ~90 instructions per tile)
+            if (TPW > 1) __syncwarp();  // every lane is done with the previous chunk in this buffer
             const int4 *src = reinterpret_cast<const int4 *>(vs.bins + beg + base);
 #pragma unroll 1
             for (int idx = lane; idx < n * 4; idx += 64) {
@@ -1201,6 +1240,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
             }
         }
     }
+  }  // the warp's next tile
 }
 
 }  // namespace
@@ -1365,7 +1405,9 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
         GG_CUDA(cudaStreamWaitEvent(st_ras, ctx->ev_bin[ctx->cur], 0));
     }
     st = st_ras;
-    const dim3 rgrid((tiles_x + GG_RASTER_WARPS - 1) / GG_RASTER_WARPS, tiles_y, n);
+    const dim3 rgrid((tiles_x + GG_RASTER_WARPS - 1) / GG_RASTER_WARPS, tiles_y, n);  // dense mode: one tile per warp
+    const int per_cta = GG_RASTER_WARPS * GG_TILES_PER_WARP;
+    const dim3 rgrid_t((tiles_x + per_cta - 1) / per_cta, tiles_y, n);
     GGDenseArgs da;
     memset(&da, 0, sizeof(da));
     if (h_pred) {  // fused dense per-pixel sums
@@ -1397,15 +1439,15 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
         da.D = D;
         switch (out_dtype) {
             case GG_OUT_F64:
-                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, double, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
+                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, double, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(
                                                      cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da)));
                 break;
             case GG_OUT_F32:
-                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
+                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, float, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(
                                                      cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da)));
                 break;
             case GG_OUT_U8:
-                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, uint8_t, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
+                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, uint8_t, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(
                                                      cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da)));
                 break;
             default: gg_set_error("bad out_dtype"); return GG_ERR_INVALID;
@@ -1414,15 +1456,15 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
     }
     if (want_winners && !d_pix2face && !d_depth)  // the fused aggregation: no raster leaves the SM
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  (k_raster_tiles<GG_RM_WINNERS_ONLY, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
+                  (k_raster_tiles<GG_RM_WINNERS_ONLY, float, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(
                       cb, ctx->vset[ctx->cur], n_tiles, nullptr, nullptr, compat_bg ? (int)ctx->F : 0, da)));
     else if (want_winners)
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  (k_raster_tiles<GG_RM_WINNERS, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(
+                  (k_raster_tiles<GG_RM_WINNERS, float, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(
                       cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, d_depth, compat_bg ? (int)ctx->F : 0, da)));
     else
         GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  (k_raster_tiles<GG_RM_PLAIN, float, 0><<<rgrid, GG_RASTER_THREADS, 0, st>>>(cb, ctx->vset[ctx->cur], n_tiles,
+                  (k_raster_tiles<GG_RM_PLAIN, float, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(cb, ctx->vset[ctx->cur], n_tiles,
                                                                                           d_pix2face, d_depth, 0, da)));
     return GG_OK;
 }
