@@ -20,11 +20,15 @@
 #define GG_TILE_W 32           // one warp rasterizes one 32 x 8 px tile; lane = 8 consecutive px of one row
 #define GG_TILE_H 8
 #ifndef GG_RASTER_WARPS
-#define GG_RASTER_WARPS 4      // independent warps (tiles) per CTA
+#define GG_RASTER_WARPS 1      // independent warps per CTA (measured: 1 warp x 4 tiles beats 4 warps x 2 tiles by 3 %:
+                               // a CTA's slot is not held by its slowest warp)
 #endif
 #define GG_RASTER_THREADS (32 * GG_RASTER_WARPS)
+#ifndef GG_DENSE_TILES_PER_WARP
+#define GG_DENSE_TILES_PER_WARP 1  // the same for the dense (pixel_sum) mode
+#endif
 #ifndef GG_TILES_PER_WARP
-#define GG_TILES_PER_WARP 2    // consecutive tiles of a row per warp (not in the dense mode); see k_raster_tiles
+#define GG_TILES_PER_WARP 4    // consecutive tiles of a row per warp (not in the dense mode); see k_raster_tiles
 #endif
 #ifndef GG_RASTER_MIN_BLOCKS
 #define GG_RASTER_MIN_BLOCKS (32 / GG_RASTER_WARPS)  // 64 registers per thread: 32 warps per SM

@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
     // tiles of a row, one after the other.  TPW > 1: the list bounds of all its tiles come back in ONE memory round
     // trip (lane j loads tile j's), and the setups of tile j+1 travel into the second shared-memory buffer (cp.async)
     // while tile j is rasterized, so that only a warp's first tile waits for memory.
-    constexpr int TPW = (MODE == GG_RM_DENSE) ? 1 : GG_TILES_PER_WARP;
+    constexpr int TPW = (MODE == GG_RM_DENSE) ? GG_DENSE_TILES_PER_WARP : GG_TILES_PER_WARP;
     const int view = blockIdx.z;
     const gg_camera &c = cams.cam[view];
     const GGViewScratch &vs = views.v[view];
@@ -1405,7 +1405,8 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
         GG_CUDA(cudaStreamWaitEvent(st_ras, ctx->ev_bin[ctx->cur], 0));
     }
     st = st_ras;
-    const dim3 rgrid((tiles_x + GG_RASTER_WARPS - 1) / GG_RASTER_WARPS, tiles_y, n);  // dense mode: one tile per warp
+    const int per_cta_d = GG_RASTER_WARPS * GG_DENSE_TILES_PER_WARP;
+    const dim3 rgrid((tiles_x + per_cta_d - 1) / per_cta_d, tiles_y, n);  // dense mode
     const int per_cta = GG_RASTER_WARPS * GG_TILES_PER_WARP;
     const dim3 rgrid_t((tiles_x + per_cta - 1) / per_cta, tiles_y, n);
     GGDenseArgs da;
