@@ -13,8 +13,9 @@
 //                   128-byte record (edge equations, float64 1/z plane, tile mask), count the tiles it touches
 //   k_reserve_tiles warp-scan of the tile counts + one atomicAdd per warp reserves each tile's list (no global scan)
 //   k_fill_bins     one 64-byte tile-relative setup per (tile, face) pair, 8 lanes per record
-//   k_raster_tiles  one WARP per 32x8-pixel tile: streams the tile's setups through shared memory, every lane owns 8
-//                   consecutive pixels of one row and keeps (1/z, face, list position) in registers; exact integer
+//   k_raster_tiles  a warp rasterizes 32x8-pixel tiles (four consecutive ones, the next tile's setups prefetched into
+//                   shared memory while the current one is worked on): every lane owns 8 consecutive pixels of one
+//                   row and keeps (1/z, face) -- the dense mode also the list position -- in registers; exact integer
 //                   edge functions with top-left rule (C3), nearest 1/z wins, ties -> lowest face ID (C4).  Epilogues
 //                   by mode: face-ID / depth rasters, last pixel per face (fused last-pixel / vote aggregation),
 //                   dense per-pixel score sums, fused render_flat gather.
@@ -662,7 +663,7 @@ __global__ void __launch_bounds__(256, GG_FILL_MIN_BLOCKS) k_fill_bins(int64_t c
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Tile rasterizer: one WARP per 32 x 8 px tile, no block-level synchronisation.
+// Tile rasterizer: a WARP per 32 x 8 px tile at a time, no block-level synchronisation.
 // ------------------------------------------------------------------------------------------------------
 // Exact evaluation of one face at one pixel (slow path: long edges or steep depth planes).
 __device__ __noinline__ bool exact_cover(const GGFaceRec &r, int j, int i, float &w) {
