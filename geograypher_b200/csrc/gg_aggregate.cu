@@ -9,6 +9,7 @@
 //   meshes/meshes.py:1921-1937   render_flat gather;  :2323-2334 uint8 cast rule
 //   utils/indexing.py:9-32       find_argmax_nonzero_value
 //   predictors/segmentor.py:59-69  inds_to_one_hot (GG_PRED_INDEX_U8 expands it on the fly)
+#include <algorithm>
 #include "gg_internal.cuh"
 
 namespace {
@@ -457,9 +458,18 @@ static int stage_host_rows(gg_context *ctx, int n, GGPredBatch &pb, int E, int f
                                                                                     row_pix, rows_per_view, row_count));
     // floor(i / E) == umulhi(i, ceil(2^32 / E)) for i * E < 2^32 -- far beyond the 2^27 elements checked above
     const unsigned magic = E > 1 ? (unsigned)((0x100000000ULL + (unsigned)E - 1) / (unsigned)E) : 0u;
+    // Grid of the fetch: what matters is how many PCIe read requests are in flight.  Every thread has one load
+    // outstanding and a row of E elements is ceil(E * sizeof(T) / 32) sectors, so the grid is sized for
+    // ctx->stage_inflight sectors (2 560): measured on the benchmark host, 500 c2 views end to end take 66 ms at that
+    // depth against 81 ms with 2 CTAs per SM (~15 k sectors in flight) and 106 ms with 8 -- requests beyond what the
+    // link can hold queue up in front of it and slow it down (profiles/r02_e2e_stage_grid.txt).
+    const int sectors_per_row = (int)((E * sizeof(T) + 31) / 32);
+    const int64_t threads = (int64_t)ctx->stage_inflight / sectors_per_row * E;
+    int grid = (int)std::min<int64_t>(std::max<int64_t>((threads + 255) / 256, 4), (int64_t)ctx->sm_count * 2);
+    if (ctx->stage_ctas > 0) grid = ctx->sm_count * ctx->stage_ctas;
+    if (ctx->stage_grid > 0) grid = ctx->stage_grid;
     GG_LAUNCH(ctx, GG_ST_STAGE, st,
-              k_fetch_rows<T><<<(unsigned)(ctx->sm_count * ctx->stage_ctas), 256, 0, st>>>(n, pb, E, magic, row_pix,
-                                                                                        rows_per_view, row_count, stage));
+              k_fetch_rows<T><<<(unsigned)grid, 256, 0, st>>>(n, pb, E, magic, row_pix, rows_per_view, row_count, stage));
     for (int i = 0; i < n; ++i) pb.p[i] = stage + (int64_t)i * rows_per_view * E;
     return GG_OK;
 }

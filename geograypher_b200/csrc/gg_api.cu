@@ -379,7 +379,9 @@ int gg_create(int device, gg_context **out) {
     if (const char *e = getenv("GG_STAGE_HOST_ROWS")) ctx->stage_host_rows = atoi(e) != 0;
     if (const char *e = getenv("GG_SETUP_CTAS")) ctx->setup_ctas = atoi(e);
     if (const char *e = getenv("GG_FILL_CTAS")) ctx->fill_ctas = atoi(e);
-    if (const char *e = getenv("GG_STAGE_CTAS")) ctx->stage_ctas = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("GG_STAGE_INFLIGHT")) ctx->stage_inflight = atoi(e) > 0 ? atoi(e) : ctx->stage_inflight;
+    if (const char *e = getenv("GG_STAGE_GRID")) ctx->stage_grid = atoi(e);
+    if (const char *e = getenv("GG_STAGE_CTAS")) ctx->stage_ctas = atoi(e) > 0 ? atoi(e) : 0;
     GG_CUDA(cudaMalloc(&ctx->d_sticky, 4 * sizeof(int32_t)));
     GG_CUDA(cudaMemset(ctx->d_sticky, 0, 4 * sizeof(int32_t)));
     // the short, latency-bound binning kernels get the higher priority so that they slip in between the CTAs of the

@@ -153,7 +153,9 @@ struct gg_context {
     char *d_stage = nullptr;      // rows fetched from prediction images that live in host memory
     size_t stage_bytes = 0;
     int stage_host_rows = 1;      // GG_STAGE_HOST_ROWS=0: resolve reads the host images directly
-    int stage_ctas = 2;           // CTAs per SM of the host-row fetch kernel (GG_STAGE_CTAS)
+    int stage_inflight = 2560;    // PCIe read requests (32-byte sectors) the host-row fetch keeps in flight (GG_STAGE_INFLIGHT)
+    int stage_grid = 0;           // > 0: absolute grid size of the host-row fetch kernel (GG_STAGE_GRID, experiments)
+    int stage_ctas = 0;           // CTAs per SM of the host-row fetch kernel (GG_STAGE_CTAS)
     int32_t *d_raster = nullptr;  // internal n x H x W raster when the caller does not want pix2face back
     int64_t raster_cap = 0;
     int32_t *d_sticky = nullptr;  // [4] since the last gg_sync: OR of the batches' overflow flags, most face records any
