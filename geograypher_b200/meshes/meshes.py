@@ -141,7 +141,7 @@ class TexturedPhotogrammetryMesh:
         self.views_per_batch = int(max(1, min(views_per_batch, _lib.MAX_VIEWS_PER_CALL)))
         self.use_principal_point = bool(use_principal_point)
         self.sparse_host_gather = bool(sparse_host_gather)
-        self.pinned_direct_limit_bytes = 4 << 30
+        self.pinned_direct_limit_bytes = int(os.environ.get("GG_PINNED_DIRECT_LIMIT", 4 << 30))
         self._context = None
         self._local_cache = None
 

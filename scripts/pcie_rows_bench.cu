@@ -78,7 +78,7 @@ int main(int argc, char **argv) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     printf("pinned buffer: %.2f GB (%d x 19.96 Mpx x 64 B)\n", P * 64 / 1e9, n_img);
     for (int row_bytes : {1, 40}) {
-        for (int blocks : {148, 148 * 4, 148 * 16}) {
+        for (int blocks : {6, 12, 24, 48, 96, 148, 148 * 4, 148 * 16}) {
             for (int rep = 0; rep < 2; ++rep) {
                 CK(cudaEventRecord(e0));
                 for (int it = 0; it < 5; ++it) k_rows<<<blocks, 256>>>(h, d_pix, n, row_bytes, d_dst);
