@@ -801,7 +801,7 @@ def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, hos
         "pinned_f32": "the same images in page-locked (cudaHostAlloc) memory, 6.4 GB of them: on this host the "
                       "scattered-read rate from page-locked memory falls with the pinned footprint "
                       "(profiles/r02_pcie_rows_footprint.txt: 284 -> 100 M 40-byte rows/s from 1.3 to 10 GB; read in "
-                      "place this leg measured ~2 600 views/s), so above 4 GiB of distinct page-locked images the API "
+                      "place this leg measured ~3 400 views/s), so above 4 GiB of distinct page-locked images the API "
                       "takes the host-gather route of the pageable leg instead "
                       "(TexturedPhotogrammetryMesh.pinned_direct_limit_bytes)",
         "pinned_index_u8": "(H,W) uint8 class-index images in pinned host memory (what LookUpSegmentor yields before "
