@@ -646,6 +646,12 @@ def run_c4(args, torch, dist, _lib, syn, ctx, world, rank, dev, verts, faces, al
     bytes_per_view = 1.0 * P + 12.0 * (f_v / 2.0) + 12.0 * f_v  # B4 fused: uint8 out, no ID raster
     achieved = bytes_per_view * B / (avg_ms * 1e-3) / 1e9
     labelled = float((out > 0).float().mean().item())
+    inst = committed_number("inst_counts.json", f"c4:render_flat:{B}")
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    issue_peak = sm_count * 4 * 1965.0 * 1e6 / 1e9  # G warp-instructions / s at the B200's 1965 MHz
+    issue = ({"bound": "issue", "achieved": inst / (avg_ms * 1e-3) / 1e9, "peak": issue_peak, "unit": "Gwarp-inst/s",
+              "frac": inst / (avg_ms * 1e-3) / 1e9 / issue_peak, "warp_instructions_per_launch": inst,
+              "peak_source": f"{sm_count} SMs x 4 schedulers x 1965 MHz"} if inst and avg_ms > 0 else None)
     return {"value": views / (tm.total_ms / 1e3), "unit": "views/s", "mpix_per_s": views / (tm.total_ms / 1e3) * P / 1e6,
             "views": views, "total_ms": tm.total_ms, "scaling": "weak (replicas only)",
             "workload": f"c4: render_flat of per-face labels (200 Voronoi polygons, 10 classes, 20% unlabelled) to "
@@ -653,8 +659,10 @@ def run_c4(args, torch, dist, _lib, syn, ctx, world, rank, dev, verts, faces, al
             "roofline": {"bound": "hbm", "kernel": "k_raster_tiles<GATHER>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": committed_number("traffic.json", f"c4:render_flat:{B}"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_view * B, "avg_launch_ms": avg_ms,
-                         "note": "the rasterizer phase of the kernel is issue bound; the uint8 raster is its only sizeable "
-                                 "HBM traffic"},
+                         "issue": issue,
+                         "note": "the kernel is issue bound like the aggregation's rasterizer (see `issue`: instruction "
+                                 "count from the committed ncu capture, time measured live); the uint8 raster is its "
+                                 "only sizeable HBM traffic"},
             "stage_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1] > 0}, "labelled_pixel_fraction": labelled}
 
 
