@@ -451,6 +451,16 @@ def run_ours(args):
                                 "of the neighbouring batches sharing the SMs (0.70 under ncu, kernel alone); the "
                                 "numerator is the kernel's own instruction count, so a leaner kernel lowers this "
                                 "fraction while raising views/s"}
+            # all kernels of the step together: what the software pipeline as a whole makes of the issue slots
+            step_inst = committed_number("inst_counts.json", key + ":step")
+            if step_inst and elapsed_s > 0:
+                step_rate = step_inst * args.steps * n_batches / elapsed_s / 1e9
+                roofline["step_issue"] = {
+                    "bound": "issue", "kernels": "reset, cull, setup, reserve, fill, k_raster_tiles, winner reset, resolve",
+                    "achieved": step_rate, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": step_rate / issue_peak,
+                    "warp_instructions_per_batch": step_inst,
+                    "note": "committed ncu instruction counts of every kernel of a batch (profiles/inst_counts.json, "
+                            "key ...:step) x batches per rank / the timed region (all-reduce and epilogue included)"}
         return {"value": views / elapsed_s, "elapsed_s": elapsed_s, "roofline": roofline, "clocks": clocks,
                 "stage_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1] > 0},
                 "launches": int(sum(v[1] for v in prof.values())), "faces_per_view": f_v,

@@ -45,7 +45,9 @@ def main(src, dst, command):
                      f"time_ns={t:12.0f} -> {i / t:7.2f} Gwarp-inst/s, {(rd + wr) / t:7.1f} GB/s (serialised, cold cache)")
     note = ("smsp__inst_executed.sum per launch of k_raster_tiles (10 views), mean over the survey's 50 launches in one ncu pass of: "
             + command + ". Key = config:mode:views_per_launch.")
-    (ROOT / "profiles" / "inst_counts.json").write_text(json.dumps({"_comment": note, **inst}, indent=1) + "\n")
+    old_inst = json.loads((ROOT / "profiles" / "inst_counts.json").read_text())  # keeps the ...:step keys (ncu_step_counts.py)
+    old_inst.update({"_comment": note, **inst})
+    (ROOT / "profiles" / "inst_counts.json").write_text(json.dumps(old_inst, indent=1) + "\n")
     old = json.loads((ROOT / "profiles" / "traffic.json").read_text())
     old["_comment"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch of k_raster_tiles, mean over the survey's 50 launches in one "
                        "ncu pass of: " + command + ". Key = config:mode:views_per_launch.")
