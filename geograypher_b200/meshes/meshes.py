@@ -473,7 +473,11 @@ class TexturedPhotogrammetryMesh:
 
         Generator of (h, w, d) float64 arrays, NaN where no face is hit, optionally paired with the camera.
         Unlike the reference, trailing cameras are not dropped when ``len(cameras) % batch_size != 0``.
+        The device-to-host copy of a batch runs on a copy stream while the next batch is rendered.  Extension
+        (keyword ``out_dtype``, undistorted renders only): "float32", or "uint8" with ``save_renders``' cast rule
+        (meshes.py:2323-2334) applied on the GPU -- label renders then cross PCIe at one byte per pixel.
         """
+        out_dtype = pix2face_kwargs.pop("out_dtype", "float64")
         if isinstance(cameras, PhotogrammetryCamera):
             cameras = PhotogrammetryCameraSet([cameras])
         elif not self._is_camera_or_set(cameras) or not hasattr(cameras, "cameras"):
@@ -485,8 +489,7 @@ class TexturedPhotogrammetryMesh:
         cam_list = self._camera_list(cameras)
         if not apply_distortion:
             k = 0
-            for batch in self.render_flat_device(cameras, batch_size, render_img_scale):
-                host = batch.cpu().numpy()
+            for host in self._to_host_owned(self.render_flat_device(cameras, batch_size, render_img_scale, out_dtype)):
                 for img in host:
                     yield (img, cam_list[k]) if return_camera else img
                     k += 1
@@ -873,6 +876,38 @@ class TexturedPhotogrammetryMesh:
         if pending is not None:
             events[pending].synchronize()
             yield slots[pending].numpy(), free[pending].release
+
+    def _to_host_owned(self, device_batches):
+        """Device batches -> host arrays that the CONSUMER owns (``render_flat``'s contract: it may keep every image).
+        Each batch gets its own page-locked block from torch's caching host allocator, filled on a copy stream while
+        the next batch is rendered; a consumer that drops an image before asking for the next -- the usual loop --
+        keeps re-using the same two or three blocks, one that keeps them pays the page-locking of each."""
+        import torch
+
+        copy_stream = self.__dict__.get("_copy_stream")
+        if copy_stream is None:
+            copy_stream = self.__dict__["_copy_stream"] = torch.cuda.Stream(device=self.device)
+        pending = None  # (page-locked tensor, event of its copy)
+        for batch in device_batches:
+            host = torch.empty(batch.shape, dtype=batch.dtype, pin_memory=True)
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):
+                host.copy_(batch, non_blocking=True)
+                event = torch.cuda.Event()
+                event.record(copy_stream)
+            batch.record_stream(copy_stream)
+            del batch
+            if pending is not None:
+                pending[1].synchronize()
+                done, pending = pending[0], (host, event)
+                yield done.numpy()
+                del done
+            else:
+                pending = (host, event)
+            del host
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0].numpy()
 
     def save_renders(self, camera_set, render_image_scale=1.0, output_folder="renders", make_composites: bool = False,
                      save_native_resolution: bool = False, cast_to_uint8: bool = True, save_as_npy: bool = False,

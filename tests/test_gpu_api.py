@@ -159,6 +159,16 @@ def test_render_flat_matches_reference_outputs(scene, golden_render):
         assert cam is cams[0]
         u8 = next(mesh.render_flat_device(cams, out_dtype="uint8")).cpu().numpy()
         np.testing.assert_array_equal(np.squeeze(u8[0]), ora.cast_render_to_uint8(r[key_r][0]))
+        # the pipelined device-to-host path: several views per batch, a ragged last batch, images kept by the
+        # caller (every image owns its host block), and the uint8 extension
+        for bs in (2, len(cams)):
+            kept = list(mesh.render_flat(cams, batch_size=bs, apply_distortion=False))
+            assert len(kept) == len(cams)
+            for k, img in enumerate(kept):
+                _eq(img, r[key_r][k])
+        for k, img in enumerate(mesh.render_flat(cams, batch_size=2, out_dtype="uint8")):
+            assert img.dtype == np.uint8
+            np.testing.assert_array_equal(np.squeeze(img), np.squeeze(ora.cast_render_to_uint8(r[key_r][k])))
     with pytest.raises(TypeError):
         list(mesh.render_flat("cameras"))
 

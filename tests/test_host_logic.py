@@ -199,3 +199,35 @@ def test_gather_rows_host_matches_numpy_indexing():
     np.testing.assert_array_equal(out8[:, 0], np.concatenate([idx[v].reshape(-1)[np.clip(pix[v], 0, 1999)] for v in range(5)]))
     with pytest.raises(ValueError):
         _lib.gather_rows_host(imgs, packed, offs[:-1], out)
+
+
+def test_vote_accumulators_to_csr_equals_the_dense_route():
+    """TexturedPhotogrammetryMeshIndexPredictions builds its CSR results (reference derived_meshes.py:527-550) where the
+    accumulators live (torch ops; CPU tensors here): same data, indices, index pointers and dtypes as csr_array(dense)
+    of the host route, including a face that was observed but recorded no vote."""
+    import torch
+    from scipy.sparse import csr_array
+
+    from geograypher_b200.meshes.derived_meshes import TexturedPhotogrammetryMeshIndexPredictions as Mesh
+
+    rng = np.random.default_rng(0)
+    F, C = 1000, 7
+    counts = rng.integers(0, 4, F).astype(np.int32)
+    summed = np.zeros((F, C))
+    for f in range(F):
+        for _ in range(counts[f]):
+            summed[f, rng.integers(0, C)] += 1
+    counts[5], summed[5] = 3, 0
+    got = Mesh._votes_to_csr(torch.from_numpy(summed), torch.from_numpy(counts))
+    ci, si = counts.astype(np.int64), summed.astype(np.int64)
+    average = np.zeros(si.shape)
+    seen = ci > 0
+    average[seen] = si[seen] * np.reciprocal(ci[seen].astype(float))[:, None]
+    for a, b in zip(got, [csr_array(average), csr_array(ci[:, None]), csr_array(si)]):
+        assert a.shape == b.shape and a.dtype == b.dtype and a.has_canonical_format
+        assert a.indices.dtype == b.indices.dtype and a.indptr.dtype == b.indptr.dtype
+        np.testing.assert_array_equal(a.indptr, b.indptr)
+        np.testing.assert_array_equal(a.indices, b.indices)
+        np.testing.assert_array_equal(a.data, b.data)
+    empty = Mesh._votes_to_csr(torch.zeros((4, 3), dtype=torch.float64), torch.zeros(4, dtype=torch.int32))
+    assert [m.nnz for m in empty] == [0, 0, 0] and empty[1].shape == (4, 1)
