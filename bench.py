@@ -743,12 +743,12 @@ def run_c5(args, torch, dist, _lib, syn, world, rank, local_rank, dev):
     C, F, P, B = cfg.n_classes, len(faces), W * H, 8
     ctx = _lib.Context(local_rank)
     ctx.set_mesh(torch.from_numpy((verts - origin).astype(np.float32)).to(dev), torch.from_numpy(faces).to(dev))
-    del verts
     mine = shard(len(c2ws), rank, world)
     n_views = min(len(mine), 240) // B * B
     ids = mine[:n_views]
     cams = {k: _lib.make_camera(np.linalg.inv(c2ws[k]), cfg.f, cfg.cx, cfg.cy, W, H, origin=origin) for k in ids}
-    preds = [torch.from_numpy(syn.class_index_image(ids[i], H, W, C)).to(dev) for i in range(B)]
+    host_preds = [syn.class_index_image(ids[i], H, W, C) for i in range(B)]
+    preds = [torch.from_numpy(h).to(dev) for h in host_preds]
     d_sum = torch.zeros((F, C), dtype=torch.float64, device=dev)
     d_count = torch.zeros((F,), dtype=torch.int32, device=dev)
     pack = torch.empty((F * (C + 1),), dtype=torch.float64, device=dev) if world > 1 else None
@@ -788,11 +788,58 @@ def run_c5(args, torch, dist, _lib, syn, world, rank, local_rank, dev):
            "workload": f"c5: {F} faces, {cfg.n_cameras} rig cameras {W}x{H} (nadir + 4 obliques per station), uint8 "
                        f"class-index images with 2% ignored pixels, one-hot votes (GG_MODE_VOTE), {B} views per launch",
            "faces_per_view": float(stats[:, 1].mean()), "tile_entries_per_view": float(stats[:, 2].mean()),
-           "faces_observed": int((d_count > 0).sum().item()),
+           "faces_observed": int((d_count > 0).sum().item()), "votes": int(torch.nansum(d_sum).item()),
            "accumulator_bytes": F * C * 8 + F * 4,
            "stage_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1] > 0}}
     ctx.close()
+    del ctx, d_sum, d_count, pack, preds
+    torch.cuda.empty_cache()
+    if world == 1 and "e2e" not in args.skip.split(",") and "e2e_extra" not in args.skip.split(","):
+        out["e2e"] = run_c5_e2e(args, torch, cfg, verts, faces, c2ws, ids, dev, host_preds)
+        same = out["e2e"]["faces_observed"] == out["faces_observed"] and out["e2e"]["votes"] == out["votes"]
+        out["e2e"]["parity_with_resident_leg"] = "ok" if same else "MISMATCH"  # same views, same images
     return out
+
+
+def run_c5_e2e(args, torch, cfg, verts, faces, c2ws, ids, dev, host_preds):
+    """BASELINE config 5 end to end: TexturedPhotogrammetryMeshIndexPredictions.aggregate_projected_images through
+    the reference-facing API -- (H, W) uint8 class-index images in page-locked HOST memory (8 distinct ones), one
+    vote per visible face and view, results returned as the reference's scipy CSR arrays (built on the device; only
+    the CSR arrays cross PCIe).  Timed: the whole call."""
+    import geograypher_b200 as gg
+
+    W, H = cfg.image_size
+    C, B = cfg.n_classes, 8
+    host = []
+    for h in host_preds:  # the images of the device-resident leg, now in page-locked host memory
+        t = torch.empty((H, W), dtype=torch.uint8, pin_memory=True)
+        t.copy_(torch.from_numpy(h))
+        host.append(t.numpy())
+    intr = {0: dict(f=cfg.f, cx=cfg.cx, cy=cfg.cy, image_width=W, image_height=H, distortion_params={})}
+    cams = gg.PhotogrammetryCameraSet(cam_to_world_transforms=[c2ws[k] for k in ids], intrinsic_params_per_sensor_type=intr)
+    seg = gg.SegmentorPhotogrammetryCameraSet(
+        cams, gg.ArraySegmentor([host[i % len(host)] for i in range(len(ids))], num_classes=C))
+    mesh = gg.TexturedPhotogrammetryMeshIndexPredictions((verts, faces), device=dev.index, views_per_batch=B,
+                                                         log_level="WARNING")
+    mesh.aggregate_projected_images(seg.get_subset_cameras(list(range(2 * B))), n_classes=C)  # warm-up (uploads the mesh)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    avg, info = mesh.aggregate_projected_images(seg, n_classes=C)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    counts, summed = info["projection_counts"], info["summed_projections"]
+    d2h = sum(a.data.nbytes + a.indices.nbytes + a.indptr.nbytes for a in (avg, counts, summed))
+    votes = int(summed.sum())
+    del mesh
+    torch.cuda.empty_cache()
+    return {"value": len(ids) / dt, "unit": "views/s", "views": len(ids), "seconds": dt,
+            "h2d_bytes_per_view": votes / max(len(ids), 1) * 32.0, "d2h_bytes": d2h, "faces_observed": int(counts.nnz),
+            "votes": votes, "input": "pinned_index_u8", "distinct_host_images": len(host),
+            "api": "TexturedPhotogrammetryMeshIndexPredictions.aggregate_projected_images(SegmentorPhotogrammetryCameraSet, "
+                   "n_classes) -> scipy.sparse.csr_array results",
+            "note": "class-index images stay in page-locked host memory; the GPU reads one byte (a 32-byte PCIe sector) "
+                    "per visible face and view in place; the CSR results (average, counts, sums) are assembled on the "
+                    "device and copied once"}
 
 
 def run_e2e(args, gg, syn, torch, dist, cfg, verts, faces, c2ws, dev, world, host, kind):
