@@ -1,0 +1,8 @@
+python bench.py > gpurun_out/r8_bench.json 2> gpurun_out/r8_bench.err; tail -c 500 gpurun_out/r8_bench.err
+python - <<'PY'
+import json
+d = json.loads(open('gpurun_out/r8_bench.json').read().strip().splitlines()[-1])
+print('value', d['value'], 'frac', d['roofline']['frac'], 'step', d['roofline']['step_issue']['frac'], 'e2e', d['e2e']['value'])
+print('c4', d['c4']['value'], d['c4']['e2e'].get('value'), d['c4']['e2e'].get('float64', {}).get('value'), d['c4']['e2e'].get('error'))
+print('c5', d['c5']['value'], d['c5']['e2e'].get('value'), d['c5']['e2e'].get('parity_with_resident_leg'), d['c5']['e2e'].get('error'))
+PY
