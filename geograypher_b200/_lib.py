@@ -307,6 +307,47 @@ def label_polygons_weights(xyz, xy, faces, labels, face_weight, rings, n_classes
     return d_w.cpu().numpy()
 
 
+_PREFAULT_POOL = None
+_PREFAULT_THREADS = 8
+_PREFAULT_MIN_BYTES = 16 << 20
+
+
+def to_fresh_host(tensors):
+    """CUDA tensors -> NEW NumPy arrays the caller owns, for results whose size changes from call to call (CSR arrays,
+    rasters): the cost of such a delivery is not the PCIe copy but the first touch of the fresh host pages (measured on
+    the benchmark host for 1 GiB, ``profiles/r02_d2h_dest.txt``: 2.2 GB/s for ``tensor.cpu()``, 4.9 GB/s into a
+    NumPy array -- numpy asks for transparent huge pages --, 2.7 GB/s into a newly page-locked block, 11 GB/s into a
+    NumPy array whose pages a few threads have touched first).  So: allocate with NumPy, pre-fault every large array on
+    a small thread pool (one write per 4-KiB page; the slice writes release the GIL), and copy array k while the
+    pages of the later ones are still being touched.  Accepts one tensor or a list; returns array(s) in the same order."""
+    import torch
+
+    global _PREFAULT_POOL
+    single = not isinstance(tensors, (list, tuple))
+    ts = [tensors] if single else list(tensors)
+    outs, futures = [], []
+    for t in ts:
+        dst = np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
+        flat = dst.reshape(-1)
+        pending = []
+        if dst.nbytes >= _PREFAULT_MIN_BYTES:
+            if _PREFAULT_POOL is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                _PREFAULT_POOL = ThreadPoolExecutor(_PREFAULT_THREADS, thread_name_prefix="gg-prefault")
+            stride = max(1, 4096 // dst.itemsize)
+            step = -(-flat.size // _PREFAULT_THREADS)
+            pending = [_PREFAULT_POOL.submit(flat[lo:lo + step:stride].fill, 0) for lo in range(0, flat.size, step)]
+        outs.append(dst)
+        futures.append(pending)
+    for t, dst, pending in zip(ts, outs, futures):
+        for f in pending:
+            f.result()
+        if dst.size:
+            torch.from_numpy(dst).copy_(t)
+    return outs[0] if single else outs
+
+
 def _stream_ptr(stream):
     if stream is None:
         import torch

@@ -36,8 +36,9 @@ class TexturedPhotogrammetryMeshIndexPredictions(TexturedPhotogrammetryMesh):
         if as_sparse:
             average, info["projection_counts"], info["summed_projections"] = self._votes_to_csr(d_sum, d_count)
             return average, info
-        counts = d_count.cpu().numpy().astype(np.int64)
-        summed = d_sum.cpu().numpy().astype(np.int64)
+        import torch
+
+        counts, summed = _lib.to_fresh_host([d_count.to(torch.int64), d_sum.to(torch.int64)])
         average = np.zeros(summed.shape, dtype=float)
         seen = counts > 0
         average[seen] = summed[seen] * np.reciprocal(counts[seen].astype(float))[:, None]
@@ -70,14 +71,14 @@ class TexturedPhotogrammetryMeshIndexPredictions(TexturedPhotogrammetryMesh):
         count_indptr = torch.zeros(F + 1, dtype=torch.int64, device=d_sum.device)
         torch.cumsum(seen, dim=0, out=count_indptr[1:])
         count_data = d_count[seen].to(torch.int64)
-        h_indptr = indptr.to(index_dtype).cpu().numpy()
-        h_cols = cols.to(index_dtype).cpu().numpy()
-        h_sums = sums.to(torch.int64).cpu().numpy()
-        h_means = means.cpu().numpy()
-        h_count_indptr = count_indptr.to(index_dtype).cpu().numpy()
-        h_count_data = count_data.cpu().numpy()
+        indptr, cols = indptr.to(index_dtype), cols.to(index_dtype)
+        # delivered into fresh, pre-faulted NumPy arrays (_lib.to_fresh_host: the first touch of the host pages, not
+        # PCIe, is what such a delivery costs); the column indices and row pointers cross twice so that the two
+        # (F, C) results share no array
+        (h_indptr, h_cols, h_sums, h_means, h_count_indptr, h_count_data, h_cols2, h_indptr2) = _lib.to_fresh_host(
+            [indptr, cols, sums.to(torch.int64), means, count_indptr.to(index_dtype), count_data, cols, indptr])
         average = csr_array((h_means, h_cols, h_indptr), shape=(F, C))
-        summed = csr_array((h_sums, h_cols.copy(), h_indptr.copy()), shape=(F, C))  # no arrays shared between results
+        summed = csr_array((h_sums, h_cols2, h_indptr2), shape=(F, C))
         counts = csr_array((h_count_data, np.zeros(len(h_count_data), dtype=h_cols.dtype), h_count_indptr), shape=(F, 1))
         return average, counts, summed
 

@@ -423,7 +423,7 @@ class TexturedPhotogrammetryMesh:
         p2f = self.pix2face_device(cameras, mesh=mesh, render_img_scale=render_img_scale, warp_follows=apply_distortion)
         if apply_distortion:
             p2f = self._warp_device(p2f, self._camera_list(cameras), distortion_set, render_img_scale)
-        p2f = p2f.to(dtype=__import__("torch").int64).cpu().numpy()
+        p2f = _lib.to_fresh_host(p2f.to(dtype=__import__("torch").int64))
         return p2f[0] if single else p2f
 
     @staticmethod
@@ -439,7 +439,7 @@ class TexturedPhotogrammetryMesh:
             return torch.stack([
                 distortion_set.warp_dewarp_device(cam, p2f[i], warped_to_ideal=False, fill_value=-1, image_scale=scale)
                 for i, cam in enumerate(cam_list)])
-        host = p2f.to(torch.int64).cpu().numpy()
+        host = _lib.to_fresh_host(p2f.to(torch.int64))
         out = np.stack([
             distortion_set.warp_dewarp_image(camera=cam, input_image=host[i], warped_to_ideal=False, fill_value=-1,
                                              interpolation_order=0, image_scale=scale)
@@ -543,7 +543,7 @@ class TexturedPhotogrammetryMesh:
                 p2f = self._pix2face_for_aggregation(cam, mesh, aggregate_img_scale, pix2face_kwargs)
                 mesh.context.aggregate(p2f[0], torch.from_numpy(arr).to(dev), kind, C, _lib.MODE_LAST_PIXEL,
                                        self._flags(_lib.FLAG_ASSIGN), d_sum, d_count)
-            yield d_sum.cpu().numpy()
+            yield _lib.to_fresh_host(d_sum)
 
     def _pix2face_for_aggregation(self, cameras, mesh, scale, pix2face_kwargs):
         """Device raster for one camera / camera batch, honouring a requested distortion warp."""

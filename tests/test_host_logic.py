@@ -231,3 +231,21 @@ def test_vote_accumulators_to_csr_equals_the_dense_route():
         np.testing.assert_array_equal(a.data, b.data)
     empty = Mesh._votes_to_csr(torch.zeros((4, 3), dtype=torch.float64), torch.zeros(4, dtype=torch.int32))
     assert [m.nnz for m in empty] == [0, 0, 0] and empty[1].shape == (4, 1)
+
+
+def test_to_fresh_host_delivers_owned_arrays():
+    """_lib.to_fresh_host: tensors -> new NumPy arrays (pre-faulted when large), any shape / dtype / layout."""
+    import torch
+
+    from geograypher_b200 import _lib
+
+    a = torch.arange(6_000_000, dtype=torch.float64).reshape(1000, 6000)  # large enough to be pre-faulted
+    b = torch.arange(7, dtype=torch.int32)
+    c = torch.zeros((0, 3), dtype=torch.uint8)
+    d = torch.arange(12, dtype=torch.int64).reshape(3, 4).t()  # not contiguous
+    ra, rb, rc, rd = _lib.to_fresh_host([a, b, c, d])
+    for got, want in zip((ra, rb, rc, rd), (a, b, c, d)):
+        assert isinstance(got, np.ndarray) and got.flags.owndata and got.flags.c_contiguous
+        assert got.dtype == want.numpy().dtype and got.shape == tuple(want.shape)
+        np.testing.assert_array_equal(got, want.numpy())
+    assert isinstance(_lib.to_fresh_host(b), np.ndarray)
