@@ -147,6 +147,8 @@ class PhotogrammetryCamera:
 
 
 class PhotogrammetryCameraSet:
+    reads_image_files = True  # get_image_by_index decodes a file per view: the aggregation may read views ahead
+
     def __init__(
         self,
         cameras: Union[None, PhotogrammetryCamera, List[PhotogrammetryCamera]] = None,

@@ -32,6 +32,7 @@ from geograypher_b200.constants import (
     NULL_TEXTURE_INT_VALUE,
     PATH_TYPE,
 )
+from geograypher_b200.utils import prefetch as _prefetch
 from geograypher_b200.utils.indexing import determine_IDs_to_labels
 
 
@@ -98,6 +99,7 @@ class TexturedPhotogrammetryMesh:
         views_per_batch: int = 8,
         use_principal_point: bool = True,
         sparse_host_gather: bool = True,
+        prefetch_threads: typing.Union[int, None] = None,
     ):
         """A mesh with per-vertex / per-face textures that can be rendered into, and painted from, posed cameras.
 
@@ -125,6 +127,10 @@ class TexturedPhotogrammetryMesh:
                 scattered PCIe reads from page-locked memory slow down with its footprint on some hosts (2.5x on
                 the benchmark host at 6 GB), where the host-gather route is then the faster one.
                 ``host_array`` memory keeps its rate and is always read in place.
+            prefetch_threads (*new*): workers that read the prediction images of the coming views ahead of the
+                aggregation.  None (default): on for predictions decoded from files (``LookUpSegmentor``, any segmentor
+                with ``io_bound = True``), off otherwise; 0 disables; a number forces it (the segmentor must then be
+                thread-safe).
         """
         if downsample_target != 1.0 or ROI is not None:
             raise NotImplementedError(
@@ -141,6 +147,7 @@ class TexturedPhotogrammetryMesh:
         self.views_per_batch = int(max(1, min(views_per_batch, _lib.MAX_VIEWS_PER_CALL)))
         self.use_principal_point = bool(use_principal_point)
         self.sparse_host_gather = bool(sparse_host_gather)
+        self.prefetch_threads = None if prefetch_threads is None else int(prefetch_threads)
         self.pinned_direct_limit_bytes = int(os.environ.get("GG_PINNED_DIRECT_LIMIT", 4 << 30))
         self._context = None
         self._local_cache = None
@@ -706,13 +713,13 @@ class TexturedPhotogrammetryMesh:
             in_flight = []
             pending = None  # a batch of pageable images whose rows the host has yet to pick
             pinned_seen = {}
+            fetch = self._prediction_fetcher(cameras, n, aggregate_img_scale, image_getter, index_getter)
             try:
                 for bi, s in enumerate(range(0, n, B)):
                     batch = cam_list[s : s + B]
                     preds, kind = [], None
                     for k in range(s, s + len(batch)):
-                        arr, this_kind, this_C = self._fetch_prediction(cameras, k, aggregate_img_scale, image_getter,
-                                                                        index_getter)
+                        arr, this_kind, this_C = fetch(k)
                         if mode == _lib.MODE_VOTE:
                             this_C = n_channels
                         if C is None:
@@ -782,7 +789,31 @@ class TexturedPhotogrammetryMesh:
                 # streams: they must finish before those tensors go back to torch's allocator
                 self._quiesce(ctx)
                 raise
+            finally:
+                close = getattr(fetch, "close", None)
+                if close is not None:
+                    close()
         return d_sum, d_count, C
+
+    def _prediction_fetcher(self, cameras, n, scale, image_getter, index_getter):
+        """``fetch(k) -> (array, pred_kind, C)`` for the views in order.  Predictions that are DECODED per view (a
+        segmentor that declares ``io_bound = True`` such as LookUpSegmentor, or a plain camera set reading image files)
+        are read ahead on ``self.prefetch_threads`` workers (utils/prefetch.py): a serial 20-Mpx PNG decode takes a
+        thousand times longer than the GPU needs for the view.  In-memory predictions (ArraySegmentor, an
+        ``image_getter``) and segmentors that say nothing (they may run a network and need not be thread-safe) are
+        fetched inline."""
+        def one(k):
+            return self._fetch_prediction(cameras, k, scale, image_getter, index_getter)
+
+        threads = getattr(self, "prefetch_threads", None)
+        if threads is None:  # auto
+            segmentor = getattr(cameras, "segmentor", None)
+            io_bound = (getattr(segmentor, "io_bound", False) if segmentor is not None
+                        else getattr(cameras, "reads_image_files", False))
+            threads = _prefetch.default_threads() if (io_bound and image_getter is None and n > 1) else 0
+        if threads <= 0:
+            return one
+        return _prefetch.OrderedPrefetcher(one, n, threads=threads, size_of=lambda item: item[0].nbytes)
 
     @staticmethod
     def _quiesce(ctx):

@@ -30,6 +30,8 @@ def _nearest_resize(image: np.ndarray, shape) -> np.ndarray:
 class LookUpSegmentor(Segmentor):
     """Class-index PNGs stored next to the images (derived_segmentors.py:32-51)."""
 
+    io_bound = True  # every call decodes a file: the aggregation reads the coming views ahead on a thread pool
+
     def __init__(self, base_folder, lookup_folder, num_classes=10):
         super().__init__(num_classes=num_classes)
         self.base_folder = Path(base_folder)

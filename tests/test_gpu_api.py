@@ -110,6 +110,34 @@ def test_aggregate_matches_reference_outputs(scene, golden_aggregate, sparse):
     _eq(avg[:-1], a["avg2"][:-1]); _eq(info["projection_counts"][:-1], a["counts2"][:-1])
 
 
+def test_lookup_segmentor_reads_ahead_and_matches_reference_outputs(scene, golden_aggregate, tmp_path):
+    """Class-index images decoded from files (LookUpSegmentor, reference derived_segmentors.py:38-51): the coming views
+    are read ahead on a thread pool; same numbers as the in-memory route, with and without read-ahead."""
+    from geograypher_b200.utils.prefetch import OrderedPrefetcher
+
+    g, _ = scene
+    a = golden_aggregate
+    C = a["avg1"].shape[1]
+    f, cx, cy, W, H = g["intrinsics"]
+    folder = tmp_path / "images"
+    cams = gg.PhotogrammetryCameraSet(
+        cameras=[gg.PhotogrammetryCamera(folder / f"flight/{i:04d}.JPG", T, f, cx, cy, int(W), int(H))
+                 for i, T in enumerate(g["c2ws"])], image_folder=folder)
+    (tmp_path / "preds" / "flight").mkdir(parents=True)
+    for i, img in enumerate(a["idx_imgs"]):
+        np.save(tmp_path / "preds" / "flight" / f"{i:04d}.npy", np.asarray(img, dtype=np.uint8))
+    seg = gg.SegmentorPhotogrammetryCameraSet(cams, gg.LookUpSegmentor(folder, tmp_path / "preds", num_classes=C))
+    for threads in (None, 0, 3):
+        mesh = gg.TexturedPhotogrammetryMesh((g["verts"], g["faces"]), compat_negative_index=True, views_per_batch=2,
+                                             prefetch_threads=threads)
+        used = []
+        orig = mesh._prediction_fetcher
+        mesh._prediction_fetcher = lambda *args: (used.append(orig(*args)), used[-1])[1]
+        avg, info = mesh.aggregate_projected_images(seg)
+        assert isinstance(used[0], OrderedPrefetcher) == (threads != 0)
+        _eq(avg, a["avg1"]); _eq(info["projection_counts"], a["counts1"]); _eq(info["summed_projections"], a["summed1"])
+
+
 def test_pageable_route_redoes_a_batch_whose_lists_were_cut(scene, golden_aggregate):
     """The pageable-image route sizes the (face, pixel) lists after the previous batch (GG_FLAG_TRUNCATE): a batch
     that needs more room is listed again at full size -- same numbers, and no overflow is reported."""
