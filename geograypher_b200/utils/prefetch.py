@@ -68,4 +68,5 @@ class OrderedPrefetcher:
 
 
 def default_threads() -> int:
-    return max(1, min(8, (os.cpu_count() or 2) - 1))
+    """Decoding scales with the cores until the memory system saturates; one core stays with the aggregation loop."""
+    return max(1, min(16, (os.cpu_count() or 2) - 1))
