@@ -376,6 +376,11 @@ int gg_create(int device, gg_context **out) {
     ctx->sm_count = prop.multiProcessorCount;
     memset(ctx->vset, 0, sizeof(ctx->vset));
     if (const char *e = getenv("GG_DENSE_PREFETCH")) ctx->dense_prefetch = atoi(e) != 0;
+    if (const char *e = getenv("GG_LANE_LISTS")) {
+        ctx->lane_lists = atoi(e) != 0;
+        ctx->lane_lists_auto = 0;
+    }
+    if (const char *e = getenv("GG_LANE_LISTS_MIN_ENTRIES")) ctx->lane_lists_min_entries = (float)atof(e);
     if (const char *e = getenv("GG_STAGE_HOST_ROWS")) ctx->stage_host_rows = atoi(e) != 0;
     if (const char *e = getenv("GG_SETUP_CTAS")) ctx->setup_ctas = atoi(e);
     if (const char *e = getenv("GG_FILL_CTAS")) ctx->fill_ctas = atoi(e);
@@ -444,6 +449,9 @@ int gg_sync(gg_context *ctx, void *stream) {
     int32_t st4[4] = {0, 0, 0, 0};
     GG_CUDA(cudaMemcpy(st4, ctx->d_sticky, sizeof(st4), cudaMemcpyDeviceToHost));
     if (st4[1] != 0 || st4[2] != 0 || st4[0] != 0) GG_CUDA(cudaMemset(ctx->d_sticky, 0, 4 * sizeof(int32_t)));
+    // st4[2]: the most tile entries any view needed since the last gg_sync -> which rasterizer variant comes next
+    if (ctx->lane_lists_auto && st4[2] > 0 && ctx->last_n_tiles > 0)
+        ctx->lane_lists = (double)st4[2] >= (double)ctx->lane_lists_min_entries * (double)ctx->last_n_tiles;
     const int32_t sticky = st4[0];
     if (sticky != 0) {
         ctx->last_overflow[0] = sticky;

@@ -124,6 +124,14 @@ struct gg_context {
     float4 *d_verts = nullptr;   // [V] xyz + pad
     int4 *d_faces = nullptr;     // [F] i0,i1,i2,face_id
     int dense_prefetch = 1;      // GG_MODE_PIXEL_SUM: L2 prefetch of the score tiles (GG_DENSE_PREFETCH=0 turns it off)
+    // Rasterizer variant whose lanes walk their own face lists (k_raster_tiles<..., LL = true>).  It pays off when tile
+    // lists are long (c5, 10.5 faces per tile: +9 %) and costs on short ones (c2, 4.3 per tile: -6 %), so by default
+    // gg_sync picks it from the longest view of the batches it has just waited for (tile entries per tile >=
+    // lane_lists_min_entries).  GG_LANE_LISTS=0 / 1 pins it off / on.
+    int lane_lists = 0;
+    int lane_lists_auto = 1;
+    float lane_lists_min_entries = 7.0f;
+    int64_t last_n_tiles = 0;    // tiles per view of the most recent rasterization
     float *d_block_lo = nullptr; // [n_blocks*3]
     float *d_block_hi = nullptr; // [n_blocks*3]
     int64_t n_blocks = 0;

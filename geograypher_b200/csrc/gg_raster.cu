@@ -738,7 +738,11 @@ __device__ __forceinline__ float dense_load(const T *__restrict__ pred, int64_t 
     return v == v ? v : 0.f;  // NaN = null -> contributes nothing
 }
 
-template <int MODE, typename T, int CT>
+// LL ("lane lists", not in the dense mode): instead of the whole warp stepping through the tile's list face by face --
+// every face costs the full per-pixel block however few lanes it touches -- every lane first collects the faces whose
+// lane mask holds ITS strip (one bit per face of the chunk) and then walks its own list: the warp runs
+// max-over-lanes iterations, lanes work on different faces in the same iteration (lane-private shared-memory reads).
+template <int MODE, typename T, int CT, bool LL = false>
 __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DENSE_MIN_BLOCKS : GG_RASTER_MIN_BLOCKS) k_raster_tiles(const __grid_constant__ GGCamBatch cams,
                                                                        const __grid_constant__ GGViewBatch views,
                                                                        int n_tiles, int32_t *__restrict__ pix2face,
@@ -858,6 +862,61 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
             }
         }
         __syncwarp();
+        if (LL) {
+            static_assert(!LL || !NEED_POS, "lane lists carry no list position");
+            unsigned mine = 0;  // bit k: face k of this chunk may touch this lane's strip
+            {
+                unsigned ma = s_faces_addr + 48;
+                for (int k = 0; k < n; ++k, ma += 64) {
+                    unsigned lm;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lm) : "r"(ma));
+                    mine |= ((lm >> lane) & 1u) << k;
+                }
+            }
+            while (__any_sync(0xffffffffu, mine != 0u)) {
+                const bool act = mine != 0u;
+                const unsigned kk = act ? (unsigned)(__ffs((int)mine) - 1) : 0u;
+                mine &= mine - 1u;  // (0 stays 0)
+                const unsigned fa = s_faces_addr + kk * 64u;
+                const int4 q3 = lds128(fa + 48);  // lanemask face rec fast
+                const unsigned nface = ~(unsigned)q3.y;
+                if (q3.w) {
+                    const int4 q0 = lds128(fa);       // e0 e1 e2 sx0
+                    const int4 q1 = lds128(fa + 16);  // sx1 sx2 sy0 sy1
+                    const int4 q2 = lds128(fa + 32);  // sy2 w_org gx gy
+                    const int s0 = q0.w, s1 = q1.x, s2 = q1.y;
+                    int e0 = q0.x + s0 * tx0 + q1.z * ty;
+                    int e1 = q0.y + s1 * tx0 + q1.w * ty;
+                    int e2 = q0.z + s2 * tx0 + q2.x * ty;
+                    e0 = act ? e0 : -1;  // a lane whose list has run out covers nothing
+                    const int s0m = act ? s0 : 0;
+                    const float gx = __int_as_float(q2.z);
+                    const float wrow = fmaf(gx, ftx0, fmaf(__int_as_float(q2.w), fty, __int_as_float(q2.y)));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float w = fmaf(gx, (float)i, wrow);
+                        const double cand = __hiloint2double(__float_as_int(w), (int)nface);
+                        asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %0;\n\tsetp.ge.and.s32 p, %2, 0, p;\n\t"
+                            "selp.f64 %0, %1, %0, p;\n\t}"
+                            : "+d"(key[i])
+                            : "d"(cand), "r"(e0 | e1 | e2));
+                        e0 += s0m;
+                        e1 += s1;
+                        e2 += s2;
+                    }
+                } else if (act) {
+                    const GGFaceRec &r = vs.recs[q3.z];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float w;
+                        if (exact_cover(r, tile_x0 + tx0 + i, tile_y0 + ty, w) && w > 0.f) {
+                            const double cand = __hiloint2double(__float_as_int(w), (int)nface);
+                            if (cand > key[i]) key[i] = cand;
+                        }
+                    }
+                }
+            }
+        } else {
         unsigned fa = s_faces_addr;  // shared-memory address of setup k: one register, bumped by 64 per face
         for (int k = 0; k < n; ++k, fa += 64) {
             const int4 q3 = lds128(fa + 48);  // lanemask face rec fast
@@ -909,6 +968,7 @@ __global__ void __launch_bounds__(GG_RASTER_THREADS, MODE == GG_RM_DENSE ? GG_DE
                 }
             }
         }
+        }  // !LL
         __syncwarp();
     }
 
@@ -1364,6 +1424,7 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
     for (int i = 0; i < n; ++i) cb.cam[i] = cams[i];
     const int tiles_x = (W + GG_TILE_W - 1) / GG_TILE_W, tiles_y = (H + GG_TILE_H - 1) / GG_TILE_H;
     const int n_tiles = tiles_x * tiles_y;
+    ctx->last_n_tiles = n_tiles;
     ctx->last_batch_n = n;
     if (want_winners) {
         if (ctx->wdense_cap < (int64_t)n * ctx->F) {
@@ -1439,34 +1500,38 @@ int gg_launch_rasterize(gg_context *ctx, const gg_camera *cams, int n, int32_t *
         da.tex = d_tex;
         da.out = d_out;
         da.D = D;
+        // (GG_LANE_LISTS picks the kernel variant whose lanes walk their own face lists; see k_raster_tiles)
+#define GG_RASTER_LAUNCH(MODE_, T_, ...)                                                                               \
+    do {                                                                                                                \
+        if (ctx->lane_lists)                                                                                            \
+            GG_LAUNCH(ctx, GG_ST_RASTER, st,                                                                            \
+                      (k_raster_tiles<MODE_, T_, 0, true><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(__VA_ARGS__)));          \
+        else                                                                                                            \
+            GG_LAUNCH(ctx, GG_ST_RASTER, st,                                                                            \
+                      (k_raster_tiles<MODE_, T_, 0, false><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(__VA_ARGS__)));         \
+    } while (0)
         switch (out_dtype) {
             case GG_OUT_F64:
-                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, double, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(
-                                                     cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da)));
+                GG_RASTER_LAUNCH(GG_RM_GATHER, double, cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da);
                 break;
             case GG_OUT_F32:
-                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, float, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(
-                                                     cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da)));
+                GG_RASTER_LAUNCH(GG_RM_GATHER, float, cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da);
                 break;
             case GG_OUT_U8:
-                GG_LAUNCH(ctx, GG_ST_RASTER, st, (k_raster_tiles<GG_RM_GATHER, uint8_t, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(
-                                                     cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da)));
+                GG_RASTER_LAUNCH(GG_RM_GATHER, uint8_t, cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, nullptr, 0, da);
                 break;
             default: gg_set_error("bad out_dtype"); return GG_ERR_INVALID;
         }
         return GG_OK;
     }
     if (want_winners && !d_pix2face && !d_depth)  // the fused aggregation: no raster leaves the SM
-        GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  (k_raster_tiles<GG_RM_WINNERS_ONLY, float, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(
-                      cb, ctx->vset[ctx->cur], n_tiles, nullptr, nullptr, compat_bg ? (int)ctx->F : 0, da)));
+        GG_RASTER_LAUNCH(GG_RM_WINNERS_ONLY, float, cb, ctx->vset[ctx->cur], n_tiles, nullptr, nullptr,
+                         compat_bg ? (int)ctx->F : 0, da);
     else if (want_winners)
-        GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  (k_raster_tiles<GG_RM_WINNERS, float, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(
-                      cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, d_depth, compat_bg ? (int)ctx->F : 0, da)));
+        GG_RASTER_LAUNCH(GG_RM_WINNERS, float, cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, d_depth,
+                         compat_bg ? (int)ctx->F : 0, da);
     else
-        GG_LAUNCH(ctx, GG_ST_RASTER, st,
-                  (k_raster_tiles<GG_RM_PLAIN, float, 0><<<rgrid_t, GG_RASTER_THREADS, 0, st>>>(cb, ctx->vset[ctx->cur], n_tiles,
-                                                                                          d_pix2face, d_depth, 0, da)));
+        GG_RASTER_LAUNCH(GG_RM_PLAIN, float, cb, ctx->vset[ctx->cur], n_tiles, d_pix2face, d_depth, 0, da);
+#undef GG_RASTER_LAUNCH
     return GG_OK;
 }
